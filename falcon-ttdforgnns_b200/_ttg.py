@@ -1,0 +1,161 @@
+"""ctypes binding of libttg_b200.so (include/ttg_b200.h) + the small amount of host logic the
+ops share: shape structs, the per-device workspace, error translation.
+
+PyTorch is used for device memory and streams only; every computation is a call through the
+C ABI.  There is no CPU or eager fallback: if the library is missing, lib() raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libttg_b200.so")
+_lib = None
+
+TTG_MAX_CORES = 4
+OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
+FLAG_FORCE_GENERIC, FLAG_PLAN_VALID = 1, 2
+
+
+class Shape(C.Structure):
+    _fields_ = [("T", C.c_int32), ("num_tables", C.c_int32), ("p", C.c_int32 * TTG_MAX_CORES),
+                ("q", C.c_int32 * TTG_MAX_CORES), ("r", C.c_int32 * (TTG_MAX_CORES + 1))]
+
+
+_vp, _i64, _i32, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.c_size_t
+_SP = C.POINTER(Shape)
+
+# name -> (restype, argtypes); exactly the entry points include/ttg_b200.h declares
+SIGNATURES = {
+    "ttg_last_error": (C.c_char_p, []),
+    "ttg_version": (C.c_int, []),
+    "ttg_launch_count": (_i64, []),
+    "ttg_profile_enable": (C.c_int, [_i32]),
+    "ttg_profile_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ttg_profile_name": (C.c_char_p, [_i32]),
+    "ttg_apply_optimizer": (C.c_int, [_SP, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "ttg_tt_workspace_bytes": (_sz, [_SP, _i64, _i64]),
+    "ttg_tt_forward": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "ttg_tt_backward": (C.c_int, [_SP, _i32, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _sz, _i32, _vp]),
+    "ttg_update_cache_state": (C.c_int, [_i64, _vp, _i64, _vp, _vp, _vp]),
+    "ttg_cache_populate_workspace_bytes": (_sz, [_SP, _i64, _i64]),
+    "ttg_cache_populate": (C.c_int, [_SP, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "ttg_preprocess_workspace_bytes": (_sz, [_i64]),
+    "ttg_preprocess_indices": (C.c_int, [_i64, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp, C.POINTER(C.c_int32), _vp, _sz, _vp]),
+    "ttg_cache_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ttg_cache_backward_sgd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f32, _vp, _vp]),
+    "ttg_cache_backward_dense": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "ttg_cache_backward_rowwise_adagrad_approx": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f32, _f32,
+                                                            _vp, _vp, _vp]),
+    "ttg_eff_workspace_bytes": (_sz, [_SP, _i64]),
+    "ttg_eff_forward": (C.c_int, [_SP, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ttg_eff_backward_sgd": (C.c_int, [_SP, _i64, _f32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "ttg_spmm_csr_fwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "ttg_spmm_csr_bwd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
+}
+
+
+def lib():
+    """Load the CUDA library; fail loudly if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "ttg_b200: %s is missing -- build it with `python falcon-ttdforgnns_b200/build.py` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().ttg_last_error()
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables=1):
+    T = len(tt_p_shapes)
+    ranks = [int(x) for x in tt_ranks]
+    if len(ranks) == T - 1:
+        ranks = [1] + ranks + [1]
+    if not (2 <= T <= TTG_MAX_CORES and len(tt_q_shapes) == T and len(ranks) == T + 1):
+        raise RuntimeError("ttg_b200: need 2..4 cores with len(p) == len(q) == len(ranks) - 1")
+    s = Shape()
+    s.T = T
+    s.num_tables = int(num_tables)
+    for t in range(T):
+        s.p[t] = int(tt_p_shapes[t])
+        s.q[t] = int(tt_q_shapes[t])
+    for t in range(T + 1):
+        s.r[t] = ranks[t]
+    return s
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (kept alive by the caller holding the return value)."""
+    arr = (C.c_void_p * TTG_MAX_CORES)()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def stream_of(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("ttg_b200: %s must be a CUDA tensor (no CPU path exists)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError("ttg_b200: %s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise RuntimeError("ttg_b200: %s must be contiguous" % name)
+    return t
+
+
+class _Workspace:
+    """One growable scratch buffer per device.  `plan_key` remembers which (indices, shape)
+    the sorted plan inside currently belongs to, so a backward that follows its forward skips
+    the sort (TTG_FLAG_PLAN_VALID)."""
+
+    def __init__(self):
+        self.buf = {}
+        self.plan_key = {}
+        self.keep = {}   # tensors the plan was built from: kept alive so their addresses
+                         # cannot be recycled while the key is still trusted
+
+    def get(self, device, nbytes):
+        key = (device.type, device.index)
+        b = self.buf.get(key)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+            self.buf[key] = b
+            self.plan_key[key] = None
+        return b
+
+    def plan(self, device):
+        return self.plan_key.get((device.type, device.index))
+
+    def set_plan(self, device, key, keep=None):
+        self.plan_key[(device.type, device.index)] = key
+        self.keep[(device.type, device.index)] = keep
+
+
+workspace = _Workspace()
+
+
+def plan_key_of(tag, indices, rowidx, nnz, B, shape_tuple):
+    return (tag, indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version,
+            int(nnz), int(B), shape_tuple)

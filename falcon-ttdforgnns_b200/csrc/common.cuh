@@ -1,0 +1,121 @@
+// common.cuh -- shared helpers for the ttg_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ttg_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "ttg_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace ttg {
+
+constexpr int kWarp = 32;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+// ---- error plumbing (host) ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define TTG_CHECK_ARG(cond, ...)  \
+  do {                            \
+    if (!(cond)) {                \
+      ttg::set_error(__VA_ARGS__); \
+      return TTG_EINVAL;          \
+    }                             \
+  } while (0)
+
+#define TTG_CUDA(expr)                                                              \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ttg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                  \
+                     cudaGetErrorString(_e));                                       \
+      return TTG_ECUDA;                                                             \
+    }                                                                               \
+  } while (0)
+
+#define TTG_LAUNCH_CHECK()                                                          \
+  do {                                                                              \
+    ttg::count_launch();                                                            \
+    cudaError_t _e = cudaGetLastError();                                            \
+    if (_e != cudaSuccess) {                                                        \
+      ttg::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__,              \
+                     cudaGetErrorString(_e));                                       \
+      return TTG_ECUDA;                                                             \
+    }                                                                               \
+  } while (0)
+
+// ---- optional per-kernel timing (CUDA events on the launching stream), api.cu ------------
+enum KernelId {
+  K_PLAN = 0, K_SORT, K_ZERO_ROWS, K_FWD, K_BWD_ROWS, K_BWD_CORES, K_REDUCE, K_OPTIM,
+  K_GENERIC_FWD, K_GENERIC_BWD, K_COUNT
+};
+void prof_begin(int id, cudaStream_t s);
+void prof_end(int id, cudaStream_t s);
+
+// ---- device-side view of a TT table (passed by value as a kernel parameter) ---------
+struct TTDev {
+  int32_t T;
+  int32_t num_tables;
+  int32_t D;                         // prod(q)
+  int32_t p[TTG_MAX_CORES];
+  int32_t q[TTG_MAX_CORES];
+  int32_t r[TTG_MAX_CORES + 1];
+  int32_t cols[TTG_MAX_CORES];       // r[t]*q[t]*r[t+1]
+  int64_t L[TTG_MAX_CORES];          // prod(p[t+1:])
+  int64_t num_rows;                  // prod(p)
+  float* core[TTG_MAX_CORES];        // device pointers [num_tables][p[t]][cols[t]]
+};
+
+// Validates `shape` and fills `dev` (host). Returns TTG_OK / TTG_EINVAL.
+int make_ttdev(const ttg_shape* shape, const float* const* host_core_ptrs, TTDev* dev);
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device helpers ------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  // REDG.E.ADD.F32x4 : one 16-byte reduction instead of four scalar atomics
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_cs_v4(float* p, float4 v) {
+  // streaming store: written once, not re-read by this kernel
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// ---- internal entry points shared between translation units --------------------------
+// generic (any T) kernels, tt_generic.cu
+int generic_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
+                    const int64_t* rowidx, const int64_t* tableidx, float* output,
+                    cudaStream_t stream);
+int generic_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
+                     const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
+                     float* const* dcore, cudaStream_t stream);
+// optimizer over whole cores, tt_generic.cu
+int apply_optimizer(const TTDev& tt, int32_t optim, float lr, float eps, float* const* dcore,
+                    float* const* state, cudaStream_t stream);
+
+// sorted prefix-reuse kernels for T == 3, tt_sorted.cu
+bool sorted_supported(const TTDev& tt);
+size_t sorted_workspace_bytes(const TTDev& tt, int64_t B, int64_t nnz);
+int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
+                   const int64_t* rowidx, const int64_t* tableidx, float* output, void* ws,
+                   size_t ws_bytes, bool plan_valid, cudaStream_t stream);
+int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
+                    const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
+                    float* const* dcore, void* ws, size_t ws_bytes, bool plan_valid,
+                    cudaStream_t stream);
+
+}  // namespace ttg

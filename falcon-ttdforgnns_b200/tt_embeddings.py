@@ -1,0 +1,317 @@
+"""Drop-in for the reference's compiled extension module `tt_embeddings`.
+
+Same 11 function names, argument orders and return types as the pybind module registered at
+FBTT/tt_embeddings.cpp:131-161 (signatures :13-129), so `import tt_embeddings` inside
+FBTT/tt_embeddings_ops.py (and anything else that calls the raw ops) keeps working when this
+directory is first on sys.path.  Each function validates its tensors, allocates outputs with
+torch and forwards raw device pointers to the C ABI (include/ttg_b200.h) on torch's current
+stream.  Errors surface as RuntimeError, like TORCH_CHECK in the reference.
+
+`batch_count` is accepted and ignored: in the reference it only sizes the scratch of the chunk
+loop (FBTT/tt_embeddings_cuda.cu:1015-1027); here one launch covers the whole batch.
+"""
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+
+import _ttg
+
+__all__ = [
+    "tt_forward", "tt_dense_backward", "tt_sgd_backward", "tt_adagrad_backward",
+    "update_cache_state", "cache_populate", "preprocess_indices_sync", "cache_forward",
+    "cache_backward_sgd", "cache_backward_dense", "cache_backward_rowwise_adagrad_approx",
+]
+
+_scratch = _ttg._Workspace()  # everything that is not the sorted TT plan
+
+# test / debugging knob: OR-ed into the flags of tt_forward / tt_*_backward
+# (_ttg.FLAG_FORCE_GENERIC selects the shape-generic kernels)
+EXTRA_FLAGS = 0
+
+
+def _cores_ok(tt_cores, T):
+    if len(tt_cores) != T:
+        raise RuntimeError("tt_embeddings: expected %d tt_cores, got %d" % (T, len(tt_cores)))
+    cores = []
+    for i, c in enumerate(tt_cores):
+        c = c.data if isinstance(c, torch.nn.Parameter) else c
+        cores.append(_ttg.require_cuda(c, "tt_cores[%d]" % i, torch.float32))
+    return cores
+
+
+def _shape_tuple(p, q, r, num_tables):
+    return (tuple(int(x) for x in p), tuple(int(x) for x in q), tuple(int(x) for x in r),
+            int(num_tables))
+
+
+def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: List[int],
+               tt_q_shapes: List[int], tt_ranks: List[int], L: torch.Tensor, nnz: int,
+               indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor,
+               tt_cores: List[torch.Tensor]) -> torch.Tensor:
+    """tt_embeddings_forward_cuda (FBTT/tt_embeddings_cuda.cu:967-1081)."""
+    cores = _cores_ok(tt_cores, len(tt_p_shapes))
+    dev = cores[0].device
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
+    if cores[0].size(0) != num_tables:
+        raise RuntimeError("tt_forward: num_tables does not match tt_cores[0].size(0)")
+    with torch.cuda.device(dev):
+        output = torch.empty((num_tables, B, D), dtype=torch.float32, device=dev)
+        nnz = int(nnz)
+        if nnz > 0:
+            _ttg.require_cuda(indices, "indices", torch.int64)
+            _ttg.require_cuda(rowidx, "rowidx", torch.int64)
+            _ttg.require_cuda(tableidx, "tableidx", torch.int64)
+            if min(indices.numel(), rowidx.numel(), tableidx.numel()) < nnz:
+                raise RuntimeError("tt_forward: nnz exceeds the index arrays")
+        lib = _ttg.lib()
+        nbytes = lib.ttg_tt_workspace_bytes(C.byref(shape), B, nnz)
+        ws = _ttg.workspace.get(dev, nbytes)
+        cp = _ttg.ptr_array(cores)
+        rc = lib.ttg_tt_forward(C.byref(shape), B, nnz, _ttg.ptr(indices), _ttg.ptr(rowidx),
+                                _ttg.ptr(tableidx), cp, _ttg.ptr(output), _ttg.ptr(ws),
+                                ws.numel(), EXTRA_FLAGS, _ttg.stream_of(dev))
+        _ttg.check(rc, "tt_forward")
+        if nnz > 0:
+            _ttg.workspace.set_plan(dev, _ttg.plan_key_of(
+                "tt", indices, rowidx, nnz, B,
+                _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)),
+                keep=(indices, rowidx))
+    return output
+
+
+def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
+              tableidx, d_output, optimizer_state, tt_cores):
+    cores = _cores_ok(tt_cores, len(tt_p_shapes))
+    dev = cores[0].device
+    num_tables = cores[0].size(0)
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
+    with torch.cuda.device(dev):
+        if not isinstance(d_output, torch.Tensor) or not d_output.is_cuda:
+            raise RuntimeError("tt_backward: d_output must be a CUDA tensor")
+        d_output = d_output.to(torch.float32).contiguous()
+        if d_output.dim() != 3 or d_output.size(0) != num_tables or d_output.size(2) != D:
+            raise RuntimeError("tt_backward: d_output must be [num_tables, B, D]")
+        B = d_output.size(1)
+        nnz = int(nnz)
+        d_cores = [torch.empty_like(c) for c in cores]
+        if nnz > 0:
+            _ttg.require_cuda(indices, "indices", torch.int64)
+            _ttg.require_cuda(rowidx, "rowidx", torch.int64)
+            _ttg.require_cuda(tableidx, "tableidx", torch.int64)
+        states = None
+        sp = None
+        if optim == _ttg.OPTIM_ADAGRAD:
+            states = [_ttg.require_cuda(s, "optimizer_state", torch.float32)
+                      for s in optimizer_state]
+            for s, c in zip(states, cores):
+                if s.shape != c.shape:
+                    raise RuntimeError("tt_adagrad_backward: optimizer_state shape mismatch")
+            sp = _ttg.ptr_array(states)
+        lib = _ttg.lib()
+        nbytes = lib.ttg_tt_workspace_bytes(C.byref(shape), B, nnz)
+        ws = _ttg.workspace.get(dev, nbytes)
+        flags = 0
+        key = None
+        if nnz > 0:
+            key = _ttg.plan_key_of("tt", indices, rowidx, nnz, B,
+                                   _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables))
+            if _ttg.workspace.plan(dev) == key:
+                flags |= _ttg.FLAG_PLAN_VALID  # the forward's sort is still in the workspace
+        cp = _ttg.ptr_array(cores)
+        dp = _ttg.ptr_array(d_cores)
+        rc = lib.ttg_tt_backward(C.byref(shape), optim, float(lr), float(eps), B, nnz,
+                                 _ttg.ptr(indices), _ttg.ptr(rowidx), _ttg.ptr(tableidx),
+                                 _ttg.ptr(d_output), cp, sp, dp, _ttg.ptr(ws), ws.numel(),
+                                 flags | EXTRA_FLAGS, _ttg.stream_of(dev))
+        _ttg.check(rc, "tt_backward")
+        if nnz > 0 and not flags:
+            _ttg.workspace.set_plan(dev, key, keep=(indices, rowidx))
+    return d_cores
+
+
+def tt_dense_backward(batch_count: int, D: int, tt_p_shapes: List[int], tt_q_shapes: List[int],
+                      tt_ranks: List[int], L: torch.Tensor, nnz: int, indices: torch.Tensor,
+                      rowidx: torch.Tensor, tableidx: torch.Tensor, d_output: torch.Tensor,
+                      tt_cores: List[torch.Tensor]) -> List[torch.Tensor]:
+    """tt_embeddings_backward_dense_cuda (FBTT/tt_embeddings_cuda.cu:656-686)."""
+    return _backward(_ttg.OPTIM_DENSE, D, 0.0, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices,
+                     rowidx, tableidx, d_output, None, tt_cores)
+
+
+def tt_sgd_backward(batch_count: int, D: int, learning_rate: float, tt_p_shapes: List[int],
+                    tt_q_shapes: List[int], tt_ranks: List[int], L: torch.Tensor, nnz: int,
+                    indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor,
+                    d_output: torch.Tensor, tt_cores: List[torch.Tensor]) -> None:
+    """tt_embeddings_backward_sgd_cuda (FBTT/tt_embeddings_cuda.cu:688-719): in place."""
+    _backward(_ttg.OPTIM_SGD, D, learning_rate, 0.0, tt_p_shapes, tt_q_shapes, tt_ranks, nnz,
+              indices, rowidx, tableidx, d_output, None, tt_cores)
+
+
+def tt_adagrad_backward(batch_count: int, D: int, learning_rate: float, eps: float,
+                        tt_p_shapes: List[int], tt_q_shapes: List[int], tt_ranks: List[int],
+                        L: torch.Tensor, nnz: int, indices: torch.Tensor, rowidx: torch.Tensor,
+                        tableidx: torch.Tensor, d_output: torch.Tensor,
+                        optimizer_state: List[torch.Tensor],
+                        tt_cores: List[torch.Tensor]) -> None:
+    """tt_embeddings_backward_adagrad_cuda (FBTT/tt_embeddings_cuda.cu:721-754): in place."""
+    _backward(_ttg.OPTIM_ADAGRAD, D, learning_rate, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz,
+              indices, rowidx, tableidx, d_output, optimizer_state, tt_cores)
+
+
+def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor,
+                       cache_freq: torch.Tensor) -> None:
+    """update_cache_state_cuda (FBTT/tt_embeddings_cuda.cu:1097-1119)."""
+    if indices.numel() == 0:
+        return
+    _ttg.require_cuda(indices, "indices", torch.int64)
+    _ttg.require_cuda(hashtbl, "hashtbl", torch.int64)
+    _ttg.require_cuda(cache_freq, "cache_freq", torch.int64)
+    if hashtbl.numel() == 0 or hashtbl.numel() != cache_freq.numel():
+        raise RuntimeError("update_cache_state: hashtbl and cache_freq must be non-empty and of "
+                           "equal length")
+    dev = indices.device
+    with torch.cuda.device(dev):
+        rc = _ttg.lib().ttg_update_cache_state(indices.numel(), _ttg.ptr(indices), hashtbl.numel(),
+                                               _ttg.ptr(hashtbl), _ttg.ptr(cache_freq),
+                                               _ttg.stream_of(dev))
+        _ttg.check(rc, "update_cache_state")
+
+
+def cache_populate(num_embeddings: int, tt_p_shapes: List[int], tt_q_shapes: List[int],
+                   tt_ranks: List[int], tt_cores: List[torch.Tensor], L: torch.Tensor,
+                   hashtbl: torch.Tensor, cache_freq: torch.Tensor, cache_state: torch.Tensor,
+                   cache_weight: torch.Tensor) -> None:
+    """cache_populate_cuda (FBTT/tt_embeddings_cuda.cu:1270-1347)."""
+    cores = _cores_ok(list(tt_cores), len(tt_p_shapes))
+    _ttg.require_cuda(hashtbl, "hashtbl", torch.int64)
+    _ttg.require_cuda(cache_freq, "cache_freq", torch.int64)
+    _ttg.require_cuda(cache_state, "cache_state", torch.int32)
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    _ttg.require_cuda(cw, "cache_weight", torch.float32)
+    if hashtbl.numel() == 0 or hashtbl.numel() != cache_freq.numel():
+        raise RuntimeError("cache_populate: hashtbl/cache_freq size mismatch")
+    if hashtbl.numel() < cw.size(0):
+        raise RuntimeError("cache_populate: hashtbl smaller than the cache")
+    dev = hashtbl.device
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, cores[0].size(0))
+    with torch.cuda.device(dev):
+        lib = _ttg.lib()
+        nbytes = lib.ttg_cache_populate_workspace_bytes(C.byref(shape), hashtbl.numel(), cw.size(0))
+        ws = _scratch.get(dev, nbytes)
+        cp = _ttg.ptr_array(cores)
+        rc = lib.ttg_cache_populate(C.byref(shape), cp, hashtbl.numel(), _ttg.ptr(hashtbl),
+                                    _ttg.ptr(cache_freq), _ttg.ptr(cache_state), cw.size(0),
+                                    _ttg.ptr(cw), _ttg.ptr(ws), ws.numel(), _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_populate")
+
+
+def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tables: int,
+                            warmup: bool, hashtbl: torch.Tensor, cache_state: torch.Tensor
+                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int,
+                                       Optional[torch.Tensor]]:
+    """preprocess_indices_sync_cuda (FBTT/tt_embeddings_cuda.cu:1388-1507)."""
+    _ttg.require_cuda(colidx, "colidx", torch.int64)
+    _ttg.require_cuda(offsets, "offsets", torch.int64)
+    dev = colidx.device
+    nnz = colidx.numel()
+    with torch.cuda.device(dev):
+        rowidx = torch.empty_like(colidx)
+        tableidx = torch.empty_like(colidx)
+        if nnz == 0:
+            return colidx, rowidx, tableidx, 0, None
+        lookup = (not warmup) and num_tables == 1
+        part_col = part_row = part_loc = None
+        if lookup:
+            _ttg.require_cuda(hashtbl, "hashtbl", torch.int64)
+            _ttg.require_cuda(cache_state, "cache_state", torch.int32)
+            part_col = torch.empty_like(colidx)
+            part_row = torch.empty_like(colidx)
+            part_loc = torch.empty(nnz, dtype=torch.int32, device=dev)
+        lib = _ttg.lib()
+        ws = _scratch.get(dev, lib.ttg_preprocess_workspace_bytes(nnz))
+        n_tt = C.c_int32(0)
+        rc = lib.ttg_preprocess_indices(
+            nnz, offsets.numel(), _ttg.ptr(colidx), _ttg.ptr(offsets), int(num_tables),
+            1 if warmup else 0, hashtbl.numel() if lookup else 0,
+            _ttg.ptr(hashtbl) if lookup else None, _ttg.ptr(cache_state) if lookup else None,
+            _ttg.ptr(rowidx), _ttg.ptr(tableidx), _ttg.ptr(part_col), _ttg.ptr(part_row),
+            _ttg.ptr(part_loc), C.byref(n_tt), _ttg.ptr(ws), ws.numel(), _ttg.stream_of(dev))
+        _ttg.check(rc, "preprocess_indices_sync")
+    if not lookup:
+        return colidx, rowidx, tableidx, nnz, None
+    return part_col, part_row, tableidx, int(n_tt.value), part_loc
+
+
+def _cache_args(nnz, grad_or_out, cache_locations, rowidx, cache_weight):
+    _ttg.require_cuda(cache_locations, "cache_locations", torch.int32)
+    _ttg.require_cuda(rowidx, "rowidx", torch.int64)
+    cw = cache_weight.data if isinstance(cache_weight, torch.nn.Parameter) else cache_weight
+    _ttg.require_cuda(cw, "cache_weight", torch.float32)
+    if min(cache_locations.numel(), rowidx.numel()) < nnz:
+        raise RuntimeError("cache op: nnz exceeds cache_locations / rowidx")
+    return cw
+
+
+def cache_forward(B: int, nnz: int, cache_locations: torch.Tensor, rowidx: torch.Tensor,
+                  cache_weight: torch.Tensor, output: torch.Tensor) -> None:
+    """cache_forward_cuda (FBTT/tt_embeddings_cuda.cu:1551-1583): accumulates into output."""
+    if B <= 0:
+        raise RuntimeError("cache_forward: B must be positive")
+    cw = _cache_args(nnz, output, cache_locations, rowidx, cache_weight)
+    _ttg.require_cuda(output, "output", torch.float32)
+    dev = output.device
+    with torch.cuda.device(dev):
+        rc = _ttg.lib().ttg_cache_forward(int(nnz), cw.size(1), _ttg.ptr(cache_locations),
+                                          _ttg.ptr(rowidx), _ttg.ptr(cw), _ttg.ptr(output),
+                                          _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_forward")
+
+
+def cache_backward_sgd(nnz: int, grad_output: torch.Tensor, cache_locations: torch.Tensor,
+                       rowidx: torch.Tensor, learning_rate: float,
+                       cache_weight: torch.Tensor) -> None:
+    """cache_backward_sgd_cuda (FBTT/tt_embeddings_cuda.cu:1634-1668)."""
+    cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
+    dev = cw.device
+    with torch.cuda.device(dev):
+        g = grad_output.to(torch.float32).contiguous()
+        rc = _ttg.lib().ttg_cache_backward_sgd(int(nnz), cw.size(1), _ttg.ptr(g),
+                                               _ttg.ptr(cache_locations), _ttg.ptr(rowidx),
+                                               float(learning_rate), _ttg.ptr(cw),
+                                               _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_backward_sgd")
+
+
+def cache_backward_dense(nnz: int, grad_output: torch.Tensor, cache_locations: torch.Tensor,
+                         rowidx: torch.Tensor, learning_rate: float,
+                         cache_weight: torch.Tensor) -> torch.Tensor:
+    """cache_backward_dense_cuda (FBTT/tt_embeddings_cuda.cu:1710-1744)."""
+    cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
+    dev = cw.device
+    with torch.cuda.device(dev):
+        grad = torch.zeros_like(cw)
+        g = grad_output.to(torch.float32).contiguous()
+        rc = _ttg.lib().ttg_cache_backward_dense(int(nnz), cw.size(1), _ttg.ptr(g),
+                                                 _ttg.ptr(cache_locations), _ttg.ptr(rowidx),
+                                                 _ttg.ptr(grad), _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_backward_dense")
+    return grad
+
+
+def cache_backward_rowwise_adagrad_approx(nnz: int, grad_output: torch.Tensor,
+                                          cache_locations: torch.Tensor, rowidx: torch.Tensor,
+                                          learning_rate: float, eps: float,
+                                          cache_optimizer_state: torch.Tensor,
+                                          cache_weight: torch.Tensor) -> None:
+    """cache_backward_rowwise_adagrad_approx_cuda (FBTT/tt_embeddings_cuda.cu:1808-1846)."""
+    cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
+    _ttg.require_cuda(cache_optimizer_state, "cache_optimizer_state", torch.float32)
+    dev = cw.device
+    with torch.cuda.device(dev):
+        g = grad_output.to(torch.float32).contiguous()
+        rc = _ttg.lib().ttg_cache_backward_rowwise_adagrad_approx(
+            int(nnz), cw.size(1), _ttg.ptr(g), _ttg.ptr(cache_locations), _ttg.ptr(rowidx),
+            float(learning_rate), float(eps), _ttg.ptr(cache_optimizer_state), _ttg.ptr(cw),
+            _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_backward_rowwise_adagrad_approx")

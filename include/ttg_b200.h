@@ -1,0 +1,223 @@
+/*
+ * ttg_b200.h -- C ABI of the B200-native TT-embedding hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one function of the
+ * reference's pybind modules (the citation after "replaces:" is path:line relative to the
+ * reference tree).  Plain pointers and sizes only: no ATen/torch types, no allocation, no
+ * hidden state.  All pointers are DEVICE pointers unless a parameter is named host_*.
+ * Every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ * without synchronising, except ttg_preprocess_indices whose contract is to return the
+ * host integer nnz_tt (the reference synchronises there too,
+ * FBTT/tt_embeddings_cuda.cu:1492-1499).
+ *
+ * Return value: 0 on success, a negative TTG_E* code otherwise; ttg_last_error() gives the
+ * message of the last failure on the calling thread.  The Python shim turns a non-zero
+ * return into RuntimeError, which is what TORCH_CHECK does in the reference
+ * (FBTT/tt_embeddings_cuda.cu:991-994).
+ *
+ * Layout conventions (identical to the reference, FBTT/tt_embeddings_ops.py:519-545):
+ *   core t   : fp32 [num_tables][p[t]][r[t]*q[t]*r[t+1]], row i_t is the row-major matrix
+ *              [r[t]][q[t]][r[t+1]]
+ *   L        : int64 [T], L[t] = prod(p[t+1:])     index split i_t = (idx % L[t-1]) / L[t]
+ *   output   : fp32 [num_tables][B][D], D = prod(q)
+ *   indices, rowidx, tableidx : int64 [nnz]
+ */
+#ifndef TTG_B200_H_
+#define TTG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTG_MAX_CORES 4
+
+enum {
+  TTG_OK = 0,
+  TTG_EINVAL = -1,   /* bad argument (shape, null pointer, D % 4 != 0 ...) */
+  TTG_ECUDA = -2,    /* a CUDA runtime call or kernel launch failed          */
+  TTG_ENOMEM = -3,   /* workspace too small                                  */
+  TTG_ENOTSUP = -4   /* shape outside what the kernels support               */
+};
+
+enum { TTG_OPTIM_SGD = 0, TTG_OPTIM_ADAGRAD = 1, TTG_OPTIM_DENSE = 2 };
+
+/* flags for ttg_tt_forward / ttg_tt_backward */
+enum {
+  TTG_FLAG_FORCE_GENERIC = 1, /* use the shape-generic kernels (any T in 2..4)      */
+  TTG_FLAG_PLAN_VALID = 2     /* workspace already holds the sorted plan of the SAME
+                                 (indices, nnz) -- skip the sort (fwd -> bwd reuse)   */
+};
+
+/* TT table description: tt_p_shapes / tt_q_shapes / tt_ranks of the reference. */
+typedef struct ttg_shape {
+  int32_t T;                      /* number of cores, 2..4                      */
+  int32_t num_tables;             /* tt_cores[t].size(0)                        */
+  int32_t p[TTG_MAX_CORES];       /* tt_p_shapes                                */
+  int32_t q[TTG_MAX_CORES];       /* tt_q_shapes                                */
+  int32_t r[TTG_MAX_CORES + 1];   /* tt_ranks incl. the leading/trailing 1      */
+} ttg_shape;
+
+const char* ttg_last_error(void);
+int ttg_version(void);
+/* number of kernel launches issued by this library on the calling process so far */
+int64_t ttg_launch_count(void);
+
+/* Per-kernel timing for bench.py's roofline line: when enabled, the library brackets each of
+ * its main kernels with CUDA events on the launching stream (do not enable while capturing a
+ * CUDA graph).  ttg_profile_read synchronises on the recorded events and returns the total
+ * device time and launch count of kernel class `id` since the last enable; ttg_profile_name
+ * returns its name or NULL when id is out of range. */
+int ttg_profile_enable(int32_t on);
+int ttg_profile_read(int32_t id, double* total_ms, int64_t* count);
+const char* ttg_profile_name(int32_t id);
+
+/* ------------------------------------------------------------------------------------
+ * (a) TT chain contraction: forward.
+ * replaces: tt_embeddings_forward_cuda  FBTT/tt_embeddings_cuda.cu:967-1081 (op tt_forward,
+ *           FBTT/tt_embeddings.cpp:13-26,132)
+ * output[tableidx[n]][rowidx[n]][:] += TT_row(indices[n]) for n < nnz; rows of `output`
+ * that no index maps to are written as zeros (the reference returns at::zeros + RMW), so
+ * `output` does not need to be initialised.  Precondition (what preprocess_indices
+ * produces): rowidx is non-decreasing within a table.
+ * workspace: ttg_tt_workspace_bytes(shape, B, nnz) bytes, 256-byte aligned; the same
+ * (shape, B, nnz) gives the same layout, which is what TTG_FLAG_PLAN_VALID relies on.
+ * ---------------------------------------------------------------------------------- */
+size_t ttg_tt_workspace_bytes(const ttg_shape* shape, int64_t B, int64_t nnz);
+
+int ttg_tt_forward(const ttg_shape* shape, int64_t B, int64_t nnz,
+                   const int64_t* indices, const int64_t* rowidx, const int64_t* tableidx,
+                   const float* const* host_core_ptrs, /* host array of T device pointers */
+                   float* output, void* workspace, size_t workspace_bytes, int32_t flags,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (b) backward + optimizer.
+ * replaces: tt_embeddings_backward_cuda  FBTT/tt_embeddings_cuda.cu:421-654 behind the ops
+ *           tt_dense_backward :656-686, tt_sgd_backward :688-719, tt_adagrad_backward
+ *           :721-754 (FBTT/tt_embeddings.cpp:28-72,133-142)
+ * d_cores[t] (fp32, same shape as core t) always receives the dense gradient (it is
+ * overwritten, not accumulated).  optim == TTG_OPTIM_SGD additionally does
+ * core -= lr * d_core; TTG_OPTIM_ADAGRAD does state += g*g; core -= lr*g/(sqrt(state)+eps)
+ * over the WHOLE core (the reference's launch config skips tail rows; we
+ * implement the formula of FBTT/tt_embeddings_cuda.cu:381-419 on every row).
+ * ---------------------------------------------------------------------------------- */
+int ttg_tt_backward(const ttg_shape* shape, int32_t optim, float lr, float eps, int64_t B,
+                    int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                    const int64_t* tableidx, const float* d_output,
+                    float* const* host_core_ptrs,      /* T device pointers, updated in place */
+                    float* const* host_state_ptrs,     /* T device pointers or NULL          */
+                    float* const* host_dcore_ptrs,     /* T device pointers (outputs)        */
+                    void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
+
+/* The optimizer step alone (what ttg_tt_backward fuses), for data-parallel training where the
+ * dense gradients are all-reduced between the backward and the update.
+ * replaces: update_tt_cores_sgd_kernel / update_tt_cores_adagrad_kernel
+ *           FBTT/tt_embeddings_cuda.cu:381-419 (launches :612-651) */
+int ttg_apply_optimizer(const ttg_shape* shape, int32_t optim, float lr, float eps,
+                        float* const* host_core_ptrs, float* const* host_state_ptrs,
+                        float* const* host_dcore_ptrs, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) index path: LFU hash-table cache.
+ * ---------------------------------------------------------------------------------- */
+/* replaces: update_cache_state_cuda FBTT/tt_embeddings_cuda.cu:1083-1119 */
+int ttg_update_cache_state(int64_t nnz, const int64_t* indices, int64_t hashtbl_size,
+                           int64_t* hashtbl, int64_t* cache_freq, void* stream);
+
+/* replaces: cache_populate_cuda FBTT/tt_embeddings_cuda.cu:1270-1347 (sort by frequency,
+ * mark_popular_colidx_kernel :1122-1149, prefetch_cached_weights_cuda :1166-1268).
+ * workspace: ttg_cache_populate_workspace_bytes(shape, hashtbl_size, cache_size). */
+size_t ttg_cache_populate_workspace_bytes(const ttg_shape* shape, int64_t hashtbl_size,
+                                          int64_t cache_size);
+int ttg_cache_populate(const ttg_shape* shape, const float* const* host_core_ptrs,
+                       int64_t hashtbl_size, int64_t* hashtbl, int64_t* cache_freq,
+                       int32_t* cache_state, int64_t cache_size, float* cache_weight,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces: preprocess_indices_sync_cuda FBTT/tt_embeddings_cuda.cu:1388-1507
+ * (compute_rowidx_kernel :1349-1365, cache_lookup_kernel :1367-1386, 3x
+ * cub::DevicePartition::Flagged :1448-1490).
+ * Always writes rowidx/tableidx[nnz].  If warmup != 0 or num_tables != 1 nothing else is
+ * written and *host_nnz_tt = nnz.  Otherwise part_colidx/part_rowidx/part_cache_loc[nnz]
+ * receive [TT items in original order | cached items in REVERSED original order] and
+ * *host_nnz_tt the number of TT items (stream is synchronised to produce it).
+ * part_cache_loc entries of TT items are -1 (the reference leaves them uninitialised).
+ * workspace: ttg_preprocess_workspace_bytes(nnz). */
+size_t ttg_preprocess_workspace_bytes(int64_t nnz);
+int ttg_preprocess_indices(int64_t nnz, int64_t num_offsets, const int64_t* colidx,
+                           const int64_t* offsets, int32_t num_tables, int32_t warmup,
+                           int64_t hashtbl_size, const int64_t* hashtbl,
+                           const int32_t* cache_state, int64_t* rowidx, int64_t* tableidx,
+                           int64_t* part_colidx, int64_t* part_rowidx,
+                           int32_t* part_cache_loc, int32_t* host_nnz_tt, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* replaces: cache_forward_cuda FBTT/tt_embeddings_cuda.cu:1509-1583
+ * output[rowidx[n]][:] += cache_weight[cache_locations[n]][:]  (accumulates) */
+int ttg_cache_forward(int64_t nnz, int32_t D, const int32_t* cache_locations,
+                      const int64_t* rowidx, const float* cache_weight, float* output,
+                      void* stream);
+/* replaces: cache_backward_sgd_cuda FBTT/tt_embeddings_cuda.cu:1585-1668 */
+int ttg_cache_backward_sgd(int64_t nnz, int32_t D, const float* grad_output,
+                           const int32_t* cache_locations, const int64_t* rowidx, float lr,
+                           float* cache_weight, void* stream);
+/* replaces: cache_backward_dense_cuda FBTT/tt_embeddings_cuda.cu:1670-1744
+ * grad_cache_weight [cache_size][D] must be zero-initialised by the caller. */
+int ttg_cache_backward_dense(int64_t nnz, int32_t D, const float* grad_output,
+                             const int32_t* cache_locations, const int64_t* rowidx,
+                             float* grad_cache_weight, void* stream);
+/* replaces: cache_backward_rowwise_adagrad_approx_cuda FBTT/tt_embeddings_cuda.cu:1746-1846 */
+int ttg_cache_backward_rowwise_adagrad_approx(int64_t nnz, int32_t D,
+                                              const float* grad_output,
+                                              const int32_t* cache_locations,
+                                              const int64_t* rowidx, float lr, float eps,
+                                              float* cache_optimizer_state,
+                                              float* cache_weight, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) Efficient_TT: prefix-reuse forward / dedup'd fused-SGD backward, 3 cores, one index
+ * per output row, cores are 2-D [p[t]][cols_t].
+ * replaces: Efficient_TT_forward_cuda Efficient_TT/efficient_tt_cuda.cu:243-377 and
+ *           Fused_Extra_Efficient_TT_backward_sgd_cuda :1011-1247
+ *           (Efficient_TT/efficient_kernel_wrap.cpp:16-28,63-80,83-89).
+ * Index math is integer (the reference's float math is identical wherever it is exact,
+ * SURVEY 8a-8).  No process-global scratch: the workspace is the caller's.
+ * ---------------------------------------------------------------------------------- */
+/* workspace for both Efficient_TT calls (index plan + dense gradient scratch) */
+size_t ttg_eff_workspace_bytes(const ttg_shape* shape, int64_t batch);
+int ttg_eff_forward(const ttg_shape* shape, int64_t batch, const int64_t* indices,
+                    const float* const* host_core_ptrs, float* output, void* workspace,
+                    size_t workspace_bytes, void* stream);
+/* core_t[i_t] -= lr * (gradient slices summed over all rows); duplicates in `indices`
+ * contribute once per occurrence, exactly like unique + inverse accumulation
+ * (Efficient_TT/efficient_tt.py:132-133, efficient_tt_cuda.cu:970-987). */
+int ttg_eff_backward_sgd(const ttg_shape* shape, int64_t batch, float lr,
+                         const int64_t* indices, const float* d_output,
+                         float* const* host_core_ptrs, void* workspace,
+                         size_t workspace_bytes, int32_t flags, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (d) neighbour aggregation on a sampled block (CSR by destination).
+ * replaces: the SpMM inside dglnn.SAGEConv(..., 'mean') gnn_model.py:78-81,211-214 and
+ *           dglnn.GraphConv(norm='both') gnn_model.py:287 (DGL 2.1.0, un-vendored).
+ * out[v][:] = scale_v * sum_{e in [indptr[v], indptr[v+1])} w_e * x[indices[e]][:]
+ *   mean != 0: scale_v = 1/deg(v) (0 rows stay 0);  mean == 0: scale_v = 1
+ *   edge_weight may be NULL (w_e = 1).  F % 4 == 0.
+ * The backward is the same kernel on the transposed CSR (built once per block by the
+ * caller) or ttg_spmm_csr_bwd which scatters with vector reductions.
+ * ---------------------------------------------------------------------------------- */
+int ttg_spmm_csr_fwd(int64_t num_dst, int32_t F, const int64_t* indptr,
+                     const int32_t* indices, const float* edge_weight, int32_t mean,
+                     const float* x, float* out, void* stream);
+/* dx[indices[e]][:] += scale_v * w_e * dout[v][:]; dx [num_src][F] must be zeroed by caller */
+int ttg_spmm_csr_bwd(int64_t num_dst, int32_t F, const int64_t* indptr,
+                     const int32_t* indices, const float* edge_weight, int32_t mean,
+                     const float* dout, float* dx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTG_B200_H_ */

@@ -1,0 +1,171 @@
+"""GPU tests of the module surface, written the way the reference's own (commented-out) unit
+test states correctness (sage_profiler.py:303-305, 362-367, 405-426, 466-500):
+forward == sum-mode EmbeddingBag over full_weight(); dense grads == autograd through
+tt_matrix_to_full; fused SGD == core - lr * grad; Adagrad == state = g^2, core - lr*g/(sqrt+eps).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bags(rng, n_emb, n_bags, one_per_bag):
+    lengths = (np.ones(n_bags, dtype=np.int64) if one_per_bag
+               else np.clip(np.round(rng.normal(4, 5, size=n_bags)), 0, None).astype(np.int64))
+    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    indices = rng.integers(0, n_emb, size=int(offsets[-1])).astype(np.int64)
+    return torch.from_numpy(indices).to(DEV), torch.from_numpy(offsets).to(DEV)
+
+
+def _make(n_emb, D, ranks, p, q, **kw):
+    from FBTT.tt_embeddings_ops import TTEmbeddingBag
+    torch.manual_seed(0)
+    np.random.seed(0)
+    kw.setdefault("weight_dist", "normal")
+    kw.setdefault("use_cache", False)
+    m = TTEmbeddingBag(n_emb, D, ranks, p, q, **kw)
+    with torch.no_grad():
+        for c in m.tt_cores:     # O(1) entries so that 1e-5 relative is a meaningful bar
+            c.mul_(n_emb ** 0.5 * 0.5)
+    return m
+
+
+@pytest.mark.parametrize("one_per_bag", [True, False])
+@pytest.mark.parametrize("cfg", [
+    (2708, 128, [16, 16], [14, 14, 14], [4, 4, 8]),
+    (5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]),
+    (99, 32, [12], [9, 11], [4, 8]),
+    (360, 48, [4, 6, 5], [3, 4, 5, 6], [2, 2, 3, 4]),
+])
+def test_forward_equals_embedding_bag_and_dense_grads_equal_autograd(ttg_lib, cfg, one_per_bag):
+    from FBTT.tt_embeddings_ops import tt_matrix_to_full
+    n_emb, D, ranks, p, q = cfg
+    m = _make(n_emb, D, ranks, p, q, sparse=False)
+    rng = np.random.default_rng(1)
+    indices, offsets = _bags(rng, n_emb, 257, one_per_bag)
+    out = m(indices.int(), offsets.int())          # DGL hands int32 ids (sage_dgl_partition.py:85)
+    W = m.full_weight()
+    ref = torch.nn.functional.embedding_bag(indices, W, offsets, mode="sum", include_last_offset=True)
+    assert out.shape == ref.shape
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    d_out = torch.rand_like(out) * 0.1
+    out.backward(d_out)
+    cores64 = [c.detach().double().requires_grad_(True) for c in m.tt_cores]
+    W64 = tt_matrix_to_full(p, q, [1] + ranks + [1], cores64, [1, 0, 2, 3]).double()
+    ref64 = torch.nn.functional.embedding_bag(indices, W64, offsets, mode="sum",
+                                              include_last_offset=True)
+    (ref64 * d_out.double()).sum().backward()
+    for c, c64 in zip(m.tt_cores, cores64):
+        torch.testing.assert_close(c.grad, c64.grad.float(), rtol=1e-5,
+                                   atol=1e-5 * float(c64.grad.abs().max()))
+
+
+def test_sparse_sgd_updates_cores_in_place(ttg_lib):
+    from FBTT.tt_embeddings_ops import OptimType
+    n_emb, D, ranks, p, q = 5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]
+    m = _make(n_emb, D, ranks, p, q, sparse=True, optimizer=OptimType.SGD, learning_rate=0.1)
+    m_dense = _make(n_emb, D, ranks, p, q, sparse=False)
+    rng = np.random.default_rng(2)
+    indices, offsets = _bags(rng, n_emb, 128, False)
+    before = [c.detach().clone() for c in m.tt_cores]
+    out = m(indices, offsets)
+    d_out = torch.rand_like(out) * 0.1
+    out.backward(d_out)
+    assert all(c.grad is None for c in m.tt_cores)      # fused path returns no gradients
+    out_d = m_dense(indices, offsets)
+    out_d.backward(d_out)
+    for b, c, cd in zip(before, m.tt_cores, m_dense.tt_cores):
+        torch.testing.assert_close(c.detach(), b - 0.1 * cd.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_cache_flow_matches_uncached_until_rows_are_trained(ttg_lib):
+    n_emb, D, ranks, p, q = 5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]
+    m = _make(n_emb, D, ranks, p, q, sparse=False, use_cache=True, cache_size=20,
+              hashtbl_size=4001)
+    rng = np.random.default_rng(3)
+    hot = torch.from_numpy(rng.choice(n_emb, size=15, replace=False)).to(DEV)
+    for _ in range(3):                                    # warm-up epoch: statistics only
+        idx = torch.cat([hot, torch.from_numpy(rng.integers(0, n_emb, size=30)).to(DEV)])
+        off = torch.arange(idx.numel() + 1, device=DEV)
+        assert m.warmup
+        m(idx, off)
+    m.cache_populate()
+    assert not m.warmup
+    idx = torch.cat([hot[:7], torch.from_numpy(rng.integers(0, n_emb, size=50)).to(DEV), hot[7:]])
+    off = torch.arange(idx.numel() + 1, device=DEV)
+    out = m(idx, off)
+    ref = m.full_weight()[idx]
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)   # cache rows are a snapshot
+    out.backward(torch.ones_like(out))
+    assert m.cache_weight.grad is not None and float(m.cache_weight.grad.abs().sum()) > 0
+    # the hot rows were served from the cache: their gradient went to cache_weight, not the cores
+    loc_rows = (m.cache_weight.grad.abs().sum(dim=1) > 0).sum().item()
+    assert loc_rows >= 10
+    sd = m.state_dict()
+    for k in ["L", "hashtbl", "cache_freq", "cache_state", "cache_weight", "tt_cores.0"]:
+        assert k in sd
+
+
+def test_eff_embedding_forward_and_fused_sgd(ttg_lib):
+    from Efficient_TT.efficient_tt import Eff_TTEmbedding
+    from FBTT.tt_embeddings_ops import tt_matrix_to_full
+    p, q, ranks = [5, 6, 7], [4, 5, 5], [16, 16]
+    n_emb = 5 * 6 * 7
+    torch.manual_seed(0)
+    m = Eff_TTEmbedding(n_emb, 100, ranks, p, q, learning_rate=0.1, device=0)
+    with torch.no_grad():
+        for c in m.tt_cores:
+            c.mul_(20.0)
+    rng = np.random.default_rng(4)
+    idx = torch.from_numpy(rng.integers(0, n_emb, size=500)).to(DEV)
+    idx[10] = idx[11]
+    cores0 = [c.detach().clone() for c in m.tt_cores]
+    out = m(idx)
+    W = tt_matrix_to_full(p, q, [1] + ranks + [1], [c[None] for c in cores0], [1, 0, 2, 3])
+    torch.testing.assert_close(out, W[idx], rtol=1e-5, atol=1e-6)
+    d_out = torch.rand_like(out) * 0.1
+    out.backward(d_out)
+    c64 = [c.double()[None].requires_grad_(True) for c in cores0]
+    W64 = tt_matrix_to_full(p, q, [1] + ranks + [1], c64, [1, 0, 2, 3]).double()
+    (W64[idx] * d_out.double()).sum().backward()
+    for c, c0, g in zip(m.tt_cores, cores0, c64):
+        torch.testing.assert_close(c.detach(), c0 - 0.1 * g.grad[0].float(), rtol=1e-5, atol=1e-6)
+
+
+def test_sageconv_and_graphconv_against_dense_torch(ttg_lib):
+    import gnn_ops
+    from helpers import random_block
+    rng = np.random.default_rng(6)
+    num_src, num_dst = 900, 300
+    indptr, indices = random_block(rng, num_src, num_dst, 9)
+    blk = gnn_ops.Block(torch.from_numpy(indptr).to(DEV), torch.from_numpy(indices).to(DEV),
+                        num_src, num_dst)
+    A = torch.zeros(num_dst, num_src, dtype=torch.float64)
+    for v in range(num_dst):
+        for e in range(indptr[v], indptr[v + 1]):
+            A[v, indices[e]] += 1
+    A = A.to(DEV)
+    deg = A.sum(1).clamp(min=1)
+    for fin, fout in [(100, 256), (256, 47)]:          # aggregate-then-linear / linear-then-aggregate
+        torch.manual_seed(1)
+        conv = gnn_ops.SAGEConv(fin, fout, "mean").to(DEV)
+        h = torch.randn(num_src, fin, device=DEV, requires_grad=True)
+        out = conv(blk, (h, h[:num_dst]))
+        h64 = h.detach().double().requires_grad_(True)
+        neigh = (A @ h64) / deg[:, None]
+        ref = (h64[:num_dst] @ conv.fc_self.weight.double().t()
+               + neigh @ conv.fc_neigh.weight.double().t() + conv.bias.double())
+        torch.testing.assert_close(out, ref.float(), rtol=1e-4, atol=1e-4)
+        g = torch.randn_like(out)
+        out.backward(g)
+        ref.backward(g.double())
+        torch.testing.assert_close(h.grad, h64.grad.float(), rtol=1e-4, atol=1e-4)
+    conv = gnn_ops.GraphConv(64, 32).to(DEV)
+    h = torch.randn(num_src, 64, device=DEV)
+    out = conv(blk, h)
+    odeg = A.sum(0).clamp(min=1)
+    ref = ((A @ (h.double() / odeg.sqrt()[:, None])) / deg.sqrt()[:, None]) @ conv.weight.double() \
+        + conv.bias.double()
+    torch.testing.assert_close(out, ref.float(), rtol=1e-4, atol=1e-4)
