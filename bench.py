@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- TT-EmbeddingBag fwd + bwd + fused SGD throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over one batch of synthetic input at BASELINE config 2
+("GraphSAGE on ogbn-products shape, FBTT p=125,140,140 q=4,5,5 ranks 16,16"): 262,144 distinct
+uniformly drawn node ids (the size of a batch-1024, fanout [5,10,15] layer-0 frontier), one index
+per bag, forward reconstruction of the rows, backward with an upstream gradient, fused SGD on the
+cores.  Prints ONE JSON line (rank 0).
+
+  value      rows/s with the inputs resident in HBM, the step replayed as a CUDA graph of the raw
+             C-ABI ops (tt_forward + tt_sgd_backward); N > 1: each rank runs its own batch (weak
+             scaling) and the dense core gradients are all-reduced over NCCL before the update
+  e2e        the same metric through the module a user calls (TTEmbeddingBag.forward + autograd),
+             indices / offsets copied from pinned host memory and the scalar loss read back every
+             step
+  roofline   dominant kernel, algorithmic bytes / CUDA-event duration vs the measured HBM peak
+  cpu_baseline / --impl reference : the oracle's C port of the same step on the host cores
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+L2: four batches are rotated; one step touches 212 MB (> 126 MB L2), the rotation 850 MB.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "falcon-ttdforgnns_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+SHAPES = {
+    "products": dict(n=2449029, p=[125, 140, 140], q=[4, 5, 5], ranks=[16, 16]),
+    "arxiv": dict(n=169343, p=[55, 55, 56], q=[4, 4, 8], ranks=[16, 16]),
+    "papers": dict(n=111059956, p=[481, 481, 481], q=[4, 4, 8], ranks=[32, 32]),
+}
+METRIC = "TT-EmbeddingBag rows/s fwd+bwd+SGD"
+NUM_ROT = 4
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "samples": len(sm),
+                "power_w_max": max(power), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return world, rank, local
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the only place bench.py executes oracle/
+# --------------------------------------------------------------------------------------------
+def cpu_step_rate(shape, sample_rows, steps, warmup, seed=0):
+    from oracle import oracle as orc
+    p, q, ranks = shape["p"], shape["q"], [1] + shape["ranks"] + [1]
+    D = int(np.prod(q))
+    rng = np.random.default_rng(seed)
+    cores = [(rng.standard_normal((1, p[t], ranks[t] * q[t] * ranks[t + 1])) /
+              np.sqrt(shape["n"])).astype(np.float32) for t in range(3)]
+    cols = [ranks[t] * q[t] * ranks[t + 1] for t in range(3)]
+    batches = [(rng.choice(shape["n"], size=sample_rows, replace=False).astype(np.int64),
+                (rng.random((sample_rows, D)) * 0.1).astype(np.float32)) for _ in range(2)]
+
+    def one(i):
+        idx, d_out = batches[i % 2]
+        orc.tt_forward_f32_rows(p, q, ranks, cores, idx)
+        g = orc.tt_backward_f32_rows(p, q, ranks, cores, idx, d_out)
+        orc.apply_optimizer(p, cols, "sgd", 0.1, 0.0, cores, None, g)
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return sample_rows * steps / dt, dt / steps, orc.num_threads()
+
+
+def calibrated_cpu_baseline(shape, target_seconds=12.0):
+    rate, _, threads = cpu_step_rate(shape, 2048, 1, 1)
+    rows = int(min(262144, max(2048, rate * target_seconds / 3)))
+    rate, sec, threads = cpu_step_rate(shape, rows, 3, 1)
+    return {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+            "sample": "%d rows x 3 steps of the same workload (C oracle port, fp32, OpenMP), "
+                      "%.2f s/step" % (rows, sec)}
+
+
+def run_reference(args, shape):
+    world, rank, _ = dist_env()
+    if rank != 0:
+        return
+    rows = args.cpu_rows
+    rate, sec, threads = cpu_step_rate(shape, rows, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows_per_step": rows,
+                   "note": "the reference has no CPU implementation of this path (CUDA only); "
+                           "this is the oracle's C port of FBTT tt_forward + tt_sgd_backward on "
+                           "all host threads, on a bounded sample of the workload"},
+        "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": "%d rows per step" % rows},
+        "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    s = SHAPES[args.shape]
+    return ("%s shape: N=%d, p=%s q=%s ranks=%s, %d distinct uniform ids per step, one index per "
+            "bag, fwd+bwd+SGD(lr=0.1)" % (args.shape, s["n"], s["p"], s["q"], s["ranks"], args.nnz))
+
+
+# --------------------------------------------------------------------------------------------
+# ours
+# --------------------------------------------------------------------------------------------
+def run_ours(args, shape):
+    import torch.distributed as dist
+    world, rank, local = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device (the product has no CPU path; "
+                           "use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import _ttg
+    import dp
+    import tt_embeddings as te
+    from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
+
+    lib = _ttg.lib()
+    p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
+    rr = [1] + ranks + [1]
+    D = int(np.prod(q))
+    nnz = args.nnz
+    torch.manual_seed(1234)
+    module = TTEmbeddingBag(N, D, ranks, p, q, optimizer=OptimType.SGD, learning_rate=0.1,
+                            sparse=True, use_cache=False, weight_dist="normal")
+    cores = [c.data for c in module.tt_cores]
+    core_bytes = sum(c.numel() * 4 for c in cores)
+
+    g = torch.Generator().manual_seed(1000 + rank)
+    idx_host = [torch.randperm(N, generator=g)[:nnz].contiguous().pin_memory() for _ in range(NUM_ROT)]
+    off_host = torch.arange(nnz + 1, dtype=torch.int64).pin_memory()
+    idx_dev = [t.to(dev) for t in idx_host]
+    rowidx = torch.arange(nnz, device=dev)
+    tableidx = torch.zeros(nnz, dtype=torch.int64, device=dev)
+    d_out = [(torch.rand(1, nnz, D, generator=g) * 0.1).to(dev) for _ in range(NUM_ROT)]
+    groups = int(torch.unique(idx_host[0] // p[2]).numel())
+
+    def raw_step(k):
+        out = te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx, cores)
+        if world == 1:
+            te.tt_sgd_backward(1000, D, 0.1, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx,
+                               d_out[k], cores)
+        else:
+            dc = te.tt_dense_backward(1000, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx,
+                                      d_out[k], cores)
+            dp.apply_optimizer(p, q, rr, cores, dp.allreduce_mean(dc), 0.1)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    # ---- warm-up (eager), then try to capture one CUDA graph per rotating batch
+    for i in range(max(args.warmup, 3)):
+        raw_step(i % NUM_ROT)
+    sync_all()
+    l0 = lib.ttg_launch_count()
+    raw_step(0)
+    launches_per_step = int(lib.ttg_launch_count() - l0)
+    sync_all()
+    graphs, use_graph = [], (world == 1 and not args.no_graph)
+    if use_graph:
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for k in range(NUM_ROT):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=side):
+                        raw_step(k)
+                    graphs.append(gr)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            sync_all()
+            for k in range(NUM_ROT):
+                graphs[k].replay()
+            sync_all()
+        except Exception as ex:  # capture is an optimisation of the launch path, not a fallback
+            print("bench.py: CUDA graph capture failed (%s); timing eager launches" % ex,
+                  file=sys.stderr)
+            graphs, use_graph = [], False
+            sync_all()
+
+    def timed(fn, steps):
+        sync_all()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    step_fn = (lambda i: graphs[i % NUM_ROT].replay()) if use_graph else (lambda i: raw_step(i % NUM_ROT))
+    for i in range(args.warmup):
+        step_fn(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(step_fn, args.steps)
+    clocks = sampler.stop() if sampler else None
+    ms_step = ms_total / args.steps
+    value = world * nnz / (ms_step * 1e-3)
+
+    # ---- per-kernel device time (eager, CUDA events inside the library)
+    kern = {}
+    if rank == 0 or world > 1:
+        lib.ttg_profile_enable(1)
+        nprof = min(args.steps, 20)
+        for i in range(nprof):
+            raw_step(i % NUM_ROT)
+        torch.cuda.synchronize(dev)
+        i = 0
+        while lib.ttg_profile_name(i):
+            tot, cnt = C.c_double(0), C.c_int64(0)
+            lib.ttg_profile_read(i, C.byref(tot), C.byref(cnt))
+            if cnt.value:
+                kern[lib.ttg_profile_name(i).decode()] = {"ms": tot.value / cnt.value,
+                                                          "launches_per_step": cnt.value / nprof}
+            i += 1
+        lib.ttg_profile_enable(0)
+
+    # ---- end to end through the module API (host indices in, scalar loss out)
+    idx_stage = torch.empty(nnz, dtype=torch.int64, device=dev)
+    off_stage = torch.empty(nnz + 1, dtype=torch.int64, device=dev)
+    target = [d.view(nnz, D) for d in d_out]
+    losses = []
+
+    def e2e_step(i):
+        k = i % NUM_ROT
+        idx_stage.copy_(idx_host[k], non_blocking=True)
+        off_stage.copy_(off_host, non_blocking=True)
+        out = module(idx_stage, off_stage)
+        if world == 1:
+            loss = (out * target[k]).sum()
+            loss.backward()
+        else:  # data parallel: explicit exchange step instead of the fused update
+            module.sparse = False
+            loss = (out * target[k]).sum()
+            loss.backward()
+            dp.dp_backward_step(module, [c.grad for c in module.tt_cores])
+            for c in module.tt_cores:
+                c.grad = None
+        losses.append(float(loss.item()))
+
+    for i in range(3):
+        e2e_step(i)
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * nnz / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline
+    hbm_peak, peak_src, sm_max = measured_peaks()
+    bytes_fwd = nnz * (8 + 4 * D)
+    bytes_bwd = nnz * (8 + 4 * D)
+    alg = {"sorted_fwd_kernel": bytes_fwd, "sorted_bwd_rows_kernel": bytes_bwd,
+           "generic_fwd_kernel": bytes_fwd, "generic_bwd_kernel": bytes_bwd}
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms"], default=None)
+    roofline = None
+    if dom:
+        achieved = alg[dom] / (kern[dom]["ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                    "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kern[dom]["ms"]}
+    step_bytes = nnz * (16 + 8 * D) + 2 * core_bytes
+    q0, q1, q2 = q
+    r1, r2 = ranks
+    f_row = 2 * (q0 * q1) * r2 * q2 * 3            # per row: row product, d_core2 slice, d(tr0)
+    f_grp = 2 * q0 * r1 * (q1 * r2) * 4            # per group: tr0 fwd, tr0 bwd, d_core1, d_core0
+    step_flops = f_row * nnz + f_grp * groups
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6
+    t_hbm = step_bytes / (hbm_peak * 1e9)
+    t_fp32 = step_flops / fp32_peak
+    bound_s = max(t_hbm, t_fp32)
+    step_roofline = {
+        "bytes_per_step": step_bytes, "flops_per_step_with_prefix_reuse": step_flops,
+        "unique_groups": groups, "t_hbm_us": t_hbm * 1e6, "t_fp32_ffma_us": t_fp32 * 1e6,
+        "fp32_peak_tflops_nominal": fp32_peak / 1e12,
+        "bound": "fp32" if t_fp32 > t_hbm else "hbm",
+        "frac_of_bound": bound_s / (ms_step * 1e-3),
+        "flops_per_step_no_reuse": nnz * (2 * q0 * r1 * q1 * r2 * 4 + 2 * q0 * q1 * r2 * q2 * 3),
+    }
+    kernel_share = {k: v["ms"] * v["launches_per_step"] for k, v in kern.items()}
+    tot_k = sum(kernel_share.values()) or 1.0
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = calibrated_cpu_baseline(shape)
+    line = {
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "rows_per_step_per_gpu": nnz,
+                   "l2": "4 rotating batches, 212 MB touched per step (> 126 MB L2)",
+                   "launch": "cuda_graph" if use_graph else "eager",
+                   "parallelism": "dp%d, replicated cores%s" % (
+                       world, ", NCCL all-reduce of d_cores per step" if world > 1 else "")},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(nnz * 8 + (nnz + 1) * 8), "d2h_bytes_per_step": 4,
+                "api": "TTEmbeddingBag.forward(indices, offsets) + loss.backward(), loss.item()",
+                "loss_last": losses[-1] if losses else None},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roofline,
+        "step_roofline": step_roofline,
+        "kernels_ms": {k: round(v["ms"], 5) for k, v in kern.items()},
+        "kernel_share": {k: round(v / tot_k, 4) for k, v in kernel_share.items()},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="products", choices=sorted(SHAPES))
+    ap.add_argument("--nnz", type=int, default=262144)
+    ap.add_argument("--cpu-rows", type=int, default=16384,
+                    help="rows per step of the --impl reference (CPU) arm")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    shape = SHAPES[args.shape]
+    if args.impl == "reference":
+        run_reference(args, shape)
+    else:
+        run_ours(args, shape)
+
+
+if __name__ == "__main__":
+    main()

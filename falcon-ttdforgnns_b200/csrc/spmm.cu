@@ -83,6 +83,45 @@ spmm_bwd_kernel(int64_t num_dst, int32_t F, const int64_t* __restrict__ indptr,
   }
 }
 
+// rows whose width is not a multiple of four floats (the 47-class output layer): scalar lanes
+__global__ void __launch_bounds__(256)
+spmm_fwd_scalar_kernel(int64_t num_dst, int32_t F, const int64_t* __restrict__ indptr,
+                       const int32_t* __restrict__ indices, const float* __restrict__ ew, int mean,
+                       const float* __restrict__ x, float* __restrict__ out) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= num_dst) return;
+  const int64_t e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  const float scale = (mean && e1 > e0) ? 1.0f / (float)(e1 - e0) : 1.0f;
+  for (int d = lane; d < F; d += 32) {
+    float acc = 0.f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const float w = ew ? __ldg(ew + e) : 1.0f;
+      acc = fmaf(w, __ldg(x + (int64_t)__ldg(indices + e) * F + d), acc);
+    }
+    out[v * F + d] = acc * scale;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+spmm_bwd_scalar_kernel(int64_t num_dst, int32_t F, const int64_t* __restrict__ indptr,
+                       const int32_t* __restrict__ indices, const float* __restrict__ ew, int mean,
+                       const float* __restrict__ dout, float* __restrict__ dx) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= num_dst) return;
+  const int64_t e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  if (e1 <= e0) return;
+  const float scale = mean ? 1.0f / (float)(e1 - e0) : 1.0f;
+  for (int d = lane; d < F; d += 32) {
+    const float g = __ldg(dout + v * F + d) * scale;
+    for (int64_t e = e0; e < e1; ++e) {
+      const float w = ew ? __ldg(ew + e) : 1.0f;
+      atomicAdd(dx + (int64_t)__ldg(indices + e) * F + d, w * g);
+    }
+  }
+}
+
 }  // namespace
 }  // namespace ttg
 
@@ -91,9 +130,15 @@ using namespace ttg;
 extern "C" int ttg_spmm_csr_fwd(int64_t num_dst, int32_t F, const int64_t* indptr,
                                 const int32_t* indices, const float* edge_weight, int32_t mean,
                                 const float* x, float* out, void* stream) {
-  TTG_CHECK_ARG(F > 0 && F % 4 == 0, "spmm_csr_fwd: F=%d must be a positive multiple of 4", F);
+  TTG_CHECK_ARG(F > 0, "spmm_csr_fwd: F=%d must be positive", F);
   if (num_dst == 0) return TTG_OK;
   TTG_CHECK_ARG(indptr && out, "spmm_csr_fwd: null pointer");
+  if (F % 4 != 0) {
+    spmm_fwd_scalar_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        num_dst, F, indptr, indices, edge_weight, mean, x, out);
+    TTG_LAUNCH_CHECK();
+    return TTG_OK;
+  }
   spmm_fwd_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       num_dst, F, indptr, indices, edge_weight, mean, x, out);
   TTG_LAUNCH_CHECK();
@@ -103,9 +148,15 @@ extern "C" int ttg_spmm_csr_fwd(int64_t num_dst, int32_t F, const int64_t* indpt
 extern "C" int ttg_spmm_csr_bwd(int64_t num_dst, int32_t F, const int64_t* indptr,
                                 const int32_t* indices, const float* edge_weight, int32_t mean,
                                 const float* dout, float* dx, void* stream) {
-  TTG_CHECK_ARG(F > 0 && F % 4 == 0, "spmm_csr_bwd: F=%d must be a positive multiple of 4", F);
+  TTG_CHECK_ARG(F > 0, "spmm_csr_bwd: F=%d must be positive", F);
   if (num_dst == 0) return TTG_OK;
   TTG_CHECK_ARG(indptr && dout && dx, "spmm_csr_bwd: null pointer");
+  if (F % 4 != 0) {
+    spmm_bwd_scalar_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        num_dst, F, indptr, indices, edge_weight, mean, dout, dx);
+    TTG_LAUNCH_CHECK();
+    return TTG_OK;
+  }
   spmm_bwd_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       num_dst, F, indptr, indices, edge_weight, mean, dout, dx);
   TTG_LAUNCH_CHECK();

@@ -1,0 +1,91 @@
+"""Data-parallel plumbing for replicated TT cores (north star: "replicated cores and the
+core-gradient allreduce over NCCL/NVLink").
+
+The reference wraps the whole model in DistributedDataParallel (sage_dgl_partition.py:235), which
+only all-reduces the cores when sparse=False; with the fused update (--sparse) its replicas would
+silently diverge.  Here the exchange step is explicit and is the ONLY collective
+on the path: one all-reduce (sum) over a flat fp32 buffer [d_core0 | d_core1 | d_core2 | extra],
+divided by the world size, followed by the identical optimizer step on every rank
+(ttg_apply_optimizer through the C ABI).  Works with the `nccl` backend on GPUs and with `gloo`
+on CPU tensors (the latter is what the CPU tests exercise; the update itself needs CUDA).
+"""
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+import _ttg
+
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous, balanced split of n work units (seed nodes / rows) over `world` ranks: the
+    first n % world ranks get one extra.  Same partitioning rule as DGL's use_ddp DataLoader
+    without drop_last (sage_dgl_partition.py:144-154)."""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def epoch_permutation(n: int, epoch: int, seed: int = 0) -> torch.Tensor:
+    """Same permutation on every rank for a given epoch (seeded), so the shards are disjoint."""
+    g = torch.Generator()
+    g.manual_seed(seed * 1000003 + epoch)
+    return torch.randperm(n, generator=g)
+
+
+def flatten(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
+    return torch.cat([t.reshape(-1) for t in tensors])
+
+
+def unflatten(flat: torch.Tensor, like: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    out, off = [], 0
+    for t in like:
+        out.append(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+    return out
+
+
+def allreduce_mean(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Tensor]:
+    """One collective for all tensors; returns views into the reduced flat buffer."""
+    flat = flatten(tensors)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(dist.get_world_size(group))
+    return unflatten(flat, tensors)
+
+
+def apply_optimizer(tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores: Sequence[torch.Tensor],
+                    d_cores: Sequence[torch.Tensor], learning_rate: float, optimizer: str = "sgd",
+                    eps: float = 1e-10, optimizer_state: Optional[Sequence[torch.Tensor]] = None):
+    """core -= lr * g (sgd) or the Adagrad rule, in place, on torch's current stream."""
+    cores = [c.data if isinstance(c, torch.nn.Parameter) else c for c in tt_cores]
+    for i, (c, g) in enumerate(zip(cores, d_cores)):
+        _ttg.require_cuda(c, "tt_cores[%d]" % i, torch.float32)
+        _ttg.require_cuda(g, "d_cores[%d]" % i, torch.float32)
+        if c.shape != g.shape:
+            raise RuntimeError("apply_optimizer: gradient %d has the wrong shape" % i)
+    num_tables = cores[0].size(0) if cores[0].dim() == 3 else 1
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
+    dev = cores[0].device
+    optim = _ttg.OPTIM_SGD if optimizer == "sgd" else _ttg.OPTIM_ADAGRAD
+    sp = None
+    if optim == _ttg.OPTIM_ADAGRAD:
+        sp = _ttg.ptr_array(optimizer_state)
+    with torch.cuda.device(dev):
+        cp, dp = _ttg.ptr_array(cores), _ttg.ptr_array(list(d_cores))
+        rc = _ttg.lib().ttg_apply_optimizer(C.byref(shape), optim, float(learning_rate), float(eps),
+                                            cp, sp, dp, _ttg.stream_of(dev))
+        _ttg.check(rc, "apply_optimizer")
+
+
+def dp_backward_step(module, d_cores: Sequence[torch.Tensor], group=None):
+    """All-reduce the dense core gradients of a TTEmbeddingBag and apply its own optimizer:
+    the data-parallel equivalent of the fused --sparse update."""
+    from FBTT.tt_embeddings_ops import OptimType
+    reduced = allreduce_mean(d_cores, group)
+    sgd = module.optimizer in (OptimType.SGD, OptimType.EXACT_SGD)
+    apply_optimizer(module.tt_p_shapes, module.tt_q_shapes, module.tt_ranks, list(module.tt_cores),
+                    reduced, module.learning_rate, "sgd" if sgd else "adagrad", module.eps,
+                    None if sgd else list(module.optimizer_state))
+    return reduced

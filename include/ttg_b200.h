@@ -205,7 +205,8 @@ int ttg_eff_backward_sgd(const ttg_shape* shape, int64_t batch, float lr,
  *           dglnn.GraphConv(norm='both') gnn_model.py:287 (DGL 2.1.0, un-vendored).
  * out[v][:] = scale_v * sum_{e in [indptr[v], indptr[v+1])} w_e * x[indices[e]][:]
  *   mean != 0: scale_v = 1/deg(v) (0 rows stay 0);  mean == 0: scale_v = 1
- *   edge_weight may be NULL (w_e = 1).  F % 4 == 0.
+ *   edge_weight may be NULL (w_e = 1).  F % 4 == 0 takes the 16-byte path, other widths
+ *   (the 47-class output layer) a scalar one.
  * The backward is the same kernel on the transposed CSR (built once per block by the
  * caller) or ttg_spmm_csr_bwd which scatters with vector reductions.
  * ---------------------------------------------------------------------------------- */

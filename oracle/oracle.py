@@ -97,6 +97,21 @@ def tt_forward_f32_rows(p, q, ranks, cores, indices):
     return out
 
 
+def tt_backward_f32_rows(p, q, ranks, cores, indices, d_output):
+    """fp32, one index per row: the backward half of the CPU baseline bench.py times."""
+    T = len(p)
+    r = _full_ranks(T, ranks)
+    indices = np.ascontiguousarray(indices, dtype=np.int64)
+    d_output = np.ascontiguousarray(d_output, dtype=np.float32)
+    cs, cp = _core_ptrs(cores)
+    outs = [np.zeros_like(c) for c in cs]
+    op = (C.POINTER(C.c_float) * T)(*[_p(o, C.c_float) for o in outs])
+    rc = lib().orc_tt_backward_f32_rows(T, _ia(p), _ia(q), _ia(r), C.c_int64(indices.size),
+                                        _p(indices, C.c_int64), _p(d_output, C.c_float), cp, op)
+    assert rc == 0
+    return outs
+
+
 def tt_backward_dense(p, q, ranks, cores, indices, rowidx, d_output, tableidx=None, num_tables=1):
     """Reference op tt_dense_backward: list of d_tt_cores (zeros_like + scatter-add)."""
     T = len(p)

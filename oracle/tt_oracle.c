@@ -249,6 +249,85 @@ int orc_tt_backward_dense(int T, int num_tables, const int* p, const int* q, con
   return 0;
 }
 
+/* fp32 backward for the timed CPU baseline: one index per row (rowidx[n] = n), one table, float
+ * arithmetic like the reference's fp32 GEMMs, thread-private gradient copies instead of
+ * atomics.  Same maths as orc_tt_backward_dense. */
+int orc_tt_backward_f32_rows(int T, const int* p, const int* q, const int* r, int64_t nnz,
+                             const int64_t* indices, const float* d_output,
+                             const float* const* cores, float* const* d_cores) {
+  shape_t s;
+  make_shape(&s, T, 1, p, q, r);
+  size_t csz[MAXT], ctot = 0, coff[MAXT];
+  for (int t = 0; t < T; ++t) {
+    csz[t] = (size_t)s.p[t] * s.cols[t];
+    coff[t] = ctot;
+    ctot += csz[t];
+  }
+  for (int t = 0; t < T; ++t) memset(d_cores[t], 0, sizeof(float) * csz[t]);
+#pragma omp parallel
+  {
+    float* X[MAXT];
+    size_t maxlen = 0;
+    for (int t = 0; t < T; ++t) {
+      X[t] = (float*)malloc(sizeof(float) * x_len(&s, t));
+      if (x_len(&s, t) > maxlen) maxlen = x_len(&s, t);
+    }
+    float* dA = (float*)malloc(sizeof(float) * maxlen);
+    float* dB = (float*)malloc(sizeof(float) * maxlen);
+    float* priv = (float*)calloc(ctot, sizeof(float));
+#pragma omp for schedule(static)
+    for (int64_t n = 0; n < nnz; ++n) {
+      int it[MAXT];
+      split_index(&s, indices[n], it);
+      memcpy(X[0], cores[0] + (int64_t)it[0] * s.cols[0], sizeof(float) * s.cols[0]);
+      int m = s.q[0];
+      for (int t = 1; t < T - 1; ++t) {
+        const int k = s.r[t], nn = s.q[t] * s.r[t + 1];
+        const float* c = cores[t] + (int64_t)it[t] * s.cols[t];
+        for (int a = 0; a < m; ++a) {
+          for (int b = 0; b < nn; ++b) X[t][a * nn + b] = 0.f;
+          for (int kk = 0; kk < k; ++kk) {
+            const float xv = X[t - 1][a * k + kk];
+            for (int b = 0; b < nn; ++b) X[t][a * nn + b] += xv * c[kk * nn + b];
+          }
+        }
+        m *= s.q[t];
+      }
+      memcpy(dA, d_output + n * s.D, sizeof(float) * s.D);
+      float *dcur = dA, *dnxt = dB;
+      for (int t = T - 1; t >= 1; --t) {
+        const int k = s.r[t], nn = s.q[t] * s.r[t + 1];
+        const float* c = cores[t] + (int64_t)it[t] * s.cols[t];
+        float* gd = priv + coff[t] + (size_t)it[t] * s.cols[t];
+        for (int a = 0; a < m; ++a)
+          for (int kk = 0; kk < k; ++kk) {
+            const float xv = X[t - 1][a * k + kk];
+            float acc = 0.f;
+            for (int b = 0; b < nn; ++b) {
+              gd[kk * nn + b] += xv * dcur[a * nn + b];
+              acc += dcur[a * nn + b] * c[kk * nn + b];
+            }
+            dnxt[a * k + kk] = acc;
+          }
+        float* tmp = dcur;
+        dcur = dnxt;
+        dnxt = tmp;
+        if (t > 1) m /= s.q[t - 1];
+      }
+      float* g0 = priv + coff[0] + (size_t)it[0] * s.cols[0];
+      for (int o = 0; o < s.cols[0]; ++o) g0[o] += dcur[o];
+    }
+#pragma omp critical
+    for (int t = 0; t < T; ++t)
+      for (size_t i = 0; i < csz[t]; ++i) d_cores[t][i] += priv[coff[t] + i];
+    free(priv);
+    free(dA);
+    free(dB);
+    for (int t = 0; t < T; ++t) free(X[t]);
+  }
+  return 0;
+}
+
 /* update_tt_cores_sgd_kernel / update_tt_cores_adagrad_kernel formulas
  * FBTT/tt_embeddings_cuda.cu:381-419, on every element (SURVEY.md 8a-6 documents that the
  * reference's launch skips tail rows; rows_limit reproduces that: only rows < rows_limit[t] of

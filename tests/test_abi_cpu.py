@@ -58,7 +58,7 @@ def test_validation_errors_are_reported_without_a_gpu(ttg_lib):
     assert rc == 0                                            # size query refuses bad shapes
     rc = lib.ttg_cache_forward(4, 10, None, None, None, None, None)
     assert rc == -1 and b"multiple of 4" in lib.ttg_last_error()
-    rc = lib.ttg_spmm_csr_fwd(4, 6, None, None, None, 1, None, None, None)
+    rc = lib.ttg_spmm_csr_fwd(4, 0, None, None, None, 1, None, None, None)
     assert rc == -1
     n_tt = ctypes.c_int32(-7)
     rc = lib.ttg_preprocess_indices(0, 1, None, None, 1, 1, 0, None, None, None, None, None, None,
