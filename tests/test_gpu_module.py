@@ -49,7 +49,8 @@ def test_forward_equals_embedding_bag_and_dense_grads_equal_autograd(ttg_lib, cf
     W = m.full_weight()
     ref = torch.nn.functional.embedding_bag(indices, W, offsets, mode="sum", include_last_offset=True)
     assert out.shape == ref.shape
-    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    # 1e-5 relative to the scale of the table (bag sums cancel, so not elementwise-relative)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
     d_out = torch.rand_like(out) * 0.1
     out.backward(d_out)
     cores64 = [c.detach().double().requires_grad_(True) for c in m.tt_cores]
