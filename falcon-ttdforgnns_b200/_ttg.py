@@ -15,7 +15,7 @@ _lib = None
 
 TTG_MAX_CORES = 4
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
-FLAG_FORCE_GENERIC, FLAG_PLAN_VALID = 1, 2
+FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC = 1, 2, 4
 
 
 class Shape(C.Structure):
@@ -156,6 +156,9 @@ class _Workspace:
 workspace = _Workspace()
 
 
-def plan_key_of(tag, indices, rowidx, nnz, B, shape_tuple):
+def plan_key_of(tag, indices, rowidx, nnz, B, shape_tuple, cores=()):
+    """Identity of an index plan + group table: the index tensors (address and version counter),
+    the sizes, the table shape and the cores the group table was computed from."""
     return (tag, indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version,
-            int(nnz), int(B), shape_tuple)
+            int(nnz), int(B), shape_tuple,
+            tuple((c.data_ptr(), c._version) for c in cores))

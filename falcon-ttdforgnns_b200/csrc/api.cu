@@ -34,7 +34,8 @@ int g_nalloc[K_COUNT];
 const char* kKernelNames[K_COUNT] = {"plan_kernel",       "radix_sort",        "zero_rows_kernel",
                                      "sorted_fwd_kernel", "sorted_bwd_rows_kernel",
                                      "sorted_bwd_cores_kernel", "reduce_partials_kernel",
-                                     "optimizer_kernel",  "generic_fwd_kernel", "generic_bwd_kernel"};
+                                     "optimizer_kernel",  "generic_fwd_kernel", "generic_bwd_kernel",
+                                     "group_table_kernel"};
 }  // namespace
 
 void prof_begin(int id, cudaStream_t s) {
@@ -94,19 +95,23 @@ int tt_forward_dispatch(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* 
                         const int64_t* rowidx, const int64_t* tableidx, float* output, void* ws,
                         size_t ws_bytes, int32_t flags, cudaStream_t stream) {
   if (!(flags & TTG_FLAG_FORCE_GENERIC) && sorted_supported(tt))
-    return sorted_forward(tt, B, nnz, indices, rowidx, tableidx, output, ws, ws_bytes,
-                          (flags & TTG_FLAG_PLAN_VALID) != 0, stream);
+    return sorted_forward(tt, B, nnz, indices, rowidx, tableidx, output, ws, ws_bytes, flags,
+                          stream);
   return generic_forward(tt, B, nnz, indices, rowidx, tableidx, output, stream);
 }
 
+// dense gradients + optimizer step (fused into the last kernel on the sorted path)
 static int tt_backward_dispatch(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                                 const int64_t* rowidx, const int64_t* tableidx,
-                                const float* d_output, float* const* dcore, void* ws,
-                                size_t ws_bytes, int32_t flags, cudaStream_t stream) {
+                                const float* d_output, float* const* dcore, int32_t optim, float lr,
+                                float eps, float* const* state, void* ws, size_t ws_bytes,
+                                int32_t flags, cudaStream_t stream) {
   if (!(flags & TTG_FLAG_FORCE_GENERIC) && sorted_supported(tt))
-    return sorted_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, ws, ws_bytes,
-                           (flags & TTG_FLAG_PLAN_VALID) != 0, stream);
-  return generic_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, stream);
+    return sorted_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, optim, lr, eps,
+                           state, ws, ws_bytes, flags, stream);
+  int rc = generic_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, stream);
+  if (rc != TTG_OK || nnz == 0) return rc;  // FBTT/tt_embeddings_cuda.cu:450-452: no update
+  return apply_optimizer(tt, optim, lr, eps, dcore, state, stream);
 }
 
 namespace {
@@ -240,11 +245,10 @@ extern "C" int ttg_tt_backward(const ttg_shape* shape, int32_t optim, float lr, 
     TTG_CHECK_ARG(tt.core[t] != nullptr, "tt_backward: null core %d", t);
     TTG_CHECK_ARG(host_dcore_ptrs[t] != nullptr, "tt_backward: null d_core %d", t);
   }
-  rc = tt_backward_dispatch(tt, B, nnz, indices, rowidx, tableidx, d_output, host_dcore_ptrs,
-                            workspace, workspace_bytes, flags, stream);
-  if (rc != TTG_OK) return rc;
-  if (nnz == 0) return TTG_OK;  // FBTT/tt_embeddings_cuda.cu:450-452 returns before the update
-  return apply_optimizer(tt, optim, lr, eps, host_dcore_ptrs, host_state_ptrs, stream);
+  if (optim == TTG_OPTIM_ADAGRAD)
+    TTG_CHECK_ARG(host_state_ptrs != nullptr, "tt_backward: adagrad needs optimizer_state");
+  return tt_backward_dispatch(tt, B, nnz, indices, rowidx, tableidx, d_output, host_dcore_ptrs, optim,
+                              lr, eps, host_state_ptrs, workspace, workspace_bytes, flags, stream);
 }
 
 extern "C" size_t ttg_eff_workspace_bytes(const ttg_shape* shape, int64_t batch) {
@@ -296,8 +300,6 @@ extern "C" int ttg_eff_backward_sgd(const ttg_shape* shape, int64_t batch, float
     eff_iota_kernel<<<(unsigned)ceil_div(batch, 256), 256, 0, stream>>>(batch, w.rowidx, w.tableidx);
     TTG_LAUNCH_CHECK();
   }
-  rc = tt_backward_dispatch(tt, batch, batch, indices, w.rowidx, w.tableidx, d_output, w.dcore,
-                            w.tt_ws, w.tt_bytes, flags, stream);
-  if (rc != TTG_OK) return rc;
-  return apply_optimizer(tt, TTG_OPTIM_SGD, lr, 0.f, w.dcore, nullptr, stream);
+  return tt_backward_dispatch(tt, batch, batch, indices, w.rowidx, w.tableidx, d_output, w.dcore,
+                              TTG_OPTIM_SGD, lr, 0.f, nullptr, w.tt_ws, w.tt_bytes, flags, stream);
 }

@@ -53,7 +53,7 @@ void count_launch(int n = 1);
 // ---- optional per-kernel timing (CUDA events on the launching stream), api.cu ------------
 enum KernelId {
   K_PLAN = 0, K_SORT, K_ZERO_ROWS, K_FWD, K_BWD_ROWS, K_BWD_CORES, K_REDUCE, K_OPTIM,
-  K_GENERIC_FWD, K_GENERIC_BWD, K_COUNT
+  K_GENERIC_FWD, K_GENERIC_BWD, K_TABLE, K_COUNT
 };
 void prof_begin(int id, cudaStream_t s);
 void prof_end(int id, cudaStream_t s);
@@ -112,10 +112,11 @@ bool sorted_supported(const TTDev& tt);
 size_t sorted_workspace_bytes(const TTDev& tt, int64_t B, int64_t nnz);
 int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                    const int64_t* rowidx, const int64_t* tableidx, float* output, void* ws,
-                   size_t ws_bytes, bool plan_valid, cudaStream_t stream);
+                   size_t ws_bytes, int32_t flags, cudaStream_t stream);
+// dense gradients into dcore AND the optimizer step (optim/lr/eps/state), fused in the last kernel
 int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                     const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
-                    float* const* dcore, void* ws, size_t ws_bytes, bool plan_valid,
-                    cudaStream_t stream);
+                    float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
+                    void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream);
 
 }  // namespace ttg

@@ -33,14 +33,26 @@ namespace {
 
 constexpr int kFwdThreads = 256;
 constexpr int kFwdRows = 4;          // rows of one group in flight per warp
-constexpr int kBwdThreads = 256;
-constexpr int kBwdCtasPerSM = 3;
+constexpr int kBwdThreads = 768;    // one CTA per SM: one shared-memory copy of d_core2 per SM
+constexpr int kBwdCtasPerSM = 1;
 constexpr int kBwdGrid = kNumSMs * kBwdCtasPerSM;
-constexpr int kBwdChunkRows = 64;
+constexpr int kBwdMinChunkRows = 32;
 constexpr int kBwdStages = 3;        // cp.async ring depth (row steps)
-constexpr size_t kSmemAccLimit = 64 * 1024;   // per-CTA copy of d_core2 (3 CTAs per SM)
+constexpr size_t kSmemAccLimit = 128 * 1024;  // per-CTA copy of d_core2 (1 CTA per SM)
 constexpr size_t kSmemCore2Limit = 64 * 1024; // per-CTA copy of core2 in the forward
 constexpr uint32_t kInvalid = 0xffffffffu;
+constexpr int kCoreSplit = 4;        // split of the reduction axis in the cores kernel
+
+// Strategy: when most groups of the table are touched (ogbn-products: 17.5k groups, 262k rows)
+// tr0 of EVERY group is produced once per step by a dense kernel into an L2-resident table
+// (22 MB at products) and the row kernels just read their group's slice; when the batch is
+// sparse in groups (papers100M) tr0 is computed inside the row kernels, once per group run.
+inline bool use_group_table(const TTDev& tt, int64_t nnz) {
+  const double groups = (double)tt.num_tables * tt.p[0] * tt.p[1];
+  const double cost_group = 2.0 * tt.q[0] * tt.r[1] * tt.q[1] * tt.r[2];
+  const double cost_row = 2.0 * tt.q[0] * tt.q[1] * tt.r[2] * tt.q[2];
+  return (tt.q[0] * tt.q[1]) % 2 == 0 && tt.r[2] <= 16 && 2.0 * groups * cost_group <= (double)nnz * cost_row;
+}
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
@@ -63,7 +75,11 @@ struct SortedWs {
   int32_t* rowcount;   // [tables * B] occurrences of each output row
   uint8_t* touched;    // [tables * p0 * p1]
   float* S;            // [tables * p0 * p1][q0 q1 r2]
+  float* Ttab;         // [tables * p0 * p1][q0 q1 r2]  tr0 of every group (dense strategy)
   float* partials;     // [kBwdGrid][tables * p2 * cols2] or nullptr
+  float* cparts;       // [kCoreSplit][core0 + core1 elements]
+  int32_t* cnt;        // [groups + 1] bucket counters / cursors
+  int32_t* base;       // [groups + 1] bucket starts
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -88,6 +104,14 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
   w.rowcount = (int32_t*)take(sizeof(int32_t) * (size_t)tt.num_tables * (size_t)(B > 0 ? B : 1));
   w.touched = (uint8_t*)take(groups);
   w.S = (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]));
+  w.Ttab = use_group_table(tt, nnz)
+               ? (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]))
+               : nullptr;
+  w.cparts = (float*)take(sizeof(float) * kCoreSplit *
+                          ((size_t)tt.num_tables * tt.p[0] * tt.cols[0] +
+                           (size_t)tt.num_tables * tt.p[1] * tt.cols[1]));
+  w.cnt = (int32_t*)take(sizeof(int32_t) * (groups + 1));
+  w.base = (int32_t*)take(sizeof(int32_t) * (groups + 1));
   w.smem_acc = (core2 * sizeof(float) <= kSmemAccLimit);
   w.partials = w.smem_acc ? (float*)take(sizeof(float) * core2 * kBwdGrid) : nullptr;
   w.cub_bytes = 0;
@@ -101,20 +125,145 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
 // ------------------------------------------------------------------------------------
 // plan: keys, output rows and row occurrence counts
 // ------------------------------------------------------------------------------------
+constexpr int kPlanItems = 4;   // rows per thread: independent loads / atomics in flight
+
 __global__ void __launch_bounds__(256)
 plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32_t total_rows,
             const int64_t* __restrict__ indices, const int64_t* __restrict__ rowidx,
             const int64_t* __restrict__ tableidx, uint32_t* __restrict__ keys,
-            int32_t* __restrict__ vals, int32_t* __restrict__ rowcount) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= nnz) return;
-  const int64_t idx = __ldg(indices + n);
-  const int64_t t = __ldg(tableidx + n);
-  const int64_t row = __ldg(rowidx + n);
-  const bool ok = idx >= 0 && idx < num_rows && t >= 0 && t < num_tables && row >= 0 && row < B;
-  keys[n] = ok ? (uint32_t)(t * num_rows + idx) : total_rows;  // invalid -> sorts to the end
-  vals[n] = ok ? (int32_t)(t * B + row) : 0;
-  if (ok) atomicAdd(rowcount + t * B + row, 1);
+            int32_t* __restrict__ vals, int32_t* __restrict__ rowcount, int32_t* __restrict__ cnt,
+            uint32_t p2, int32_t num_groups) {
+  const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
+  int64_t idx[kPlanItems], t[kPlanItems], row[kPlanItems];
+#pragma unroll
+  for (int k = 0; k < kPlanItems; ++k) {
+    const int64_t n = n0 + k * 256;
+    idx[k] = (n < nnz) ? __ldg(indices + n) : 0;
+    t[k] = (n < nnz) ? __ldg(tableidx + n) : 0;
+    row[k] = (n < nnz) ? __ldg(rowidx + n) : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < kPlanItems; ++k) {
+    const int64_t n = n0 + k * 256;
+    if (n >= nnz) continue;
+    const bool ok = idx[k] >= 0 && idx[k] < num_rows && t[k] >= 0 && t[k] < num_tables &&
+                    row[k] >= 0 && row[k] < B;
+    const uint32_t key = ok ? (uint32_t)(t[k] * num_rows + idx[k]) : total_rows;  // invalid -> end
+    keys[n] = key;
+    vals[n] = ok ? (int32_t)(t[k] * B + row[k]) : 0;
+    if (ok) atomicAdd(rowcount + t[k] * B + row[k], 1);
+    if (cnt) atomicAdd(cnt + (ok ? key / p2 : num_groups), 1);  // bucket plan: rows per group
+  }
+}
+
+// exclusive scan of the bucket counters (single CTA, 8 counters per thread and pass); the
+// counters are cleared so that the scatter can reuse them as cursors
+__global__ void __launch_bounds__(1024)
+bucket_scan_kernel(int32_t n, int32_t* __restrict__ cnt, int32_t* __restrict__ base) {
+  constexpr int IPT = 8;
+  __shared__ int32_t warp_tot[32];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int32_t b0 = 0; b0 < n; b0 += 1024 * IPT) {
+    const int32_t i = b0 + threadIdx.x * IPT;
+    int32_t v[IPT];
+    int32_t tot = 0;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      v[k] = (i + k < n) ? cnt[i + k] : 0;
+      tot += v[k];
+    }
+    int32_t x = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int32_t t = warp_tot[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (threadIdx.x >= o) t += y;
+      }
+      warp_tot[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int32_t warp_excl = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
+    const int32_t incl = carry + warp_excl + x;
+    int32_t run = incl - tot;
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      if (i + k < n) {
+        base[i + k] = run;
+        cnt[i + k] = 0;
+      }
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = incl;
+    __syncthreads();
+  }
+}
+
+// rows of one group become adjacent (order inside a group is arbitrary: nothing depends on it)
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num_groups,
+                      const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals,
+                      const int32_t* __restrict__ base, int32_t* __restrict__ cursor,
+                      uint32_t* __restrict__ skeys, int32_t* __restrict__ srow) {
+  const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
+  uint32_t key[kPlanItems];
+  int32_t val[kPlanItems], g[kPlanItems], pos[kPlanItems];
+#pragma unroll
+  for (int k = 0; k < kPlanItems; ++k) {
+    const int64_t n = n0 + k * 256;
+    key[k] = (n < nnz) ? keys[n] : total_rows;
+    val[k] = (n < nnz) ? vals[n] : 0;
+    g[k] = key[k] < total_rows ? (int32_t)(key[k] / p2) : num_groups;
+  }
+#pragma unroll
+  for (int k = 0; k < kPlanItems; ++k)
+    pos[k] = (n0 + k * 256 < nnz) ? __ldg(base + g[k]) + atomicAdd(cursor + g[k], 1) : 0;
+#pragma unroll
+  for (int k = 0; k < kPlanItems; ++k) {
+    if (n0 + k * 256 < nnz) {
+      skeys[pos[k]] = key[k];
+      srow[pos[k]] = val[k];
+    }
+  }
+}
+
+// tr0 of every group: Ttab[(t, i0, i1)][j0, (j1 k2)] = sum_k1 core0[i0][j0, k1] core1[i1][k1, (j1 k2)]
+// CTA = (table, i1), thread = (j0, column): core1[i1] stays in registers across the i0 loop.
+template <int Q0, int Q1, int R1, int R2>
+__global__ void __launch_bounds__(Q0 * Q1 * R2)
+group_table_kernel(TTDev tt, float* __restrict__ Ttab) {
+  constexpr int C = Q1 * R2;
+  const int p0 = tt.p[0], p1 = tt.p[1];
+  const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
+  const int c = threadIdx.x % C, j0 = threadIdx.x / C;
+  const float* b1 = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C) + c;
+  float b[R1];
+#pragma unroll
+  for (int k1 = 0; k1 < R1; ++k1) b[k1] = __ldg(b1 + k1 * C);
+#pragma unroll 4
+  for (int i0 = blockIdx.y; i0 < p0; i0 += gridDim.y) {
+    const float* a0 = tt.core[0] + ((size_t)tix * p0 + i0) * (Q0 * R1) + j0 * R1;
+    float t = 0.f;
+#pragma unroll
+    for (int v = 0; v < R1 / 4; ++v) {
+      const float4 x = ldg4(a0 + 4 * v);
+      t = fmaf(x.x, b[4 * v], t);
+      t = fmaf(x.y, b[4 * v + 1], t);
+      t = fmaf(x.z, b[4 * v + 2], t);
+      t = fmaf(x.w, b[4 * v + 3], t);
+    }
+    Ttab[(((size_t)tix * p0 + i0) * p1 + i1) * (Q0 * C) + threadIdx.x] = t;
+  }
 }
 
 // rows that are not written by exactly one index start from zero (empty bags stay zero,
@@ -317,15 +466,184 @@ sorted_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __
 }
 
 // ------------------------------------------------------------------------------------
+// forward, dense strategy: tr0 comes from the group table.  Two rows (j0 j1) of tr0 per lane,
+// so a row of the output needs only A/2 lanes (10 at products, 8 at D = 128) and three / four
+// consecutive sorted rows run side by side in one warp; each 16-byte load of core2 from shared
+// memory feeds 8 FFMAs.
+// ------------------------------------------------------------------------------------
+template <int Q0, int Q1, int Q2, int R2, bool C2_SMEM>
+__global__ void __launch_bounds__(kFwdThreads)
+table_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
+                 const int32_t* __restrict__ srow, const int32_t* __restrict__ rowcount,
+                 const float* __restrict__ Ttab, float* __restrict__ output, int rows_per_warp,
+                 int core2_elems) {
+  constexpr int A = Q0 * Q1;
+  constexpr int LPR = A / 2;       // lanes per output row
+  constexpr int RPW = 32 / LPR;    // rows per warp step
+  constexpr int D = A * Q2;
+  constexpr int COLS2 = R2 * Q2;
+  // rows of core2 are padded by 4 floats in shared memory: the RPW sub-warps read RPW different
+  // rows with one LDS.128, a 320-byte stride would put every other row on the same banks
+  constexpr int C2S = C2_SMEM ? COLS2 + 4 : COLS2;
+  constexpr bool kDirect = (Q2 % 4 == 0);
+  static_assert(A % 2 == 0 && R2 % 4 == 0 && COLS2 % 4 == 0 && D % 4 == 0, "layout");
+  extern __shared__ __align__(16) float smem[];
+  float* c2s = smem;
+  const int c2_rows = core2_elems / COLS2;
+  float* stage = smem + (C2_SMEM ? c2_rows * C2S : 0);           // [warps][RPW][D] if !kDirect
+
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  if (C2_SMEM) {
+    for (int i = threadIdx.x; i < core2_elems / 4; i += kFwdThreads) {
+      const int row = i / (COLS2 / 4), c4 = i - row * (COLS2 / 4);
+      *reinterpret_cast<float4*>(c2s + row * C2S + 4 * c4) = ldg4(tt.core[2] + 4 * i);
+    }
+    __syncthreads();
+  }
+  const float* c2base = C2_SMEM ? c2s : tt.core[2];
+  const int64_t gw = (int64_t)blockIdx.x * (kFwdThreads / 32) + wib;
+  const int sub = lane / LPR;
+  const int l = lane % LPR;
+  const bool lane_on = sub < RPW;
+  const uint32_t p2 = tt.p[2];
+  const uint32_t num_rows32 = (uint32_t)tt.num_rows;
+  float* my_stage = stage + (kDirect ? 0 : wib * RPW * D);
+
+  const int64_t s_begin = gw * rows_per_warp;
+  const int64_t s_end = (s_begin + rows_per_warp < nnz) ? s_begin + rows_per_warp : nnz;
+  if (s_begin >= s_end) return;
+
+  float T[2][R2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int i = 0; i < R2; ++i) T[u][i] = 0.f;
+  uint32_t g_held = kInvalid;
+
+  uint32_t nkey = total_rows;
+  int32_t ngrow = 0;
+  {
+    const int64_t my = s_begin + lane;
+    if (my < s_end) {
+      nkey = __ldg(skeys + my);
+      ngrow = __ldg(srow + my);
+    }
+  }
+  for (int64_t w0 = s_begin; w0 < s_end; w0 += 32) {
+    const uint32_t key = nkey;
+    const int32_t grow = ngrow;
+    {
+      const int64_t my = w0 + 32 + lane;
+      nkey = total_rows;
+      ngrow = 0;
+      if (my < s_end) {
+        nkey = __ldg(skeys + my);
+        ngrow = __ldg(srow + my);
+      }
+    }
+    const bool kvalid = key < total_rows;
+    const uint32_t gid = kvalid ? key / p2 : kInvalid;
+    const int c2row = kvalid ? (int)((key / num_rows32) * p2 + (key - gid * p2)) : 0;
+    const int one = kvalid ? (__ldg(rowcount + grow) == 1) : 0;
+    const int nrows = (int)((s_end - w0 < 32) ? (s_end - w0) : 32);
+    for (int it = 0; it < nrows; it += RPW) {
+      const int src = it + sub;
+      const uint32_t g = __shfl_sync(0xffffffffu, gid, src & 31);
+      const int c2r = __shfl_sync(0xffffffffu, c2row, src & 31);
+      const int64_t gr = __shfl_sync(0xffffffffu, grow, src & 31);
+      const int single = __shfl_sync(0xffffffffu, one, src & 31);
+      const bool valid = lane_on && src < nrows && g != kInvalid;
+      if (valid && g != g_held) {
+        g_held = g;
+        const float* tp = Ttab + (size_t)g * (A * R2) + l * R2;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < R2 / 4; ++v) {
+            const float4 x = ldg4(tp + u * (LPR * R2) + 4 * v);
+            T[u][4 * v] = x.x;
+            T[u][4 * v + 1] = x.y;
+            T[u][4 * v + 2] = x.z;
+            T[u][4 * v + 3] = x.w;
+          }
+      }
+      const float* c2p = c2base + (size_t)(valid ? c2r : 0) * C2S;
+      float acc[2][Q2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < Q2; ++j) acc[u][j] = 0.f;
+#pragma unroll
+      for (int v = 0; v < COLS2 / 4; ++v) {
+        const float4 c = C2_SMEM ? *reinterpret_cast<const float4*>(c2p + 4 * v) : ldg4(c2p + 4 * v);
+        const float ce[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int f = 4 * v + e;
+          acc[0][f % Q2] = fmaf(T[0][f / Q2], ce[e], acc[0][f % Q2]);
+          acc[1][f % Q2] = fmaf(T[1][f / Q2], ce[e], acc[1][f % Q2]);
+        }
+      }
+      if constexpr (kDirect) {
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float* o = output + gr * D + (l + u * LPR) * Q2;
+#pragma unroll
+            for (int v = 0; v < Q2 / 4; ++v) {
+              const float4 x =
+                  make_float4(acc[u][4 * v], acc[u][4 * v + 1], acc[u][4 * v + 2], acc[u][4 * v + 3]);
+              if (single)
+                st_cs_v4(o + 4 * v, x);
+              else
+                red_add_v4(o + 4 * v, x);
+            }
+          }
+        }
+      } else {
+        if (valid) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < Q2; ++j) my_stage[sub * D + (l + u * LPR) * Q2 + j] = acc[u][j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < RPW; ++h) {
+          const int srch = (it + h) & 31;
+          const uint32_t gh = __shfl_sync(0xffffffffu, gid, srch);
+          const int64_t grh = __shfl_sync(0xffffffffu, grow, srch);
+          const int sh = __shfl_sync(0xffffffffu, one, srch);
+          if (it + h < nrows && gh != kInvalid) {
+            for (int c = lane; c < D / 4; c += 32) {
+              const float4 x = *reinterpret_cast<const float4*>(my_stage + h * D + 4 * c);
+              float* o = output + grh * D + 4 * c;
+              if (sh)
+                st_cs_v4(o, x);
+              else
+                red_add_v4(o, x);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
 // backward, rows kernel
 // ------------------------------------------------------------------------------------
-template <int Q0, int Q1, int Q2, int R1, int R2, bool SMEM_ACC>
+template <int Q0, int Q1, int Q2, int R1, int R2, bool SMEM_ACC, bool TTAB>
 __global__ void __launch_bounds__(kBwdThreads)
 sorted_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows,
                        const uint32_t* __restrict__ skeys, const int32_t* __restrict__ srow,
-                       const float* __restrict__ d_output, float* __restrict__ Sbuf,
+                       const float* __restrict__ d_output, const float* __restrict__ Ttab,
+                       float* __restrict__ Sbuf,
                        uint8_t* __restrict__ touched,
-                       float* __restrict__ acc_dst /* partials or d_core2 */, int core2_elems) {
+                       float* __restrict__ acc_dst /* partials or d_core2 */, int core2_elems,
+                       int chunk_rows) {
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int LPR = R2;        // lane = k2
@@ -350,13 +668,13 @@ sorted_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows,
   float* ring = ring_all + (size_t)wib * NST * RPW * D;
   const uint32_t p0 = tt.p[0], p1 = tt.p[1], p2 = tt.p[2];
   const uint32_t num_rows32 = (uint32_t)tt.num_rows;
-  const int64_t nchunks = (nnz + kBwdChunkRows - 1) / kBwdChunkRows;
+  const int64_t nchunks = (nnz + chunk_rows - 1) / chunk_rows;
   const int64_t gw = (int64_t)blockIdx.x * (kBwdThreads / 32) + wib;
   const int64_t nw = (int64_t)gridDim.x * (kBwdThreads / 32);
 
   for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
-    const int64_t nom_begin = chunk * kBwdChunkRows;
-    const int64_t nom_end = (nom_begin + kBwdChunkRows < nnz) ? nom_begin + kBwdChunkRows : nnz;
+    const int64_t nom_begin = chunk * chunk_rows;
+    const int64_t nom_end = (nom_begin + chunk_rows < nnz) ? nom_begin + chunk_rows : nnz;
     int64_t s = nom_begin;
     if (chunk > 0) {
       // groups are owned by the chunk in which they START: skip the tail of the previous one
@@ -450,27 +768,33 @@ sorted_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows,
       for (int st = 0; st < NST - 1; ++st) issue(st);
       if (boundary) {
         // ---- tr0[:, k2] for this group (lane = k2); overlaps with the copies above
-        const uint32_t c0row = g_cur / p1;
-        const uint32_t i1 = g_cur - c0row * p1;
-        const float* a0p = tt.core[0] + (size_t)c0row * (Q0 * R1);
-        const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * Q1 * R2) + k2;
+        if (TTAB) {
+          const float* tp = Ttab + (size_t)g_cur * (A * R2) + k2;
 #pragma unroll
-        for (int j1 = 0; j1 < Q1; ++j1) {
-          float b[R1];
+          for (int i = 0; i < A; ++i) T[i] = __ldg(tp + i * R2);
+        } else {
+          const uint32_t c0row = g_cur / p1;
+          const uint32_t i1 = g_cur - c0row * p1;
+          const float* a0p = tt.core[0] + (size_t)c0row * (Q0 * R1);
+          const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * Q1 * R2) + k2;
 #pragma unroll
-          for (int k1 = 0; k1 < R1; ++k1) b[k1] = __ldg(b1p + k1 * (Q1 * R2) + j1 * R2);
+          for (int j1 = 0; j1 < Q1; ++j1) {
+            float b[R1];
 #pragma unroll
-          for (int j0 = 0; j0 < Q0; ++j0) {
-            float t = 0.f;
+            for (int k1 = 0; k1 < R1; ++k1) b[k1] = __ldg(b1p + k1 * (Q1 * R2) + j1 * R2);
 #pragma unroll
-            for (int v = 0; v < R1 / 4; ++v) {
-              const float4 x = ldg4(a0p + j0 * R1 + 4 * v);
-              t = fmaf(x.x, b[4 * v], t);
-              t = fmaf(x.y, b[4 * v + 1], t);
-              t = fmaf(x.z, b[4 * v + 2], t);
-              t = fmaf(x.w, b[4 * v + 3], t);
+            for (int j0 = 0; j0 < Q0; ++j0) {
+              float t = 0.f;
+#pragma unroll
+              for (int v = 0; v < R1 / 4; ++v) {
+                const float4 x = ldg4(a0p + j0 * R1 + 4 * v);
+                t = fmaf(x.x, b[4 * v], t);
+                t = fmaf(x.y, b[4 * v + 1], t);
+                t = fmaf(x.z, b[4 * v + 2], t);
+                t = fmaf(x.w, b[4 * v + 3], t);
+              }
+              T[j0 * Q1 + j1] = t;
             }
-            T[j0 * Q1 + j1] = t;
           }
         }
 #pragma unroll
@@ -530,176 +854,235 @@ sorted_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows,
 // backward, cores kernel: dense reductions over the touched groups
 //   blocks [0, tables*p1)            : d_core1[i1][k1, c] = sum_i0 sum_j0 core0[i0][j0,k1] S[i0,i1][j0,c]
 //   blocks [tables*p1, +tables*p0)   : d_core0[i0][j0,k1] = sum_i1 sum_c  S[i0,i1][j0,c] core1[i1][k1,c]
-// thread = (column c of [q1 r2], slab of k1); the loop over the other index is unrolled by four
-// with predicated loads so that four groups are in flight per thread.
+// blockIdx.y owns a slice of the reduction axis and writes its own partial copy (summed by the
+// finalize kernel).  thread = (column c of [q1 r2], lane sl of 4 over the reduction index); the
+// per-thread partial sums meet in shared memory.
 // ------------------------------------------------------------------------------------
 template <int Q0, int Q1, int Q2, int R1, int R2>
 __global__ void __launch_bounds__(4 * Q1 * R2)
 sorted_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf,
                         const uint8_t* __restrict__ touched, float* __restrict__ dcore0,
-                        float* __restrict__ dcore1) {
+                        float* __restrict__ dcore1, size_t part_stride) {
   constexpr int A = Q0 * Q1;
-  constexpr int C = Q1 * R2;   // columns of tr0
-  constexpr int KS = R1 / 4;   // k1 values per thread
+  constexpr int C = Q1 * R2;               // columns of tr0
   constexpr int NT = 4 * C;
-  constexpr int U = 4;
-  __shared__ float red[(NT / 32) * Q0 * R1];
+  constexpr int KH = (R1 < 16) ? R1 : 16;  // k1 values per pass of the core0 role
+  extern __shared__ __align__(16) float red[];
   __shared__ uint8_t flag[1024];
   const int c = threadIdx.x % C;
-  const int slab = threadIdx.x / C;
+  const int sl = threadIdx.x / C;
   const int p0 = tt.p[0], p1 = tt.p[1];
   const int nb1 = tt.num_tables * p1;
+  dcore0 += (size_t)blockIdx.y * part_stride;
+  dcore1 += (size_t)blockIdx.y * part_stride;
   if ((int)blockIdx.x < nb1) {
     const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
-    float acc[KS];
+    const int per = (p0 + gridDim.y - 1) / gridDim.y;
+    const int lo = blockIdx.y * per, hi = (lo + per < p0) ? lo + per : p0;
+    float acc[R1];
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) acc[kk] = 0.f;
-    for (int base = 0; base < p0; base += 1024) {
-      const int cnt = (p0 - base < 1024) ? p0 - base : 1024;
+    for (int k = 0; k < R1; ++k) acc[k] = 0.f;
+    for (int base = lo; base < hi; base += 1024) {
+      const int cnt = (hi - base < 1024) ? hi - base : 1024;
       __syncthreads();
       for (int i = threadIdx.x; i < cnt; i += NT)
         flag[i] = touched[((size_t)tix * p0 + base + i) * p1 + i1];
       __syncthreads();
-      for (int ib = 0; ib < cnt; ib += U) {
-        float sv[U][Q0];
+#pragma unroll 2
+      for (int ib = sl; ib < cnt; ib += 4) {
+        const bool on = flag[ib] != 0;
+        const size_t row0 = (size_t)tix * p0 + base + ib;
+        const float* sp = Sbuf + (row0 * p1 + i1) * (A * R2) + c;
+        const float* a0 = tt.core[0] + row0 * (Q0 * R1);
+        float sv[Q0];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i0 = base + ib + u;
-          const bool on = (ib + u < cnt) && flag[ib + u];
-          const float* sp = Sbuf + (((size_t)tix * p0 + i0) * p1 + i1) * (A * R2) + c;
+        for (int j0 = 0; j0 < Q0; ++j0) sv[j0] = on ? sp[j0 * C] : 0.f;
 #pragma unroll
-          for (int j0 = 0; j0 < Q0; ++j0) sv[u][j0] = on ? sp[j0 * C] : 0.f;
-        }
+        for (int j0 = 0; j0 < Q0; ++j0)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i0 = (ib + u < cnt) ? base + ib + u : base;
-          const float* a0 = tt.core[0] + ((size_t)tix * p0 + i0) * (Q0 * R1) + slab * KS;
-#pragma unroll
-          for (int j0 = 0; j0 < Q0; ++j0)
-#pragma unroll
-            for (int kk = 0; kk < KS; ++kk)
-              acc[kk] = fmaf(__ldg(a0 + j0 * R1 + kk), sv[u][j0], acc[kk]);
-        }
+          for (int v = 0; v < R1 / 4; ++v) {
+            const float4 x = ldg4(a0 + j0 * R1 + 4 * v);
+            acc[4 * v] = fmaf(x.x, sv[j0], acc[4 * v]);
+            acc[4 * v + 1] = fmaf(x.y, sv[j0], acc[4 * v + 1]);
+            acc[4 * v + 2] = fmaf(x.z, sv[j0], acc[4 * v + 2]);
+            acc[4 * v + 3] = fmaf(x.w, sv[j0], acc[4 * v + 3]);
+          }
       }
     }
+    // sum the 4 reduction lanes: red[sl][k1][c]
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < R1; ++k) red[(sl * R1 + k) * C + c] = acc[k];
+    __syncthreads();
     float* dst = dcore1 + (size_t)blockIdx.x * (R1 * C) + c;
 #pragma unroll
-    for (int kk = 0; kk < KS; ++kk) dst[(slab * KS + kk) * C] = acc[kk];
+    for (int kk = 0; kk < R1 / 4; ++kk) {
+      const int k = sl * (R1 / 4) + kk;
+      dst[k * C] = red[(0 * R1 + k) * C + c] + red[(1 * R1 + k) * C + c] +
+                   red[(2 * R1 + k) * C + c] + red[(3 * R1 + k) * C + c];
+    }
   } else {
     const int b = blockIdx.x - nb1;
     const int tix = b / p0, i0 = b % p0;
-    float acc[Q0 * KS];
+    const int per = (p1 + gridDim.y - 1) / gridDim.y;
+    const int lo = blockIdx.y * per, hi = (lo + per < p1) ? lo + per : p1;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (int half = 0; half < R1 / KH; ++half) {
+      float acc[Q0][KH];
 #pragma unroll
-    for (int i = 0; i < Q0 * KS; ++i) acc[i] = 0.f;
-    for (int base = 0; base < p1; base += 1024) {
-      const int cnt = (p1 - base < 1024) ? p1 - base : 1024;
-      __syncthreads();
-      for (int i = threadIdx.x; i < cnt; i += NT)
-        flag[i] = touched[((size_t)tix * p0 + i0) * p1 + base + i];
-      __syncthreads();
-      for (int ib = 0; ib < cnt; ib += U) {
-        float sv[U][Q0];
+      for (int j0 = 0; j0 < Q0; ++j0)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i1 = base + ib + u;
-          const bool on = (ib + u < cnt) && flag[ib + u];
+        for (int kk = 0; kk < KH; ++kk) acc[j0][kk] = 0.f;
+      for (int base = lo; base < hi; base += 1024) {
+        const int cnt = (hi - base < 1024) ? hi - base : 1024;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += NT)
+          flag[i] = touched[((size_t)tix * p0 + i0) * p1 + base + i];
+        __syncthreads();
+#pragma unroll 2
+        for (int ib = sl; ib < cnt; ib += 4) {
+          const bool on = flag[ib] != 0;
+          const int i1 = base + ib;
           const float* sp = Sbuf + (((size_t)tix * p0 + i0) * p1 + i1) * (A * R2) + c;
+          const float* b1 = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C) + (size_t)(half * KH) * C + c;
+          float sv[Q0];
 #pragma unroll
-          for (int j0 = 0; j0 < Q0; ++j0) sv[u][j0] = on ? sp[j0 * C] : 0.f;
-        }
+          for (int j0 = 0; j0 < Q0; ++j0) sv[j0] = on ? sp[j0 * C] : 0.f;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i1 = (ib + u < cnt) ? base + ib + u : base;
-          const float* b1 =
-              tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C) + (size_t)(slab * KS) * C + c;
-#pragma unroll
-          for (int kk = 0; kk < KS; ++kk) {
+          for (int kk = 0; kk < KH; ++kk) {
             const float bv = __ldg(b1 + kk * C);
 #pragma unroll
-            for (int j0 = 0; j0 < Q0; ++j0)
-              acc[j0 * KS + kk] = fmaf(sv[u][j0], bv, acc[j0 * KS + kk]);
+            for (int j0 = 0; j0 < Q0; ++j0) acc[j0][kk] = fmaf(sv[j0], bv, acc[j0][kk]);
           }
         }
       }
-    }
-    // reduce over the C columns: a warp may straddle two k1 slabs, so it produces a partial sum
-    // for its first and for its last slab; per-warp slots in shared memory, then a final pass.
-    for (int i = threadIdx.x; i < (NT / 32) * Q0 * R1; i += NT) red[i] = 0.f;
-    __syncthreads();
-    const int w = threadIdx.x >> 5;
-    const int slab_lo = __shfl_sync(0xffffffffu, slab, 0);
-    const int slab_hi = __shfl_sync(0xffffffffu, slab, 31);
+      // every thread holds Q0*KH partial sums: transpose through shared memory, one warp per output
+      __syncthreads();
 #pragma unroll
-    for (int j0 = 0; j0 < Q0; ++j0) {
+      for (int j0 = 0; j0 < Q0; ++j0)
 #pragma unroll
-      for (int kk = 0; kk < KS; ++kk) {
-        const float v = acc[j0 * KS + kk];
-        float lo = (slab == slab_lo) ? v : 0.f;
-        float hi = (slab == slab_lo) ? 0.f : v;
+        for (int kk = 0; kk < KH; ++kk) red[(j0 * KH + kk) * NT + threadIdx.x] = acc[j0][kk];
+      __syncthreads();
+      for (int o = w; o < Q0 * KH; o += NT / 32) {
+        float v = 0.f;
+        for (int t = lane; t < NT; t += 32) v += red[o * NT + t];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lo += __shfl_xor_sync(0xffffffffu, lo, o);
-          hi += __shfl_xor_sync(0xffffffffu, hi, o);
-        }
-        if ((threadIdx.x & 31) == 0) {
-          red[w * (Q0 * R1) + j0 * R1 + slab_lo * KS + kk] += lo;
-          if (slab_hi != slab_lo) red[w * (Q0 * R1) + j0 * R1 + slab_hi * KS + kk] += hi;
+        for (int sh = 16; sh > 0; sh >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sh);
+        if (lane == 0) {
+          const int j0 = o / KH, kk = o % KH;
+          dcore0[((size_t)tix * p0 + i0) * (Q0 * R1) + j0 * R1 + half * KH + kk] = v;
         }
       }
-    }
-    __syncthreads();
-    if (threadIdx.x < Q0 * R1) {
-      float t = 0.f;
-      for (int ww = 0; ww < NT / 32; ++ww) t += red[ww * (Q0 * R1) + threadIdx.x];
-      dcore0[((size_t)tix * p0 + i0) * (Q0 * R1) + threadIdx.x] = t;
     }
   }
 }
 
 // ------------------------------------------------------------------------------------
-// finalize: d_core2 = sum of per-CTA copies.  block = 32 float4 columns x 8 part lanes.
+// finalize: dense gradients from the partial copies, then the optional fused optimizer
+//   d_core2 = sum of the per-CTA shared-memory copies      (block = 32 float4 columns x 8 lanes)
+//   d_core0 | d_core1 = sum of the kCoreSplit partial copies (thread = one float4)
+// SGD: core -= lr g;  Adagrad: state += g g, core -= lr g / (sqrt(state) + eps)
+// (FBTT/tt_embeddings_cuda.cu:381-419, applied to every row -- SURVEY 8a-6)
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-reduce_partials_kernel(int64_t elems, int nparts, const float* __restrict__ partials,
-                       float* __restrict__ dcore2) {
-  __shared__ float4 sm[8][32];
-  const int col = threadIdx.x & 31;
-  const int pl = threadIdx.x >> 5;
-  const int64_t i = ((int64_t)blockIdx.x * 32 + col) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < elems) {
-    int p = pl;
-    for (; p + 24 < nparts; p += 32) {
-      float4 v[4];
+struct FinalArgs {
+  int64_t e0, e1, e2;        // element counts of the three cores
+  int nparts2;               // per-CTA copies of d_core2 (0: d_core2 already holds the sum)
+  const float* partials2;
+  const float* cparts;       // [kCoreSplit][e0 + e1]
+  float* dcore[3];
+  float* core[3];
+  float* state[3];
+  int32_t optim;
+  float lr, eps;
+  int nb2;                   // blocks that work on core2
+};
+
+__device__ __forceinline__ void apply_update4(const FinalArgs& a, int t, int64_t i, float4 g) {
+  *reinterpret_cast<float4*>(a.dcore[t] + i) = g;
+  if (a.optim == TTG_OPTIM_DENSE) return;
+  float4 c = *reinterpret_cast<float4*>(a.core[t] + i);
+  if (a.optim == TTG_OPTIM_SGD) {
+    c.x -= a.lr * g.x;
+    c.y -= a.lr * g.y;
+    c.z -= a.lr * g.z;
+    c.w -= a.lr * g.w;
+  } else {
+    float4 st = *reinterpret_cast<float4*>(a.state[t] + i);
+    st.x += g.x * g.x;
+    st.y += g.y * g.y;
+    st.z += g.z * g.z;
+    st.w += g.w * g.w;
+    *reinterpret_cast<float4*>(a.state[t] + i) = st;
+    c.x -= a.lr * g.x / (sqrtf(st.x) + a.eps);
+    c.y -= a.lr * g.y / (sqrtf(st.y) + a.eps);
+    c.z -= a.lr * g.z / (sqrtf(st.z) + a.eps);
+    c.w -= a.lr * g.w / (sqrtf(st.w) + a.eps);
+  }
+  *reinterpret_cast<float4*>(a.core[t] + i) = c;
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalArgs a) {
+  __shared__ float4 sm[32][8];
+  if ((int)blockIdx.x < a.nb2) {
+    const int col = threadIdx.x & 7;     // 8 float4 columns per block
+    const int pl = threadIdx.x >> 3;     // 32 lanes over the per-CTA copies
+    const int64_t i = ((int64_t)blockIdx.x * 8 + col) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.e2) {
+      if (a.nparts2 == 0) {
+        if (pl == 0) acc = *reinterpret_cast<const float4*>(a.dcore[2] + i);
+      } else {
+        int p = pl;
+        for (; p + 96 < a.nparts2; p += 128) {
+          float4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg4(partials + (size_t)(p + 8 * u) * elems + i);
+          for (int u = 0; u < 4; ++u) v[u] = ldg4(a.partials2 + (size_t)(p + 32 * u) * a.e2 + i);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc.x += v[u].x;
-        acc.y += v[u].y;
-        acc.z += v[u].z;
-        acc.w += v[u].w;
+          for (int u = 0; u < 4; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
+          }
+        }
+        for (; p < a.nparts2; p += 32) {
+          const float4 v = ldg4(a.partials2 + (size_t)p * a.e2 + i);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
       }
     }
-    for (; p < nparts; p += 8) {
-      const float4 v = ldg4(partials + (size_t)p * elems + i);
+    sm[pl][col] = acc;
+    __syncthreads();
+    if (pl == 0 && i < a.e2) {
+#pragma unroll
+      for (int q = 1; q < 32; ++q) {
+        acc.x += sm[q][col].x;
+        acc.y += sm[q][col].y;
+        acc.z += sm[q][col].z;
+        acc.w += sm[q][col].w;
+      }
+      apply_update4(a, 2, i, acc);
+    }
+  } else {
+    const int64_t i = ((int64_t)(blockIdx.x - a.nb2) * 256 + threadIdx.x) * 4;
+    if (i >= a.e0 + a.e1) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int y = 0; y < kCoreSplit; ++y) {
+      const float4 v = ldg4(a.cparts + (size_t)y * (a.e0 + a.e1) + i);
       acc.x += v.x;
       acc.y += v.y;
       acc.z += v.z;
       acc.w += v.w;
     }
-  }
-  sm[pl][col] = acc;
-  __syncthreads();
-  if (pl == 0 && i < elems) {
-#pragma unroll
-    for (int q = 1; q < 8; ++q) {
-      acc.x += sm[q][col].x;
-      acc.y += sm[q][col].y;
-      acc.z += sm[q][col].z;
-      acc.w += sm[q][col].w;
-    }
-    *reinterpret_cast<float4*>(dcore2 + i) = acc;
+    if (i < a.e0)
+      apply_update4(a, 0, i, acc);
+    else
+      apply_update4(a, 1, i - a.e0, acc);
   }
 }
 
@@ -710,9 +1093,49 @@ struct ShapeKey {
   int q0, q1, q2, r1, r2;
 };
 
+struct BwdOpt {
+  int32_t optim;
+  float lr, eps;
+  float* const* state;   // host array of device pointers or nullptr
+  bool table_valid;      // Ttab in the workspace matches the current cores
+};
+
 typedef int (*FwdLaunch)(const TTDev&, int64_t, uint32_t, const SortedWs&, float*, cudaStream_t);
 typedef int (*BwdLaunch)(const TTDev&, int64_t, uint32_t, const SortedWs&, const float*,
-                         float* const*, cudaStream_t);
+                         float* const*, const BwdOpt&, cudaStream_t);
+
+template <int Q0, int Q1, int Q2, int R1, int R2>
+int launch_table(const TTDev& tt, const SortedWs& w, cudaStream_t stream) {
+  const int nb = tt.num_tables * tt.p[1];
+  int split = 1;
+  while (split < 8 && nb * split < 2 * kNumSMs && split * 4 < tt.p[0]) split *= 2;
+  prof_begin(K_TABLE, stream);
+  group_table_kernel<Q0, Q1, R1, R2><<<dim3(nb, split), Q0 * Q1 * R2, 0, stream>>>(tt, w.Ttab);
+  prof_end(K_TABLE, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
+// persistent forward grid: every resident warp gets one contiguous run of sorted rows
+template <typename Kern>
+int fwd_grid(Kern kern, size_t smem, int slot, int64_t nnz, int64_t* grid, int64_t* rpw) {
+  static size_t cached_smem[4] = {~(size_t)0, ~(size_t)0, ~(size_t)0, ~(size_t)0};
+  static int cached_per_sm[4] = {0, 0, 0, 0};
+  constexpr int wpb = kFwdThreads / 32;
+  if (cached_smem[slot] != smem) {  // first call for this (kernel, smem): query once
+    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = 0;
+    TTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kFwdThreads, smem));
+    cached_per_sm[slot] = q < 1 ? 1 : q;
+    cached_smem[slot] = smem;
+  }
+  int64_t g = (int64_t)kNumSMs * cached_per_sm[slot];
+  const int64_t min_rows = 32;  // do not spread tiny batches thinner than one window per warp
+  if (g * wpb * min_rows > nnz) g = ceil_div(nnz, wpb * min_rows);
+  *grid = g;
+  *rpw = ceil_div(nnz, g * wpb);
+  return TTG_OK;
+}
 
 template <int Q0, int Q1, int Q2, int R1, int R2>
 int launch_fwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs& w, float* output,
@@ -721,25 +1144,35 @@ int launch_fwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
   constexpr int D = Q0 * Q1 * Q2;
   const int core2_elems = tt.num_tables * tt.p[2] * tt.cols[2];
   const bool c2_smem = sizeof(float) * (size_t)core2_elems <= kSmemCore2Limit;
+  int64_t grid = 0, rpw = 0;
+  if constexpr ((Q0 * Q1) % 2 == 0 && R2 <= 16) {
+    if (w.Ttab != nullptr) {
+      // dense strategy: tr0 of every group first, then the table-driven row kernel
+      int rc = launch_table<Q0, Q1, Q2, R1, R2>(tt, w, stream);
+      if (rc != TTG_OK) return rc;
+      constexpr int RPW = 32 / (Q0 * Q1 / 2);
+      const size_t stage_bytes = (Q2 % 4 == 0) ? 0 : sizeof(float) * wpb * RPW * D;
+      const size_t c2_rows = (size_t)tt.num_tables * tt.p[2];
+      const size_t smem = stage_bytes + (c2_smem ? sizeof(float) * c2_rows * (R2 * Q2 + 4) : 0);
+      auto kern = c2_smem ? table_fwd_kernel<Q0, Q1, Q2, R2, true>
+                          : table_fwd_kernel<Q0, Q1, Q2, R2, false>;
+      rc = fwd_grid(kern, smem, c2_smem ? 2 : 3, nnz, &grid, &rpw);
+      if (rc != TTG_OK) return rc;
+      prof_begin(K_FWD, stream);
+      kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow,
+                                                          w.rowcount, w.Ttab, output, (int)rpw,
+                                                          core2_elems);
+      prof_end(K_FWD, stream);
+      TTG_LAUNCH_CHECK();
+      return TTG_OK;
+    }
+  }
   const size_t stage_bytes = (Q2 % 4 == 0) ? 0 : sizeof(float) * wpb * kFwdRows * D;
   const size_t smem = stage_bytes + (c2_smem ? sizeof(float) * (size_t)core2_elems : 0);
   auto kern = c2_smem ? sorted_fwd_kernel<Q0, Q1, Q2, R1, R2, true>
                       : sorted_fwd_kernel<Q0, Q1, Q2, R1, R2, false>;
-  static size_t cached_smem[2] = {~(size_t)0, ~(size_t)0};
-  static int cached_per_sm[2] = {0, 0};
-  if (cached_smem[c2_smem] != smem) {  // first call for this (kernel, smem): query once
-    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int q = 0;
-    TTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kFwdThreads, smem));
-    cached_per_sm[c2_smem] = q < 1 ? 1 : q;
-    cached_smem[c2_smem] = smem;
-  }
-  const int per_sm = cached_per_sm[c2_smem];
-  // persistent grid: every resident warp gets one contiguous run of sorted rows
-  int64_t grid = (int64_t)kNumSMs * per_sm;
-  const int64_t min_rows = 32;  // do not spread tiny batches thinner than one window per warp
-  if (grid * wpb * min_rows > nnz) grid = ceil_div(nnz, wpb * min_rows);
-  const int64_t rpw = ceil_div(nnz, grid * wpb);
+  int rc = fwd_grid(kern, smem, c2_smem ? 0 : 1, nnz, &grid, &rpw);
+  if (rc != TTG_OK) return rc;
   prof_begin(K_FWD, stream);
   kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow,
                                                       w.rowcount, output, (int)rpw, core2_elems);
@@ -748,46 +1181,104 @@ int launch_fwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
   return TTG_OK;
 }
 
-template <int Q0, int Q1, int Q2, int R1, int R2>
-int launch_bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs& w,
-               const float* d_output, float* const* dcore, cudaStream_t stream) {
+template <int Q0, int Q1, int Q2, int R1, int R2, bool SMEM_ACC, bool TTAB>
+int launch_bwd_rows(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs& w,
+                    const float* d_output, float* dcore2, cudaStream_t stream) {
   constexpr int D = Q0 * Q1 * Q2;
   constexpr int RPW = 32 / R2;
   const int core2_elems = tt.num_tables * tt.p[2] * tt.cols[2];
-  const size_t groups = (size_t)tt.num_tables * tt.p[0] * tt.p[1];
   const size_t ring_bytes = sizeof(float) * (kBwdThreads / 32) * kBwdStages * RPW * D;
-  TTG_CUDA(cudaMemsetAsync(w.touched, 0, groups, stream));
-  if (w.smem_acc) {
-    auto kern = sorted_bwd_rows_kernel<Q0, Q1, Q2, R1, R2, true>;
-    const size_t smem = sizeof(float) * (size_t)core2_elems + ring_bytes;
+  const size_t smem = ring_bytes + (SMEM_ACC ? sizeof(float) * (size_t)core2_elems : 0);
+  auto kern = sorted_bwd_rows_kernel<Q0, Q1, Q2, R1, R2, SMEM_ACC, TTAB>;
+  static size_t set_smem = ~(size_t)0;
+  if (set_smem != smem) {
     TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prof_begin(K_BWD_ROWS, stream);
-    kern<<<kBwdGrid, kBwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow, d_output,
-                                                  w.S, w.touched, w.partials, core2_elems);
-    prof_end(K_BWD_ROWS, stream);
-    TTG_LAUNCH_CHECK();
-    prof_begin(K_REDUCE, stream);
-    reduce_partials_kernel<<<(unsigned)ceil_div(core2_elems, 128), 256, 0, stream>>>(
-        core2_elems, kBwdGrid, w.partials, dcore[2]);
-    prof_end(K_REDUCE, stream);
-    TTG_LAUNCH_CHECK();
-  } else {
-    TTG_CUDA(cudaMemsetAsync(dcore[2], 0, sizeof(float) * (size_t)core2_elems, stream));
-    auto kern = sorted_bwd_rows_kernel<Q0, Q1, Q2, R1, R2, false>;
-    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)ring_bytes));
-    prof_begin(K_BWD_ROWS, stream);
-    kern<<<kBwdGrid, kBwdThreads, ring_bytes, stream>>>(tt, nnz, total_rows, w.skeys, w.srow,
-                                                        d_output, w.S, w.touched, dcore[2],
-                                                        core2_elems);
-    prof_end(K_BWD_ROWS, stream);
-    TTG_LAUNCH_CHECK();
+    set_smem = smem;
   }
+  // one contiguous, equally long run of sorted rows per warp (groups belong to the run they
+  // start in), so every warp finishes at the same time
+  int64_t chunk_rows = ceil_div(nnz, (int64_t)kBwdGrid * (kBwdThreads / 32));
+  if (chunk_rows < kBwdMinChunkRows) chunk_rows = kBwdMinChunkRows;
+  prof_begin(K_BWD_ROWS, stream);
+  kern<<<kBwdGrid, kBwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow, d_output,
+                                                w.Ttab, w.S, w.touched,
+                                                SMEM_ACC ? w.partials : dcore2, core2_elems,
+                                                (int)chunk_rows);
+  prof_end(K_BWD_ROWS, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
+template <int Q0, int Q1, int Q2, int R1, int R2>
+int launch_bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs& w,
+               const float* d_output, float* const* dcore, const BwdOpt& opt,
+               cudaStream_t stream) {
+  const int64_t e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
+  const int64_t e1 = (int64_t)tt.num_tables * tt.p[1] * tt.cols[1];
+  const int64_t e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
+  const size_t groups = (size_t)tt.num_tables * tt.p[0] * tt.p[1];
+  TTG_CUDA(cudaMemsetAsync(w.touched, 0, groups, stream));
+  int rc = TTG_OK;
+  bool table = false;
+  if constexpr ((Q0 * Q1) % 2 == 0 && R2 <= 16) {
+    table = (w.Ttab != nullptr);
+    if (table && !opt.table_valid) {
+      rc = launch_table<Q0, Q1, Q2, R1, R2>(tt, w, stream);
+      if (rc != TTG_OK) return rc;
+    }
+  }
+  if (w.smem_acc) {
+    rc = table ? launch_bwd_rows<Q0, Q1, Q2, R1, R2, true, true>(tt, nnz, total_rows, w, d_output,
+                                                                 dcore[2], stream)
+               : launch_bwd_rows<Q0, Q1, Q2, R1, R2, true, false>(tt, nnz, total_rows, w, d_output,
+                                                                  dcore[2], stream);
+  } else {
+    TTG_CUDA(cudaMemsetAsync(dcore[2], 0, sizeof(float) * (size_t)e2, stream));
+    rc = table ? launch_bwd_rows<Q0, Q1, Q2, R1, R2, false, true>(tt, nnz, total_rows, w, d_output,
+                                                                  dcore[2], stream)
+               : launch_bwd_rows<Q0, Q1, Q2, R1, R2, false, false>(tt, nnz, total_rows, w,
+                                                                   d_output, dcore[2], stream);
+  }
+  if (rc != TTG_OK) return rc;
   const int nblocks = tt.num_tables * (tt.p[0] + tt.p[1]);
   prof_begin(K_BWD_CORES, stream);
-  sorted_bwd_cores_kernel<Q0, Q1, Q2, R1, R2><<<nblocks, 4 * Q1 * R2, 0, stream>>>(
-      tt, w.S, w.touched, dcore[0], dcore[1]);
+  {
+    constexpr int C = Q1 * R2, NT = 4 * C, KH = (R1 < 16) ? R1 : 16;
+    constexpr size_t csmem =
+        sizeof(float) * ((size_t)Q0 * KH * NT > (size_t)4 * R1 * C ? (size_t)Q0 * KH * NT
+                                                                   : (size_t)4 * R1 * C);
+    auto ckern = sorted_bwd_cores_kernel<Q0, Q1, Q2, R1, R2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      TTG_CUDA(cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      attr_set = true;
+    }
+    ckern<<<dim3(nblocks, kCoreSplit), NT, csmem, stream>>>(tt, w.S, w.touched, w.cparts,
+                                                            w.cparts + e0, (size_t)(e0 + e1));
+  }
   prof_end(K_BWD_CORES, stream);
+  TTG_LAUNCH_CHECK();
+  FinalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.e0 = e0;
+  a.e1 = e1;
+  a.e2 = e2;
+  a.nparts2 = w.smem_acc ? kBwdGrid : 0;
+  a.partials2 = w.partials;
+  a.cparts = w.cparts;
+  for (int t = 0; t < 3; ++t) {
+    a.dcore[t] = dcore[t];
+    a.core[t] = tt.core[t];
+    a.state[t] = opt.state ? opt.state[t] : nullptr;
+  }
+  a.optim = opt.optim;
+  a.lr = opt.lr;
+  a.eps = opt.eps;
+  a.nb2 = (int)ceil_div(e2, 32);
+  const int nb01 = (int)ceil_div(e0 + e1, 1024);
+  prof_begin(K_REDUCE, stream);
+  finalize_kernel<<<a.nb2 + nb01, 256, 0, stream>>>(a);
+  prof_end(K_REDUCE, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
 }
@@ -813,6 +1304,7 @@ const Entry kEntries[] = {
 const Entry* find_entry(const TTDev& tt) {
   if (tt.T != 3) return nullptr;
   if ((uint64_t)tt.num_tables * (uint64_t)tt.num_rows >= 0xfffffff0ull) return nullptr;
+  if ((uint64_t)tt.num_tables * tt.p[0] * tt.p[1] >= 0x7ffffff0ull) return nullptr;
   for (const Entry& e : kEntries) {
     if (e.k.q0 == tt.q[0] && e.k.q1 == tt.q[1] && e.k.q2 == tt.q[2] && e.k.r1 == tt.r[1] &&
         e.k.r2 == tt.r[2])
@@ -821,26 +1313,41 @@ const Entry* find_entry(const TTDev& tt) {
   return nullptr;
 }
 
+// Index plan.  Default: bucket the rows by group (count, scan, scatter -- three small kernels);
+// deterministic == true: full radix sort of the keys (fixed order inside a group, so repeated
+// runs give bit-identical gradients).
 int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                const int64_t* rowidx, const int64_t* tableidx, const SortedWs& w,
-               cudaStream_t stream) {
+               bool deterministic, cudaStream_t stream) {
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
+  const int32_t groups = tt.num_tables * tt.p[0] * tt.p[1];
   TTG_CUDA(cudaMemsetAsync(w.rowcount, 0, sizeof(int32_t) * (size_t)tt.num_tables * B, stream));
+  if (!deterministic)
+    TTG_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * ((size_t)groups + 1), stream));
   prof_begin(K_PLAN, stream);
-  plan_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, stream>>>(
+  plan_kernel<<<(unsigned)ceil_div(nnz, 256 * kPlanItems), 256, 0, stream>>>(
       nnz, B, tt.num_rows, tt.num_tables, total_rows, indices, rowidx, tableidx, w.keys_in,
-      w.vals_in, w.rowcount);
+      w.vals_in, w.rowcount, deterministic ? nullptr : w.cnt, (uint32_t)tt.p[2], groups);
   prof_end(K_PLAN, stream);
   TTG_LAUNCH_CHECK();
-  int end_bit = 1;
-  while (end_bit < 32 && (1ull << end_bit) <= (uint64_t)total_rows) ++end_bit;
-  size_t bytes = w.cub_bytes;
   prof_begin(K_SORT, stream);
-  TTG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const uint32_t*)w.keys_in, w.skeys,
-                                           (const int32_t*)w.vals_in, w.srow, (int)nnz, 0, end_bit,
-                                           stream));
+  if (deterministic) {
+    int end_bit = 1;
+    while (end_bit < 32 && (1ull << end_bit) <= (uint64_t)total_rows) ++end_bit;
+    size_t bytes = w.cub_bytes;
+    TTG_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, bytes, (const uint32_t*)w.keys_in, w.skeys,
+                                             (const int32_t*)w.vals_in, w.srow, (int)nnz, 0,
+                                             end_bit, stream));
+    count_launch(3);
+  } else {
+    bucket_scan_kernel<<<1, 1024, 0, stream>>>(groups + 1, w.cnt, w.base);
+    TTG_LAUNCH_CHECK();
+    bucket_scatter_kernel<<<(unsigned)ceil_div(nnz, 256 * kPlanItems), 256, 0, stream>>>(
+        nnz, total_rows, (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in, w.base, w.cnt, w.skeys,
+        w.srow);
+    TTG_LAUNCH_CHECK();
+  }
   prof_end(K_SORT, stream);
-  count_launch(3);
   return TTG_OK;
 }
 
@@ -867,7 +1374,7 @@ size_t sorted_workspace_bytes(const TTDev& tt, int64_t B, int64_t nnz) {
 
 int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                    const int64_t* rowidx, const int64_t* tableidx, float* output, void* ws,
-                   size_t ws_bytes, bool plan_valid, cudaStream_t stream) {
+                   size_t ws_bytes, int32_t flags, cudaStream_t stream) {
   const Entry* e = find_entry(tt);
   if (!e) {
     set_error("sorted_forward: unsupported shape");
@@ -888,8 +1395,9 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
     set_error("sorted_forward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
   }
-  if (!plan_valid) {
-    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, stream);
+  if (!(flags & TTG_FLAG_PLAN_VALID)) {
+    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
+                    stream);
     if (rc != TTG_OK) return rc;
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
@@ -903,14 +1411,14 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
 
 int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                     const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
-                    float* const* dcore, void* ws, size_t ws_bytes, bool plan_valid,
-                    cudaStream_t stream) {
+                    float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
+                    void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream) {
   const Entry* e = find_entry(tt);
   if (!e) {
     set_error("sorted_backward: unsupported shape");
     return TTG_ENOTSUP;
   }
-  if (nnz == 0) {
+  if (nnz == 0) {  // FBTT/tt_embeddings_cuda.cu:450-452 returns zero gradients, no update
     for (int t = 0; t < tt.T; ++t)
       TTG_CUDA(cudaMemsetAsync(dcore[t], 0,
                                sizeof(float) * (size_t)tt.num_tables * tt.p[t] * tt.cols[t], stream));
@@ -918,8 +1426,19 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
   }
   int rc = check_common(tt, B, nnz, "sorted_backward");
   if (rc != TTG_OK) return rc;
-  if (((uintptr_t)d_output & 15) != 0 || ((uintptr_t)dcore[2] & 15) != 0) {
-    set_error("sorted_backward: d_output and d_cores must be 16-byte aligned");
+  for (int t = 0; t < 3; ++t) {
+    if (((uintptr_t)dcore[t] & 15) != 0 || ((uintptr_t)tt.core[t] & 15) != 0 ||
+        (state && ((uintptr_t)state[t] & 15) != 0)) {
+      set_error("sorted_backward: cores, d_cores and optimizer state must be 16-byte aligned");
+      return TTG_EINVAL;
+    }
+  }
+  if (((uintptr_t)d_output & 15) != 0) {
+    set_error("sorted_backward: d_output must be 16-byte aligned");
+    return TTG_EINVAL;
+  }
+  if (optim == TTG_OPTIM_ADAGRAD && state == nullptr) {
+    set_error("sorted_backward: adagrad needs optimizer_state");
     return TTG_EINVAL;
   }
   SortedWs w = carve(tt, B, nnz, (char*)ws);
@@ -927,12 +1446,20 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
     set_error("sorted_backward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
   }
+  const bool plan_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
   if (!plan_valid) {
-    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, stream);
+    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
+                    stream);
     if (rc != TTG_OK) return rc;
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
-  return e->bwd(tt, nnz, total_rows, w, d_output, dcore, stream);
+  BwdOpt opt;
+  opt.optim = optim;
+  opt.lr = lr;
+  opt.eps = eps;
+  opt.state = state;
+  opt.table_valid = plan_valid;  // the forward that built the plan also built the table
+  return e->bwd(tt, nnz, total_rows, w, d_output, dcore, opt, stream);
 }
 
 }  // namespace ttg

@@ -63,8 +63,8 @@ def Eff_TT_forward(batch_size: int, table_length: int, feature_dim: int, index: 
                                  _ttg.ptr(ws), ws.numel(), _ttg.stream_of(dev))
         _ttg.check(rc, "Eff_TT_forward")
         if index.data_ptr() == raw.data_ptr():  # only trust a plan built from the caller's tensor
-            _ws.set_plan(dev, ("eff", index.data_ptr(), index._version, int(batch_size)),
-                         keep=(index,))
+            _ws.set_plan(dev, ("eff", index.data_ptr(), index._version, int(batch_size),
+                               tuple((c.data_ptr(), c._version) for c in cores)), keep=(index,))
         else:
             _ws.set_plan(dev, None)
     return out
@@ -94,13 +94,15 @@ def Fused_Extra_Eff_TT_backward(batch_size: int, table_length: int, feature_dim:
         lib = _ttg.lib()
         ws = _ws.get(dev, lib.ttg_eff_workspace_bytes(C.byref(shape), batch_size))
         flags = 0
-        if _ws.plan(dev) == ("eff", indices.data_ptr(), indices._version, int(batch_size)):
+        if _ws.plan(dev) == ("eff", indices.data_ptr(), indices._version, int(batch_size),
+                             tuple((c.data_ptr(), c._version) for c in cores)):
             flags = _ttg.FLAG_PLAN_VALID
         cp = _ttg.ptr_array(cores)
         rc = lib.ttg_eff_backward_sgd(C.byref(shape), batch_size, float(learning_rate),
                                       _ttg.ptr(indices), _ttg.ptr(g), cp, _ttg.ptr(ws), ws.numel(),
                                       flags, _ttg.stream_of(dev))
         _ttg.check(rc, "Eff_TT_backward")
+        _ws.set_plan(dev, None)   # cores updated in place: plan's group table is stale
 
 
 def Eff_TT_backward(batch_size, table_length, feature_dim, learning_rate, indices, tt_p_shapes,

@@ -40,6 +40,11 @@ def _cores_ok(tt_cores, T):
     return cores
 
 
+def _plan_tag():
+    # a plan built by the bucket pass must not be reused by a caller asking for the sorted one
+    return "tt-det" if (EXTRA_FLAGS & _ttg.FLAG_DETERMINISTIC) else "tt"
+
+
 def _shape_tuple(p, q, r, num_tables):
     return (tuple(int(x) for x in p), tuple(int(x) for x in q), tuple(int(x) for x in r),
             int(num_tables))
@@ -74,8 +79,8 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
         _ttg.check(rc, "tt_forward")
         if nnz > 0:
             _ttg.workspace.set_plan(dev, _ttg.plan_key_of(
-                "tt", indices, rowidx, nnz, B,
-                _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)),
+                _plan_tag(), indices, rowidx, nnz, B,
+                _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables), cores),
                 keep=(indices, rowidx))
     return output
 
@@ -114,8 +119,9 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
         flags = 0
         key = None
         if nnz > 0:
-            key = _ttg.plan_key_of("tt", indices, rowidx, nnz, B,
-                                   _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables))
+            key = _ttg.plan_key_of(_plan_tag(), indices, rowidx, nnz, B,
+                                   _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables),
+                                   cores)
             if _ttg.workspace.plan(dev) == key:
                 flags |= _ttg.FLAG_PLAN_VALID  # the forward's sort is still in the workspace
         cp = _ttg.ptr_array(cores)
@@ -125,8 +131,12 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
                                  _ttg.ptr(d_output), cp, sp, dp, _ttg.ptr(ws), ws.numel(),
                                  flags | EXTRA_FLAGS, _ttg.stream_of(dev))
         _ttg.check(rc, "tt_backward")
-        if nnz > 0 and not flags:
-            _ttg.workspace.set_plan(dev, key, keep=(indices, rowidx))
+        if nnz > 0:
+            if optim != _ttg.OPTIM_DENSE:
+                # the cores were updated in place by the kernel: the group table is stale
+                _ttg.workspace.set_plan(dev, None)
+            elif not flags:
+                _ttg.workspace.set_plan(dev, key, keep=(indices, rowidx))
     return d_cores
 
 

@@ -47,8 +47,11 @@ enum { TTG_OPTIM_SGD = 0, TTG_OPTIM_ADAGRAD = 1, TTG_OPTIM_DENSE = 2 };
 /* flags for ttg_tt_forward / ttg_tt_backward */
 enum {
   TTG_FLAG_FORCE_GENERIC = 1, /* use the shape-generic kernels (any T in 2..4)      */
-  TTG_FLAG_PLAN_VALID = 2     /* workspace already holds the sorted plan of the SAME
-                                 (indices, nnz) -- skip the sort (fwd -> bwd reuse)   */
+  TTG_FLAG_PLAN_VALID = 2,    /* workspace already holds the index plan (and group table) of
+                                 the SAME (indices, rowidx, nnz, B) and the cores have not
+                                 changed since -- skip both (forward -> backward reuse)   */
+  TTG_FLAG_DETERMINISTIC = 4  /* full radix sort instead of the bucket plan: fixed summation
+                                 order, bit-identical gradients run to run             */
 };
 
 /* TT table description: tt_p_shapes / tt_q_shapes / tt_ranks of the reference. */
