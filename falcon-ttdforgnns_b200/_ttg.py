@@ -15,7 +15,7 @@ _lib = None
 
 TTG_MAX_CORES = 4
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
-FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC = 1, 2, 4
+FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC, FLAG_TF32, FLAG_FFMA = 1, 2, 4, 8, 16
 
 
 class Shape(C.Structure):

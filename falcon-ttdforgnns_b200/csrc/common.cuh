@@ -119,4 +119,22 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
                     float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
                     void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream);
 
+// tensor-core kernels for the group-table strategy, tt_mma.cu (plan built by tt_sorted.cu)
+struct MmaPlan {
+  const uint32_t* skeys;   // keys grouped by (i0, i1), invalid keys last
+  const int32_t* srow;     // output row of each sorted key, bit 31 = bag has several indices
+  const int32_t* cnt;      // [groups + 1] rows per group (last: invalid keys)
+  const int32_t* base;     // [groups + 1] exclusive scan of cnt
+  float* Ttab;             // [groups][q0 q1][r2]
+  float* S;                // [groups][q0 q1][r2]
+  float* d0parts;          // [4][core0 elements]
+};
+bool mma_supported(const TTDev& tt);
+int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream);
+int mma_forward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl, float* output,
+                bool tf32, cudaStream_t stream);
+int mma_backward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl,
+                 const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
+                 float* const* state, bool tf32, cudaStream_t stream);
+
 }  // namespace ttg

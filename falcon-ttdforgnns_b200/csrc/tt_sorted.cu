@@ -49,9 +49,13 @@ constexpr int kCoreSplit = 4;        // split of the reduction axis in the cores
 // sparse in groups (papers100M) tr0 is computed inside the row kernels, once per group run.
 inline bool use_group_table(const TTDev& tt, int64_t nnz) {
   const double groups = (double)tt.num_tables * tt.p[0] * tt.p[1];
+  if ((tt.q[0] * tt.q[1]) % 2 != 0 || tt.r[2] > 16) return false;
+  // tensor-core kernels: the table costs one small GEMM per i1; worth it as soon as a group
+  // has a row on average
+  if (mma_supported(tt)) return groups <= (double)nnz;
   const double cost_group = 2.0 * tt.q[0] * tt.r[1] * tt.q[1] * tt.r[2];
   const double cost_row = 2.0 * tt.q[0] * tt.q[1] * tt.r[2] * tt.q[2];
-  return (tt.q[0] * tt.q[1]) % 2 == 0 && tt.r[2] <= 16 && 2.0 * groups * cost_group <= (double)nnz * cost_row;
+  return 2.0 * groups * cost_group <= (double)nnz * cost_row;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -69,17 +73,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // ------------------------------------------------------------------------------------
 struct SortedWs {
   uint32_t* keys_in;
-  int32_t* vals_in;
-  uint32_t* skeys;     // sorted keys
-  int32_t* srow;       // output row (table * B + rowidx) of each sorted key
-  int32_t* rowcount;   // [tables * B] occurrences of each output row
-  uint8_t* touched;    // [tables * p0 * p1]
+  int32_t* vals_in;    // output row (table * B + rowidx) of each index, input order
+  int32_t* ranks;      // position of each row inside its group's bucket
+  uint32_t* skeys;     // keys grouped by (i0, i1) (fully sorted in deterministic mode)
+  int32_t* srow;       // output row of each sorted key; bit 31 set when the output row does not
+                       // have exactly one valid index (accumulate instead of store)
+  uint8_t* touched;    // [tables * p0 * p1]                      (FFMA kernels)
   float* S;            // [tables * p0 * p1][q0 q1 r2]
   float* Ttab;         // [tables * p0 * p1][q0 q1 r2]  tr0 of every group (dense strategy)
-  float* partials;     // [kBwdGrid][tables * p2 * cols2] or nullptr
-  float* cparts;       // [kCoreSplit][core0 + core1 elements]
-  int32_t* cnt;        // [groups + 1] bucket counters / cursors
-  int32_t* base;       // [groups + 1] bucket starts
+  float* partials;     // [kBwdGrid][tables * p2 * cols2] or nullptr (FFMA kernels)
+  float* cparts;       // [kCoreSplit][core0 + core1 elements]    (FFMA kernels)
+  float* d0parts;      // [4][core0 elements]                     (tensor-core kernels)
+  int32_t* cnt;        // [cnt_elems] rows per group (+1: invalid keys), padded to scan tiles
+  int32_t* rowcount;   // [tables * B] valid indices per output row; directly behind cnt
+  size_t cnt_bytes;    // cnt alone (backward-only plan)
+  size_t clear_bytes;  // cnt + rowcount, cleared by one memset
+  int32_t* base;       // [cnt_elems] exclusive scan of cnt
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -97,21 +106,28 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
   const size_t n = (size_t)(nnz > 0 ? nnz : 1);
   const size_t groups = (size_t)tt.num_tables * tt.p[0] * tt.p[1];
   const size_t core2 = (size_t)tt.num_tables * tt.p[2] * tt.cols[2];
+  const size_t e0 = (size_t)tt.num_tables * tt.p[0] * tt.cols[0];
+  const size_t e1 = (size_t)tt.num_tables * tt.p[1] * tt.cols[1];
+  const size_t out_rows = (size_t)tt.num_tables * (size_t)(B > 0 ? B : 1);
   w.keys_in = (uint32_t*)take(sizeof(uint32_t) * n);
   w.vals_in = (int32_t*)take(sizeof(int32_t) * n);
+  w.ranks = (int32_t*)take(sizeof(int32_t) * n);
   w.skeys = (uint32_t*)take(sizeof(uint32_t) * (n + 64));
   w.srow = (int32_t*)take(sizeof(int32_t) * (n + 64));
-  w.rowcount = (int32_t*)take(sizeof(int32_t) * (size_t)tt.num_tables * (size_t)(B > 0 ? B : 1));
   w.touched = (uint8_t*)take(groups);
   w.S = (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]));
   w.Ttab = use_group_table(tt, nnz)
                ? (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]))
                : nullptr;
-  w.cparts = (float*)take(sizeof(float) * kCoreSplit *
-                          ((size_t)tt.num_tables * tt.p[0] * tt.cols[0] +
-                           (size_t)tt.num_tables * tt.p[1] * tt.cols[1]));
-  w.cnt = (int32_t*)take(sizeof(int32_t) * (groups + 1));
-  w.base = (int32_t*)take(sizeof(int32_t) * (groups + 1));
+  w.cparts = (float*)take(sizeof(float) * kCoreSplit * (e0 + e1));
+  w.d0parts = (float*)take(sizeof(float) * 4 * e0);
+  // counters (padded to whole 4096-counter scan tiles) and the per-row counts share one memset
+  const size_t cnt_elems = align_up(groups + 1, 4096);
+  w.cnt_bytes = sizeof(int32_t) * cnt_elems;
+  w.clear_bytes = sizeof(int32_t) * (cnt_elems + out_rows);
+  w.cnt = (int32_t*)take(w.clear_bytes);
+  w.rowcount = base ? w.cnt + cnt_elems : nullptr;
+  w.base = (int32_t*)take(sizeof(int32_t) * cnt_elems);
   w.smem_acc = (core2 * sizeof(float) <= kSmemAccLimit);
   w.partials = w.smem_acc ? (float*)take(sizeof(float) * core2 * kBwdGrid) : nullptr;
   w.cub_bytes = 0;
@@ -123,16 +139,18 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
 }
 
 // ------------------------------------------------------------------------------------
-// plan: keys, output rows and row occurrence counts
+// plan: 32-bit keys, output rows, the rank of every index inside its group's bucket and the
+// number of valid indices per output row.  Integer-only; any order of (tableidx, rowidx) works.
 // ------------------------------------------------------------------------------------
 constexpr int kPlanItems = 4;   // rows per thread: independent loads / atomics in flight
+constexpr uint32_t kMultiBit = 0x80000000u;
 
 __global__ void __launch_bounds__(256)
 plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32_t total_rows,
             const int64_t* __restrict__ indices, const int64_t* __restrict__ rowidx,
             const int64_t* __restrict__ tableidx, uint32_t* __restrict__ keys,
-            int32_t* __restrict__ vals, int32_t* __restrict__ rowcount, int32_t* __restrict__ cnt,
-            uint32_t p2, int32_t num_groups) {
+            int32_t* __restrict__ vals, int32_t* __restrict__ ranks, int32_t* __restrict__ cnt,
+            int32_t* __restrict__ rowcount, uint32_t p2, int32_t num_groups) {
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
   int64_t idx[kPlanItems], t[kPlanItems], row[kPlanItems];
 #pragma unroll
@@ -149,133 +167,195 @@ plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32
     const bool ok = idx[k] >= 0 && idx[k] < num_rows && t[k] >= 0 && t[k] < num_tables &&
                     row[k] >= 0 && row[k] < B;
     const uint32_t key = ok ? (uint32_t)(t[k] * num_rows + idx[k]) : total_rows;  // invalid -> end
+    const int32_t gr = ok ? (int32_t)(t[k] * B + row[k]) : 0;
     keys[n] = key;
-    vals[n] = ok ? (int32_t)(t[k] * B + row[k]) : 0;
-    if (ok) atomicAdd(rowcount + t[k] * B + row[k], 1);
-    if (cnt) atomicAdd(cnt + (ok ? key / p2 : num_groups), 1);  // bucket plan: rows per group
+    vals[n] = gr;
+    ranks[n] = atomicAdd(cnt + (ok ? key / p2 : num_groups), 1);
+    if (ok && rowcount) atomicAdd(rowcount + gr, 1);
   }
 }
 
-// exclusive scan of the bucket counters (single CTA, 8 counters per thread and pass); the
-// counters are cleared so that the scatter can reuse them as cursors
+// exclusive scan of the bucket counters: each CTA owns 4096 counters and first re-reads (int4,
+// coalesced) everything in front of them -- 70 KB at ogbn-products -- instead of chaining CTAs
 __global__ void __launch_bounds__(1024)
-bucket_scan_kernel(int32_t n, int32_t* __restrict__ cnt, int32_t* __restrict__ base) {
-  constexpr int IPT = 8;
+bucket_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ base) {
   __shared__ int32_t warp_tot[32];
-  __shared__ int32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int32_t b0 = 0; b0 < n; b0 += 1024 * IPT) {
-    const int32_t i = b0 + threadIdx.x * IPT;
-    int32_t v[IPT];
-    int32_t tot = 0;
+  __shared__ int32_t prefix_s;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int4* c4 = reinterpret_cast<const int4*>(cnt);
+  int32_t acc = 0;
+  for (int i = threadIdx.x; i < (int)blockIdx.x * 1024; i += 1024) {
+    const int4 v = __ldg(c4 + i);
+    acc += v.x + v.y + v.z + v.w;
+  }
+  const int4 mine = __ldg(c4 + (size_t)blockIdx.x * 1024 + threadIdx.x);
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      v[k] = (i + k < n) ? cnt[i + k] : 0;
-      tot += v[k];
-    }
-    int32_t x = tot;
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) warp_tot[wib] = acc;
+  __syncthreads();
+  if (wib == 0) {
+    int32_t t = warp_tot[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) prefix_s = t;
+  }
+  __syncthreads();
+  const int32_t prefix = prefix_s;
+  const int32_t tot = mine.x + mine.y + mine.z + mine.w;
+  int32_t x = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  __syncthreads();
+  if (lane == 31) warp_tot[wib] = x;
+  __syncthreads();
+  if (wib == 0) {
+    int32_t t = warp_tot[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
+      const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += y;
     }
-    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      int32_t t = warp_tot[threadIdx.x];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int32_t y = __shfl_up_sync(0xffffffffu, t, o);
-        if (threadIdx.x >= o) t += y;
-      }
-      warp_tot[threadIdx.x] = t;
-    }
-    __syncthreads();
-    const int32_t warp_excl = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
-    const int32_t incl = carry + warp_excl + x;
-    int32_t run = incl - tot;
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-      if (i + k < n) {
-        base[i + k] = run;
-        cnt[i + k] = 0;
-      }
-      run += v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = incl;
-    __syncthreads();
+    warp_tot[lane] = t;
   }
+  __syncthreads();
+  const int32_t excl = prefix + (wib ? warp_tot[wib - 1] : 0) + x - tot;
+  int4 out;
+  out.x = excl;
+  out.y = excl + mine.x;
+  out.z = out.y + mine.y;
+  out.w = out.z + mine.z;
+  reinterpret_cast<int4*>(base)[(size_t)blockIdx.x * 1024 + threadIdx.x] = out;
 }
 
-// rows of one group become adjacent (order inside a group is arbitrary: nothing depends on it)
+// rows of one group become adjacent (order inside a group is arbitrary: nothing depends on it).
+// ranks == nullptr: the keys were radix-sorted already (skeys / srow hold keys and output rows),
+// only the accumulate bit is added.  output != nullptr (forward): every output row that does
+// not have exactly one valid index is zero-filled here (the reference returns at::zeros and
+// accumulates, FBTT/tt_embeddings_cuda.cu:1006-1009); rows with one index are stored by it.
 __global__ void __launch_bounds__(256)
 bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num_groups,
                       const uint32_t* __restrict__ keys, const int32_t* __restrict__ vals,
-                      const int32_t* __restrict__ base, int32_t* __restrict__ cursor,
-                      uint32_t* __restrict__ skeys, int32_t* __restrict__ srow) {
+                      const int32_t* __restrict__ ranks, const int32_t* __restrict__ base,
+                      const int32_t* __restrict__ rowcount, uint32_t* __restrict__ skeys,
+                      int32_t* __restrict__ srow, float* __restrict__ output, int64_t out_rows,
+                      int32_t D4) {
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
-  uint32_t key[kPlanItems];
-  int32_t val[kPlanItems], g[kPlanItems], pos[kPlanItems];
+  if (ranks != nullptr) {
+    uint32_t key[kPlanItems];
+    int32_t val[kPlanItems], pos[kPlanItems], rc[kPlanItems];
 #pragma unroll
-  for (int k = 0; k < kPlanItems; ++k) {
-    const int64_t n = n0 + k * 256;
-    key[k] = (n < nnz) ? keys[n] : total_rows;
-    val[k] = (n < nnz) ? vals[n] : 0;
-    g[k] = key[k] < total_rows ? (int32_t)(key[k] / p2) : num_groups;
+    for (int k = 0; k < kPlanItems; ++k) {
+      const int64_t n = n0 + k * 256;
+      key[k] = (n < nnz) ? __ldg(keys + n) : total_rows;
+      val[k] = (n < nnz) ? __ldg(vals + n) : 0;
+      pos[k] = (n < nnz) ? __ldg(ranks + n) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kPlanItems; ++k) {
+      const int32_t g = key[k] < total_rows ? (int32_t)(key[k] / p2) : num_groups;
+      pos[k] += __ldg(base + g);
+      rc[k] = rowcount ? __ldg(rowcount + val[k]) : 1;
+    }
+#pragma unroll
+    for (int k = 0; k < kPlanItems; ++k) {
+      if (n0 + k * 256 < nnz) {
+        skeys[pos[k]] = key[k];
+        srow[pos[k]] = (int32_t)((uint32_t)val[k] | (rc[k] == 1 ? 0u : kMultiBit));
+      }
+    }
+  } else if (rowcount != nullptr) {
+#pragma unroll
+    for (int k = 0; k < kPlanItems; ++k) {
+      const int64_t n = n0 + k * 256;
+      if (n < nnz) {
+        const int32_t v = srow[n];
+        if (__ldg(rowcount + v) != 1) srow[n] = (int32_t)((uint32_t)v | kMultiBit);
+      }
+    }
   }
-#pragma unroll
-  for (int k = 0; k < kPlanItems; ++k)
-    pos[k] = (n0 + k * 256 < nnz) ? __ldg(base + g[k]) + atomicAdd(cursor + g[k], 1) : 0;
-#pragma unroll
-  for (int k = 0; k < kPlanItems; ++k) {
-    if (n0 + k * 256 < nnz) {
-      skeys[pos[k]] = key[k];
-      srow[pos[k]] = val[k];
+  if (output != nullptr) {
+    // one warp per 32 output rows; all lanes zero the rows that need it, 16 bytes per lane
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t r0 = warp * 32; r0 < out_rows; r0 += nwarps * 32) {
+      const int64_t r = r0 + lane;
+      uint32_t pending = __ballot_sync(0xffffffffu, r < out_rows && __ldg(rowcount + r) != 1);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        float4* o = reinterpret_cast<float4*>(output) + (r0 + src) * D4;
+        for (int i = lane; i < D4; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
 }
 
 // tr0 of every group: Ttab[(t, i0, i1)][j0, (j1 k2)] = sum_k1 core0[i0][j0, k1] core1[i1][k1, (j1 k2)]
-// CTA = (table, i1), thread = (j0, column): core1[i1] stays in registers across the i0 loop.
+// CTA = (table, i1) x a slice of i0; thread = (j0, column c).  The column of core1[i1] stays in
+// registers, the CTA's rows of core0 are staged in shared memory (read back as broadcast
+// LDS.128), four i0 are in flight per thread and every store is a coalesced 1.25 KB row.
+constexpr int kTableUnroll = 4;
+
 template <int Q0, int Q1, int R1, int R2>
 __global__ void __launch_bounds__(Q0 * Q1 * R2)
-group_table_kernel(TTDev tt, float* __restrict__ Ttab) {
+group_table_kernel(TTDev tt, float* __restrict__ Ttab, int i0_per_cta) {
   constexpr int C = Q1 * R2;
+  constexpr int NT = Q0 * C;
+  extern __shared__ __align__(16) float a_s[];   // [i0_per_cta][Q0][R1]
   const int p0 = tt.p[0], p1 = tt.p[1];
   const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
+  const int lo = blockIdx.y * i0_per_cta;
+  const int cnt = (lo + i0_per_cta < p0) ? i0_per_cta : p0 - lo;
+  if (cnt <= 0) return;
   const int c = threadIdx.x % C, j0 = threadIdx.x / C;
+  {
+    const float4* src = reinterpret_cast<const float4*>(tt.core[0] + ((size_t)tix * p0 + lo) * (Q0 * R1));
+    for (int i = threadIdx.x; i < cnt * (Q0 * R1 / 4); i += NT)
+      reinterpret_cast<float4*>(a_s)[i] = __ldg(src + i);
+  }
   const float* b1 = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C) + c;
   float b[R1];
 #pragma unroll
   for (int k1 = 0; k1 < R1; ++k1) b[k1] = __ldg(b1 + k1 * C);
-#pragma unroll 4
-  for (int i0 = blockIdx.y; i0 < p0; i0 += gridDim.y) {
-    const float* a0 = tt.core[0] + ((size_t)tix * p0 + i0) * (Q0 * R1) + j0 * R1;
+  __syncthreads();
+  float* dst = Ttab + (((size_t)tix * p0 + lo) * p1 + i1) * NT + threadIdx.x;
+  const size_t dstride = (size_t)p1 * NT;
+  int i = 0;
+  for (; i + kTableUnroll <= cnt; i += kTableUnroll) {
+    float t[kTableUnroll];
+#pragma unroll
+    for (int u = 0; u < kTableUnroll; ++u) {
+      const float* a0 = a_s + ((i + u) * Q0 + j0) * R1;
+      t[u] = 0.f;
+#pragma unroll
+      for (int v = 0; v < R1 / 4; ++v) {
+        const float4 x = *reinterpret_cast<const float4*>(a0 + 4 * v);
+        t[u] = fmaf(x.x, b[4 * v], t[u]);
+        t[u] = fmaf(x.y, b[4 * v + 1], t[u]);
+        t[u] = fmaf(x.z, b[4 * v + 2], t[u]);
+        t[u] = fmaf(x.w, b[4 * v + 3], t[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kTableUnroll; ++u) dst[(size_t)(i + u) * dstride] = t[u];
+  }
+  for (; i < cnt; ++i) {
+    const float* a0 = a_s + (i * Q0 + j0) * R1;
     float t = 0.f;
 #pragma unroll
     for (int v = 0; v < R1 / 4; ++v) {
-      const float4 x = ldg4(a0 + 4 * v);
+      const float4 x = *reinterpret_cast<const float4*>(a0 + 4 * v);
       t = fmaf(x.x, b[4 * v], t);
       t = fmaf(x.y, b[4 * v + 1], t);
       t = fmaf(x.z, b[4 * v + 2], t);
       t = fmaf(x.w, b[4 * v + 3], t);
     }
-    Ttab[(((size_t)tix * p0 + i0) * p1 + i1) * (Q0 * C) + threadIdx.x] = t;
+    dst[(size_t)i * dstride] = t;
   }
-}
-
-// rows that are not written by exactly one index start from zero (empty bags stay zero,
-// multi-index bags are accumulated with vector reductions)
-__global__ void __launch_bounds__(256)
-zero_rows_kernel(int64_t rows, int32_t D, const int32_t* __restrict__ rowcount,
-                 float* __restrict__ output) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= rows) return;
-  if (__ldg(rowcount + r) == 1) return;
-  float4* o = reinterpret_cast<float4*>(output + r * D);
-  for (int d = 0; d < D / 4; ++d) o[d] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------
@@ -284,8 +364,8 @@ zero_rows_kernel(int64_t rows, int32_t D, const int32_t* __restrict__ rowcount,
 template <int Q0, int Q1, int Q2, int R1, int R2, bool C2_SMEM>
 __global__ void __launch_bounds__(kFwdThreads)
 sorted_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
-                  const int32_t* __restrict__ srow, const int32_t* __restrict__ rowcount,
-                  float* __restrict__ output, int rows_per_warp, int core2_elems) {
+                  const int32_t* __restrict__ srow, float* __restrict__ output, int rows_per_warp,
+                  int core2_elems) {
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int COLS2 = R2 * Q2;
@@ -334,7 +414,8 @@ sorted_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __
   }
   for (int64_t w0 = s_begin; w0 < s_end; w0 += 32) {
     const uint32_t key = nkey;
-    const int32_t grow = ngrow;
+    const int32_t grow = ngrow & 0x7fffffff;
+    const int one = ((uint32_t)ngrow & kMultiBit) == 0;
     {  // prefetch the next window while this one is processed
       const int64_t my = w0 + 32 + lane;
       nkey = total_rows;
@@ -347,7 +428,6 @@ sorted_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __
     const bool kvalid = key < total_rows;
     const uint32_t gid = kvalid ? key / p2 : kInvalid;
     const int c2row = kvalid ? (int)((key / num_rows32) * p2 + (key - gid * p2)) : 0;
-    const int one = kvalid ? (__ldg(rowcount + grow) == 1) : 0;
     const int nrows = (int)((s_end - w0 < 32) ? (s_end - w0) : 32);
     int it = 0;
     while (it < nrows) {
@@ -474,9 +554,8 @@ sorted_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __
 template <int Q0, int Q1, int Q2, int R2, bool C2_SMEM>
 __global__ void __launch_bounds__(kFwdThreads)
 table_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
-                 const int32_t* __restrict__ srow, const int32_t* __restrict__ rowcount,
-                 const float* __restrict__ Ttab, float* __restrict__ output, int rows_per_warp,
-                 int core2_elems) {
+                 const int32_t* __restrict__ srow, const float* __restrict__ Ttab,
+                 float* __restrict__ output, int rows_per_warp, int core2_elems) {
   constexpr int A = Q0 * Q1;
   constexpr int LPR = A / 2;       // lanes per output row
   constexpr int RPW = 32 / LPR;    // rows per warp step
@@ -532,7 +611,8 @@ table_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __r
   }
   for (int64_t w0 = s_begin; w0 < s_end; w0 += 32) {
     const uint32_t key = nkey;
-    const int32_t grow = ngrow;
+    const int32_t grow = ngrow & 0x7fffffff;
+    const int one = ((uint32_t)ngrow & kMultiBit) == 0;
     {
       const int64_t my = w0 + 32 + lane;
       nkey = total_rows;
@@ -545,7 +625,6 @@ table_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __r
     const bool kvalid = key < total_rows;
     const uint32_t gid = kvalid ? key / p2 : kInvalid;
     const int c2row = kvalid ? (int)((key / num_rows32) * p2 + (key - gid * p2)) : 0;
-    const int one = kvalid ? (__ldg(rowcount + grow) == 1) : 0;
     const int nrows = (int)((s_end - w0 < 32) ? (s_end - w0) : 32);
     for (int it = 0; it < nrows; it += RPW) {
       const int src = it + sub;
@@ -757,7 +836,7 @@ sorted_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows,
           const int src = step * RPW + sub;
           const int64_t gr = __shfl_sync(0xffffffffu, grow_l, src & 31);
           if (src < nsame) {
-            const float* gp = d_output + (int64_t)gr * D;
+            const float* gp = d_output + (int64_t)(gr & 0x7fffffff) * D;
             float* dst = ring + ((step % NST) * RPW + sub) * D;
             for (int c = k2; c < CH; c += LPR) cp_async16(dst + 4 * c, gp + 4 * c);
           }
@@ -1107,10 +1186,23 @@ typedef int (*BwdLaunch)(const TTDev&, int64_t, uint32_t, const SortedWs&, const
 template <int Q0, int Q1, int Q2, int R1, int R2>
 int launch_table(const TTDev& tt, const SortedWs& w, cudaStream_t stream) {
   const int nb = tt.num_tables * tt.p[1];
-  int split = 1;
-  while (split < 8 && nb * split < 2 * kNumSMs && split * 4 < tt.p[0]) split *= 2;
+  // about four resident CTAs per SM, at least 8 i0 per CTA so the staging of core0 pays
+  int split = (int)ceil_div(4 * kNumSMs, nb);
+  if (split < 1) split = 1;
+  int per = (int)ceil_div(tt.p[0], split);
+  if (per < 8) per = 8;
+  if (per > 128) per = 128;      // 128 * Q0 * R1 floats of shared memory at most
+  split = (int)ceil_div(tt.p[0], per);
+  const size_t smem = sizeof(float) * (size_t)per * Q0 * R1;
+  auto kern = group_table_kernel<Q0, Q1, R1, R2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(float) * 128 * Q0 * R1)));
+    attr_set = true;
+  }
   prof_begin(K_TABLE, stream);
-  group_table_kernel<Q0, Q1, R1, R2><<<dim3(nb, split), Q0 * Q1 * R2, 0, stream>>>(tt, w.Ttab);
+  kern<<<dim3(nb, split), Q0 * Q1 * R2, smem, stream>>>(tt, w.Ttab, per);
   prof_end(K_TABLE, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -1160,8 +1252,7 @@ int launch_fwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
       if (rc != TTG_OK) return rc;
       prof_begin(K_FWD, stream);
       kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow,
-                                                          w.rowcount, w.Ttab, output, (int)rpw,
-                                                          core2_elems);
+                                                          w.Ttab, output, (int)rpw, core2_elems);
       prof_end(K_FWD, stream);
       TTG_LAUNCH_CHECK();
       return TTG_OK;
@@ -1174,8 +1265,8 @@ int launch_fwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
   int rc = fwd_grid(kern, smem, c2_smem ? 0 : 1, nnz, &grid, &rpw);
   if (rc != TTG_OK) return rc;
   prof_begin(K_FWD, stream);
-  kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow,
-                                                      w.rowcount, output, (int)rpw, core2_elems);
+  kern<<<(unsigned)grid, kFwdThreads, smem, stream>>>(tt, nnz, total_rows, w.skeys, w.srow, output,
+                                                      (int)rpw, core2_elems);
   prof_end(K_FWD, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -1313,24 +1404,39 @@ const Entry* find_entry(const TTDev& tt) {
   return nullptr;
 }
 
-// Index plan.  Default: bucket the rows by group (count, scan, scatter -- three small kernels);
-// deterministic == true: full radix sort of the keys (fixed order inside a group, so repeated
-// runs give bit-identical gradients).
+// Index plan.  plan_kernel (keys, bucket ranks, per-row counts) -> bucket_scan_kernel ->
+// bucket_scatter_kernel (rows of a group adjacent, accumulate bit, zero-fill of the output rows
+// that are not stored by exactly one index).  deterministic: the scatter is replaced by a stable
+// radix sort of the keys, so the order inside a group -- and with it the summation order of
+// d_core0 / d_core1 -- is fixed.  zero_only (forward with TTG_FLAG_PLAN_VALID): the plan in the
+// workspace is still valid, only the zero-fill is repeated.
 int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                const int64_t* rowidx, const int64_t* tableidx, const SortedWs& w,
-               bool deterministic, cudaStream_t stream) {
+               bool deterministic, float* output, bool zero_only, cudaStream_t stream) {
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
   const int32_t groups = tt.num_tables * tt.p[0] * tt.p[1];
-  TTG_CUDA(cudaMemsetAsync(w.rowcount, 0, sizeof(int32_t) * (size_t)tt.num_tables * B, stream));
-  if (!deterministic)
-    TTG_CUDA(cudaMemsetAsync(w.cnt, 0, sizeof(int32_t) * ((size_t)groups + 1), stream));
+  const int64_t out_rows = (int64_t)tt.num_tables * B;
+  const unsigned nblk = (unsigned)ceil_div(nnz, 256 * kPlanItems);
+  int32_t* rowcount = output ? w.rowcount : nullptr;
+  if (zero_only) {
+    prof_begin(K_SORT, stream);
+    bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(0, total_rows, (uint32_t)tt.p[2], groups,
+                                                    nullptr, nullptr, nullptr, nullptr, w.rowcount,
+                                                    nullptr, nullptr, output, out_rows, tt.D / 4);
+    prof_end(K_SORT, stream);
+    TTG_LAUNCH_CHECK();
+    return TTG_OK;
+  }
+  TTG_CUDA(cudaMemsetAsync(w.cnt, 0, output ? w.clear_bytes : w.cnt_bytes, stream));
   prof_begin(K_PLAN, stream);
-  plan_kernel<<<(unsigned)ceil_div(nnz, 256 * kPlanItems), 256, 0, stream>>>(
-      nnz, B, tt.num_rows, tt.num_tables, total_rows, indices, rowidx, tableidx, w.keys_in,
-      w.vals_in, w.rowcount, deterministic ? nullptr : w.cnt, (uint32_t)tt.p[2], groups);
+  plan_kernel<<<nblk, 256, 0, stream>>>(nnz, B, tt.num_rows, tt.num_tables, total_rows, indices,
+                                        rowidx, tableidx, w.keys_in, w.vals_in, w.ranks, w.cnt,
+                                        rowcount, (uint32_t)tt.p[2], groups);
   prof_end(K_PLAN, stream);
   TTG_LAUNCH_CHECK();
   prof_begin(K_SORT, stream);
+  bucket_scan_kernel<<<(unsigned)ceil_div(groups + 1, 4096), 1024, 0, stream>>>(w.cnt, w.base);
+  TTG_LAUNCH_CHECK();
   if (deterministic) {
     int end_bit = 1;
     while (end_bit < 32 && (1ull << end_bit) <= (uint64_t)total_rows) ++end_bit;
@@ -1339,16 +1445,31 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                                              (const int32_t*)w.vals_in, w.srow, (int)nnz, 0,
                                              end_bit, stream));
     count_launch(3);
-  } else {
-    bucket_scan_kernel<<<1, 1024, 0, stream>>>(groups + 1, w.cnt, w.base);
-    TTG_LAUNCH_CHECK();
-    bucket_scatter_kernel<<<(unsigned)ceil_div(nnz, 256 * kPlanItems), 256, 0, stream>>>(
-        nnz, total_rows, (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in, w.base, w.cnt, w.skeys,
-        w.srow);
-    TTG_LAUNCH_CHECK();
   }
+  bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(
+      nnz, total_rows, (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in,
+      deterministic ? nullptr : w.ranks, w.base, rowcount, w.skeys, w.srow, output, out_rows,
+      tt.D / 4);
+  TTG_LAUNCH_CHECK();
   prof_end(K_SORT, stream);
   return TTG_OK;
+}
+
+// tensor-core kernels: the group-table strategy on a shape tt_mma.cu is instantiated for
+bool use_mma(const TTDev& tt, const SortedWs& w, int32_t flags) {
+  return w.Ttab != nullptr && !(flags & TTG_FLAG_FFMA) && mma_supported(tt);
+}
+
+MmaPlan mma_plan(const SortedWs& w) {
+  MmaPlan pl;
+  pl.skeys = w.skeys;
+  pl.srow = w.srow;
+  pl.cnt = w.cnt;
+  pl.base = w.base;
+  pl.Ttab = w.Ttab;
+  pl.S = w.S;
+  pl.d0parts = w.d0parts;
+  return pl;
 }
 
 int check_common(const TTDev& tt, int64_t B, int64_t nnz, const char* who) {
@@ -1395,17 +1516,17 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
     set_error("sorted_forward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
   }
-  if (!(flags & TTG_FLAG_PLAN_VALID)) {
-    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
-                    stream);
-    if (rc != TTG_OK) return rc;
-  }
+  rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
+                  output, (flags & TTG_FLAG_PLAN_VALID) != 0, stream);
+  if (rc != TTG_OK) return rc;
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
-  const int64_t rows = (int64_t)tt.num_tables * B;
-  prof_begin(K_ZERO_ROWS, stream);
-  zero_rows_kernel<<<(unsigned)ceil_div(rows, 256), 256, 0, stream>>>(rows, tt.D, w.rowcount, output);
-  prof_end(K_ZERO_ROWS, stream);
-  TTG_LAUNCH_CHECK();
+  if (use_mma(tt, w, flags)) {
+    const bool tf32 = (flags & TTG_FLAG_TF32) != 0;
+    const MmaPlan pl = mma_plan(w);
+    rc = mma_table(tt, pl, tf32, stream);
+    if (rc != TTG_OK) return rc;
+    return mma_forward(tt, nnz, total_rows, pl, output, tf32, stream);
+  }
   return e->fwd(tt, nnz, total_rows, w, output, stream);
 }
 
@@ -1449,10 +1570,19 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
   const bool plan_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
   if (!plan_valid) {
     rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
-                    stream);
+                    nullptr, false, stream);
     if (rc != TTG_OK) return rc;
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
+  if (use_mma(tt, w, flags)) {
+    const bool tf32 = (flags & TTG_FLAG_TF32) != 0;
+    const MmaPlan pl = mma_plan(w);
+    if (!plan_valid) {  // otherwise the forward that built the plan also built the table
+      rc = mma_table(tt, pl, tf32, stream);
+      if (rc != TTG_OK) return rc;
+    }
+    return mma_backward(tt, nnz, total_rows, pl, d_output, dcore, optim, lr, eps, state, tf32, stream);
+  }
   BwdOpt opt;
   opt.optim = optim;
   opt.lr = lr;

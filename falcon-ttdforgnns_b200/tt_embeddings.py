@@ -41,8 +41,8 @@ def _cores_ok(tt_cores, T):
 
 
 def _plan_tag():
-    # a plan built by the bucket pass must not be reused by a caller asking for the sorted one
-    return "tt-det" if (EXTRA_FLAGS & _ttg.FLAG_DETERMINISTIC) else "tt"
+    # a plan (and group table) built under one set of flags is not reused under another
+    return "tt-%d" % EXTRA_FLAGS
 
 
 def _shape_tuple(p, q, r, num_tables):

@@ -50,8 +50,12 @@ enum {
   TTG_FLAG_PLAN_VALID = 2,    /* workspace already holds the index plan (and group table) of
                                  the SAME (indices, rowidx, nnz, B) and the cores have not
                                  changed since -- skip both (forward -> backward reuse)   */
-  TTG_FLAG_DETERMINISTIC = 4  /* full radix sort instead of the bucket plan: fixed summation
-                                 order, bit-identical gradients run to run             */
+  TTG_FLAG_DETERMINISTIC = 4, /* full radix sort instead of the bucket plan: fixed summation
+                                 order for d_core0 / d_core1 run to run                */
+  TTG_FLAG_TF32 = 8,          /* tensor-core kernels use plain TF32 operands (about 1e-3
+                                 relative) instead of the default 3xTF32 split, which keeps
+                                 fp32 accuracy (about 3e-7 relative)                    */
+  TTG_FLAG_FFMA = 16          /* fp32 FFMA kernels instead of the tensor-core kernels     */
 };
 
 /* TT table description: tt_p_shapes / tt_q_shapes / tt_ranks of the reference. */
@@ -83,8 +87,7 @@ const char* ttg_profile_name(int32_t id);
  *           FBTT/tt_embeddings.cpp:13-26,132)
  * output[tableidx[n]][rowidx[n]][:] += TT_row(indices[n]) for n < nnz; rows of `output`
  * that no index maps to are written as zeros (the reference returns at::zeros + RMW), so
- * `output` does not need to be initialised.  Precondition (what preprocess_indices
- * produces): rowidx is non-decreasing within a table.
+ * `output` does not need to be initialised.  (tableidx, rowidx) may come in any order.
  * workspace: ttg_tt_workspace_bytes(shape, B, nnz) bytes, 256-byte aligned; the same
  * (shape, B, nnz) gives the same layout, which is what TTG_FLAG_PLAN_VALID relies on.
  * ---------------------------------------------------------------------------------- */

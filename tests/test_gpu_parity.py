@@ -31,11 +31,12 @@ def _fwd(te, c, cores, indices, rowidx, B, num_tables=1, tableidx=None):
                          indices, rowidx, tb, cores)
 
 
-@pytest.fixture(params=[0, 1], ids=["sorted", "generic"])
+@pytest.fixture(params=[0, 16, 1], ids=["mma", "ffma", "generic"])
 def te(request, ttg_lib):
-    import _ttg
+    """default = tensor-core kernels (3xTF32) where the shape has them, FLAG_FFMA = the fp32 FFMA
+    sorted kernels, FLAG_FORCE_GENERIC = the shape-generic kernels"""
     import tt_embeddings
-    tt_embeddings.EXTRA_FLAGS = _ttg.FLAG_FORCE_GENERIC if request.param else 0
+    tt_embeddings.EXTRA_FLAGS = request.param
     yield tt_embeddings
     tt_embeddings.EXTRA_FLAGS = 0
 
@@ -153,6 +154,18 @@ def test_multiple_tables(te):
         assert rel_err(gd[t].cpu().numpy(), wd[t]) < TOL
 
 
+@pytest.mark.parametrize("name", ["products_small_bags", "cora_r16_bags"])
+def test_rowidx_in_any_order(te, golden, name):
+    """The reference accumulates output[rowidx[n]] for any rowidx order
+    (FBTT/tt_embeddings_cuda.cu:1027-1078); shuffling (indices, rowidx) together changes nothing."""
+    c = golden[name]
+    cores = [_t(x) for x in case_cores(c)]
+    B = c["offsets"].size - 1
+    perm = np.random.default_rng(4).permutation(c["indices"].size)
+    out = _fwd(te, c, cores, _t(c["indices"][perm]), _t(c["rowidx"][perm]), B)
+    assert rel_err(out[0].cpu().numpy(), c["out64"]) < TOL
+
+
 def test_out_of_range_indices_contribute_nothing(te, golden):
     c = golden["products_small"]
     p, q, r = list(c["p"]), list(c["q"]), list(c["ranks"])
@@ -207,11 +220,13 @@ def test_medium_batch_against_oracle(ttg_lib, shape):
         assert rel_err(gd[t].cpu().numpy(), wd[t]) < TOL, "core %d" % t
 
 
-def test_full_size_products_properties(ttg_lib):
+@pytest.mark.parametrize("base_flags", [0, 16], ids=["mma", "ffma"])
+def test_full_size_products_properties(ttg_lib, base_flags):
     """BASELINE config 2 size (262,144 distinct ids of 2,449,029): sorted kernels == generic
     kernels, permutation equivariance, linearity of the gradient in d_output."""
     import _ttg
     import tt_embeddings as te
+    te.EXTRA_FLAGS = base_flags
     p, q, r, n_emb = SHAPES["products"]
     D = 100
     cores = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 12)]
@@ -225,7 +240,7 @@ def test_full_size_products_properties(ttg_lib):
     try:
         out_g = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx, row, tb, cores)
     finally:
-        te.EXTRA_FLAGS = 0
+        te.EXTRA_FLAGS = base_flags
     assert float((out - out_g).abs().max() / out_g.abs().max()) < TOL
     # permutation equivariance: looking up a permuted index list permutes the rows
     perm = torch.randperm(nnz, generator=g).to(DEV)
@@ -242,7 +257,7 @@ def test_full_size_products_properties(ttg_lib):
     try:
         gg = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
     finally:
-        te.EXTRA_FLAGS = 0
+        te.EXTRA_FLAGS = base_flags
     for a, b in zip(gs, gg):
         assert float((a - b).abs().max() / b.abs().max()) < 5e-5   # atomics reorder fp32 sums
     g2 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, (2.0 * dO).contiguous(), cores)
@@ -254,16 +269,47 @@ def test_full_size_products_properties(ttg_lib):
     for a, b in zip(gs, gs2):   # bucket plan: order inside a group is arbitrary -> fp32 reorder
         assert float((a - b).abs().max() / b.abs().max()) < 1e-6
     # TTG_FLAG_DETERMINISTIC: radix-sorted plan, fixed summation order for core0 / core1
-    te.EXTRA_FLAGS = _ttg.FLAG_DETERMINISTIC
+    te.EXTRA_FLAGS = base_flags | _ttg.FLAG_DETERMINISTIC
     try:
         gd1 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
         gd2 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
     finally:
-        te.EXTRA_FLAGS = 0
+        te.EXTRA_FLAGS = base_flags
     assert torch.equal(gd1[0], gd2[0]) and torch.equal(gd1[1], gd2[1])
     assert float((gd1[2] - gd2[2]).abs().max() / gd1[2].abs().max()) < 1e-6
     for a, b in zip(gs, gd1):
         assert float((a - b).abs().max() / b.abs().max()) < 1e-6
+    te.EXTRA_FLAGS = 0
+
+
+def test_tf32_mode_stated_bound(ttg_lib):
+    """TTG_FLAG_TF32: single-pass TF32 tensor-core kernels.  Stated bound: 3e-3 of the tensor's
+    max (TF32 has a 10-bit mantissa; the default 3xTF32 mode is held to 1e-5 everywhere else)."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["products"]
+    D = 100
+    cores_cpu = _random_cores(p, q, r, n_emb, 21)
+    cores = [c.to(DEV) for c in cores_cpu]
+    rng = np.random.default_rng(5)
+    nnz = 40000
+    idx = rng.integers(0, 60000, size=nnz).astype(np.int64)     # ~430 groups, dense in groups
+    row = np.arange(nnz, dtype=np.int64)
+    dO = (rng.random(size=(1, nnz, D)).astype(np.float32) * 0.1)
+    cn = [c.numpy() for c in cores_cpu]
+    want = orc.tt_forward(p, q, r, cn, idx, row, nnz)
+    wd = orc.tt_backward_dense(p, q, r, cn, idx, row, dO)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    for flags, tol in ((_ttg.FLAG_TF32, 3e-3), (0, TOL)):
+        te.EXTRA_FLAGS = flags
+        try:
+            got = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+            gd = te.tt_dense_backward(1000, D, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), cores)
+        finally:
+            te.EXTRA_FLAGS = 0
+        assert rel_err(got.cpu().numpy(), want) < tol
+        for t in range(3):
+            assert rel_err(gd[t].cpu().numpy(), wd[t]) < tol, "core %d" % t
 
 
 def test_full_table_arange_arxiv(ttg_lib):
