@@ -26,26 +26,28 @@ namespace {
 
 constexpr int kThreads = 512;            // row kernels: one CTA per SM, 16 warps
 constexpr int kWarps = kThreads / 32;
-constexpr int kFwdRB = 16;               // rows per forward staging buffer
-constexpr int kBwdRB = 8;                // rows per backward d_output buffer (two per warp)
 constexpr int kCoreThreads = 256;        // table / cores kernels
 constexpr int kCoreWarps = kCoreThreads / 32;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr size_t kSmemMax = 227 * 1024;
 
 // ---- TF32 helpers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-
+// mma.sync .tf32 ignores the low 13 bits of its operands and cvt.rna.tf32.f32 equals
+// (bits + 0x1000) & 0xffffe000 for finite values (both checked on B200 by
+// profiles/tools/tf32_probe.cu; ptxas expands the cvt into five instructions).  So:
+//   TERMS == 1: operand = bits + 0x1000              (round to nearest, the hardware drops the rest)
+//   TERMS == 3: hi = (bits + 0x1000) & 0xffffe000, lo = x - hi  (exact in fp32; the hardware keeps
+//               its top 11 bits, i.e. x is represented to about 2^-21)
 template <int TERMS>
 struct Frag {  // one operand register: hi part and (TERMS == 3) lo part
   uint32_t hi, lo;
   __device__ __forceinline__ void set(float x) {
-    hi = to_tf32(x);
-    if (TERMS == 3) lo = to_tf32(x - __uint_as_float(hi));
+    if (TERMS == 3) {
+      hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+      lo = __float_as_uint(x - __uint_as_float(hi));
+    } else {
+      hi = __float_as_uint(x) + 0x1000u;
+    }
   }
   __device__ __forceinline__ void set_split(float h, float l) {  // already split
     hi = __float_as_uint(h);
@@ -53,14 +55,31 @@ struct Frag {  // one operand register: hi part and (TERMS == 3) lo part
   }
 };
 
+__device__ __forceinline__ float tf32_hi(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                                          uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
       "{%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+
+// one of the 3xTF32 terms (0: lo*hi, 1: hi*lo, 2: hi*hi); callers loop term-major over several
+// independent accumulators so that back-to-back HMMAs never depend on each other
+template <int TERMS>
+__device__ __forceinline__ void mma_term(int term, float (&c)[4], const Frag<TERMS> (&a)[4],
+                                         const Frag<TERMS> (&b)[2]) {
+  if (term == 0)
+    mma_tf32(c, a[0].lo, a[1].lo, a[2].lo, a[3].lo, b[0].hi, b[1].hi);
+  else if (term == 1)
+    mma_tf32(c, a[0].hi, a[1].hi, a[2].hi, a[3].hi, b[0].lo, b[1].lo);
+  else
+    mma_tf32(c, a[0].hi, a[1].hi, a[2].hi, a[3].hi, b[0].hi, b[1].hi);
+}
+constexpr int first_term(int terms) { return terms == 3 ? 0 : 2; }
 
 // c += a * b with a = 16x8 fragment (4 regs), b = 8x8 fragment (2 regs); small terms first
 template <int TERMS>
@@ -125,6 +144,63 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+// Stage core2 into shared memory: every thread first has kStageU independent 16-byte loads in
+// flight (the loop used to wait for one L2 round trip per element), then scatters them.
+constexpr int kStageU = 6;
+template <int NT, typename F>
+__device__ __forceinline__ void stage_core2(const float* __restrict__ core2, int nelem, F&& put) {
+  const int n4 = nelem / 4;
+  for (int base4 = 0; base4 < n4; base4 += NT * kStageU) {
+    float4 v[kStageU];
+#pragma unroll
+    for (int u = 0; u < kStageU; ++u) {
+      const int i4 = base4 + u * NT + (int)threadIdx.x;
+      v[u] = (i4 < n4) ? ldg4(core2 + 4 * i4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kStageU; ++u) {
+      const int i4 = base4 + u * NT + (int)threadIdx.x;
+      if (i4 < n4) {
+        put(4 * i4, v[u].x);
+        put(4 * i4 + 1, v[u].y);
+        put(4 * i4 + 2, v[u].z);
+        put(4 * i4 + 3, v[u].w);
+      }
+    }
+  }
+}
+
+// Shared-memory float add without the serialising CAS loop nvcc emits for atomicAdd(float*) on
+// shared memory: callers first read all their targets, then try one compare-and-swap each (all
+// independent, so their latencies overlap), and only the rare loser falls back to the loop.
+__device__ __forceinline__ uint32_t lds_volatile_u32(const float* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cas_shared_u32(float* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;"
+               : "=r"(old)
+               : "r"(smem_u32(p)), "r"(cmp), "r"(val)
+               : "memory");
+  return old;
+}
+template <int N>
+__device__ __forceinline__ void shared_add_batch(float* const (&addr)[N], const float (&val)[N],
+                                                 const bool (&on)[N]) {
+  uint32_t old[N], got[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) old[i] = on[i] ? lds_volatile_u32(addr[i]) : 0u;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    got[i] = on[i] ? cas_shared_u32(addr[i], old[i], __float_as_uint(__uint_as_float(old[i]) + val[i]))
+                   : old[i];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (got[i] != old[i]) atomicAdd(addr[i], val[i]);
+}
+
 // position of core2[i2][k2][j2] inside the shared-memory copies ("pair" = i2 * Q2 + j2 selects a
 // 16-float slot holding the 16 k2 values of one output column)
 //   forward : lane tid reads k2 = tid, tid+4, tid+8, tid+12 as one 16-byte load
@@ -157,9 +233,9 @@ mma_table_kernel(TTDev tt, float* __restrict__ Ttab, int mtiles_per_cta) {
       const int nt = r / 64, l = (r % 64) >> 1, h = r & 1;
       const int k1 = (l & 3) + 4 * h + 8 * ks, c = (l >> 2) + 8 * nt;
       const float v = __ldg(b1p + k1 * C + c);
-      const float hi = __uint_as_float(to_tf32(v));
+      const float hi = tf32_hi(v);
       bs_hi[e] = hi;
-      if (TERMS == 3) bs_lo[e] = __uint_as_float(to_tf32(v - hi));
+      if (TERMS == 3) bs_lo[e] = v - hi;
     }
   }
   __syncthreads();
@@ -209,9 +285,36 @@ mma_table_kernel(TTDev tt, float* __restrict__ Ttab, int mtiles_per_cta) {
 }
 
 // ------------------------------------------------------------------------------------------
-// forward rows.  Persistent CTAs, one contiguous run of sorted rows per warp, 16-row staging
-// buffers.  For every run of rows of one group inside a buffer ("segment") the output columns
-// (n, j2) are the M side (16 per tile), (j0 j1) the N side, k2 the K side.
+// Row kernels.  The sorted rows of one group that sit in one staging buffer form a "segment";
+// a segment is processed in tiles of TR = 16 / Q2 rows, i.e. 16 "pairs" (row, j2) of which
+// NP = TR * Q2 are real (15 of 16 at Q2 = 5, 16 of 16 at Q2 = 8).  Which (row, j2) a lane's
+// fragment registers stand for depends on the lane only, never on the tile, so the whole index
+// arithmetic of a tile is a handful of compares against the rows left in the segment.
+// ------------------------------------------------------------------------------------------
+constexpr int tile_rows(int q2) { return 16 / q2; }
+constexpr int fwd_rb(int q2) { return (16 / tile_rows(q2)) * tile_rows(q2); }   // 15 / 16 rows
+constexpr int bwd_rb(int q2) { return (q2 <= 5 ? 3 : 4) * tile_rows(q2); }      // 9 / 8 rows
+constexpr int kC2Stride = 20;  // forward: floats per (i2, j2) slot; 20 keeps 8 slots on 32 banks
+
+struct PairSlot {
+  int row;   // row inside the tile, 99 for the padding pairs
+  int j2;
+};
+template <int Q2>
+__device__ __forceinline__ PairSlot pair_slot(int p) {
+  PairSlot s;
+  s.row = p / Q2;
+  s.j2 = p - s.row * Q2;
+  if (p >= tile_rows(Q2) * Q2) {
+    s.row = 99;
+    s.j2 = 0;
+  }
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward rows.  Persistent CTAs, one contiguous run of sorted rows per warp.  M side = pairs,
+// N side = (j0 j1), K side = k2:  out[(n j2), (j0 j1)] = sum_k2 core2[i2_n][k2, j2] tr0[(j0 j1), k2]
 // ------------------------------------------------------------------------------------------
 template <int Q0, int Q1, int Q2, int R2, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -221,25 +324,30 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;
-  constexpr int RB = kFwdRB;
+  constexpr int TR = tile_rows(Q2);
+  constexpr int RB = fwd_rb(Q2);
+  constexpr int CS = kC2Stride;
   static_assert(R2 == 16, "forward fragment layout is written for r2 = 16");
-  static_assert(D % 4 == 0, "rows must be multiples of 16 bytes");
+  static_assert(D % 4 == 0 && A % 2 == 0 && 2 * RB <= 32, "layout");
   extern __shared__ __align__(128) float smem[];
-  float* c2hi = smem;                                            // [npairs_c2][16]
-  float* c2lo = smem + (size_t)npairs_c2 * 16;                   // TERMS == 3 only
-  float* stage_all = smem + (size_t)npairs_c2 * 16 * (TERMS == 3 ? 2 : 1);
+  float* c2hi = smem;                                            // [npairs_c2][CS]
+  float* c2lo = smem + (size_t)npairs_c2 * CS;                   // TERMS == 3 only
+  float* stage_all = smem + (size_t)npairs_c2 * CS * (TERMS == 3 ? 2 : 1);
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
-  for (int e = threadIdx.x; e < npairs_c2 * 16; e += kThreads) {
+  stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
     const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
     const int k2 = rem / Q2, j2 = rem % Q2;
-    const float v = __ldg(tt.core[2] + e);
-    const float hi = __uint_as_float(to_tf32(v));
-    const int dst = (i2row * Q2 + j2) * 16 + fwd_slot(k2);
-    c2hi[dst] = hi;
-    if (TERMS == 3) c2lo[dst] = __uint_as_float(to_tf32(v - hi));
-  }
+    const int dst = (i2row * Q2 + j2) * CS + k2;
+    if (TERMS == 3) {
+      const float hi = tf32_hi(v);
+      c2hi[dst] = hi;
+      c2lo[dst] = v - hi;
+    } else {
+      c2hi[dst] = __uint_as_float(__float_as_uint(v) + 0x1000u);
+    }
+  });
   __syncthreads();
 
   const uint32_t p2 = tt.p[2];
@@ -250,31 +358,55 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
   const int64_t s_end = (s_begin + rows_per_warp < nnz) ? s_begin + rows_per_warp : nnz;
   if (s_begin >= s_end) return;
 
-  // window of 32 sorted rows: lane l owns row w0 + l; the next window is prefetched
+  // the two pairs whose output columns this lane's accumulator rows hold
+  const PairSlot sl0 = pair_slot<Q2>(gid), sl1 = pair_slot<Q2>(gid + 8);
+  // last n-tile: columns (j0 j1) >= A do not exist
+  const bool last_nt_ok = (8 * (NTL - 1) + 2 * tid + 1) < A;
+
+  Frag<TERMS> bt[NTL][2][2];   // tr0 of the group held, N-side operand
+  float traw[NTL][2][2];       // tr0 of the group that comes next, loaded one segment ahead
+  uint32_t g_held = kInvalid, g_pref = kInvalid;
+  // b0 = T[col][tid + 8 ks], b1 = T[col][tid + 4 + 8 ks], col = gid + 8 nt
+  auto load_T = [&](uint32_t gq) {
+    const float* tp = Ttab + (size_t)gq * (A * 16) + gid * 16 + tid;
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) {
+      const bool cv = (8 * nt + 7 < A) || (gid + 8 * nt < A);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        traw[nt][ks][0] = cv ? __ldg(tp + nt * 128 + 8 * ks) : 0.f;
+        traw[nt][ks][1] = cv ? __ldg(tp + nt * 128 + 8 * ks + 4) : 0.f;
+      }
+    }
+    g_pref = gq;
+  };
+
+  // window of 2 RB sorted rows: lane l owns row w0 + l; the next window is prefetched
   uint32_t nkey = total_rows;
   int32_t nsr = 0;
-  if (s_begin + lane < s_end) {
+  if (lane < 2 * RB && s_begin + lane < s_end) {
     nkey = __ldg(skeys + s_begin + lane);
     nsr = __ldg(srow + s_begin + lane);
   }
-  for (int64_t w0 = s_begin; w0 < s_end; w0 += 32) {
+  for (int64_t w0 = s_begin; w0 < s_end; w0 += 2 * RB) {
     const uint32_t key = nkey;
     const int32_t sr = nsr;
     nkey = total_rows;
     nsr = 0;
-    if (w0 + 32 + lane < s_end) {
-      nkey = __ldg(skeys + w0 + 32 + lane);
-      nsr = __ldg(srow + w0 + 32 + lane);
+    if (lane < 2 * RB && w0 + 2 * RB + lane < s_end) {
+      nkey = __ldg(skeys + w0 + 2 * RB + lane);
+      nsr = __ldg(srow + w0 + 2 * RB + lane);
     }
-    const int nwin = (int)((s_end - w0 < 32) ? (s_end - w0) : 32);
+    const int nwin = (int)((s_end - w0 < 2 * RB) ? (s_end - w0) : 2 * RB);
     const bool kvalid = key < total_rows;
     const uint32_t g = kvalid ? key / p2 : kInvalid;
+    const uint32_t ng = (nkey < total_rows) ? nkey / p2 : kInvalid;   // lane 0: first group of the next window
     const int c2pair = kvalid ? (int)((key / num_rows32) * p2 + (key - g * p2)) * Q2 : 0;
     const uint32_t gprev = __shfl_up_sync(0xffffffffu, g, 1);
-    const bool bnd = (lane < nwin) && ((lane & (RB - 1)) == 0 || g != gprev);
+    const bool bnd = (lane < nwin) && (lane == 0 || lane == RB || g != gprev);
     const uint32_t bmask = __ballot_sync(0xffffffffu, bnd);
 #pragma unroll 1
-    for (int h = 0; h < 32 / RB; ++h) {
+    for (int h = 0; h < 2; ++h) {
       const int nrows = (nwin - h * RB < RB) ? nwin - h * RB : RB;
       if (nrows <= 0) break;
       // the bulk stores of the previous buffer must have read the stage
@@ -287,66 +419,73 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
         const int b = m ? (__ffs(m) - 1) : nrows;
         const uint32_t gs = __shfl_sync(0xffffffffu, g, h * RB + a);
         if (gs == kInvalid) break;  // invalid keys sort to the end
-        // tr0 of the group as the N-side operand: b0 = T[col][tid + 8 ks], b1 = T[col][tid + 4 + 8 ks]
-        Frag<TERMS> bt[NTL][2][2];
-        {
-          const float* tp = Ttab + (size_t)gs * (A * 16);
+        if (gs != g_held) {
+          if (gs != g_pref) load_T(gs);   // first segment of the run: nothing was prefetched
+          g_held = gs;
 #pragma unroll
-          for (int nt = 0; nt < NTL; ++nt) {
-            const int col = gid + 8 * nt;
+          for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              bt[nt][ks][0].set(col < A ? __ldg(tp + col * 16 + tid + 8 * ks) : 0.f);
-              bt[nt][ks][1].set(col < A ? __ldg(tp + col * 16 + tid + 4 + 8 * ks) : 0.f);
+              bt[nt][ks][0].set(traw[nt][ks][0]);
+              bt[nt][ks][1].set(traw[nt][ks][1]);
+            }
+        }
+        {
+          // the group after this segment: next boundary of the window, else the next window
+          const int sh = h * RB + a + 1;
+          const uint32_t wm = (sh < 32) ? (bmask >> sh) : 0u;
+          const int nxt = wm ? (h * RB + a + __ffs(wm)) : 0;
+          uint32_t gn = wm ? g : ng;
+          gn = __shfl_sync(0xffffffffu, gn, nxt);
+          if (gn != kInvalid && gn != g_held) load_T(gn);
+        }
+#pragma unroll 1
+        for (int rb = a; rb < b; rb += TR) {
+          const int nrem = b - rb;
+          const bool v0 = sl0.row < nrem, v1 = sl1.row < nrem;
+          const int r0 = rb + (v0 ? sl0.row : 0), r1 = rb + (v1 ? sl1.row : 0);
+          const int cp0 = __shfl_sync(0xffffffffu, c2pair, h * RB + r0) + sl0.j2;
+          const int cp1 = __shfl_sync(0xffffffffu, c2pair, h * RB + r1) + sl1.j2;
+          const float* ph0 = c2hi + cp0 * CS + tid;
+          const float* ph1 = c2hi + cp1 * CS + tid;
+          Frag<TERMS> af[2][4];
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            if (TERMS == 3) {
+              const float* pl0 = ph0 + (size_t)npairs_c2 * CS;
+              const float* pl1 = ph1 + (size_t)npairs_c2 * CS;
+              af[ks][0].set_split(ph0[8 * ks], pl0[8 * ks]);
+              af[ks][1].set_split(ph1[8 * ks], pl1[8 * ks]);
+              af[ks][2].set_split(ph0[8 * ks + 4], pl0[8 * ks + 4]);
+              af[ks][3].set_split(ph1[8 * ks + 4], pl1[8 * ks + 4]);
+            } else {
+              af[ks][0].set_split(ph0[8 * ks], 0.f);
+              af[ks][1].set_split(ph1[8 * ks], 0.f);
+              af[ks][2].set_split(ph0[8 * ks + 4], 0.f);
+              af[ks][3].set_split(ph1[8 * ks + 4], 0.f);
             }
           }
-        }
-        const int np = (b - a) * Q2;      // output columns (n, j2) of this segment
-        const int P0 = a * Q2;
-#pragma unroll 1
-        for (int mt = 0; mt * 16 < np; ++mt) {
-          const int pl0 = mt * 16 + gid, pl1 = pl0 + 8;
-          const bool v0 = pl0 < np, v1 = pl1 < np;
-          const int Pa = P0 + (v0 ? pl0 : 0), Pb = P0 + (v1 ? pl1 : 0);
-          const int rr0 = Pa / Q2, j20 = Pa - rr0 * Q2;
-          const int rr1 = Pb / Q2, j21 = Pb - rr1 * Q2;
-          const int cp0 = __shfl_sync(0xffffffffu, c2pair, h * RB + rr0) + j20;
-          const int cp1 = __shfl_sync(0xffffffffu, c2pair, h * RB + rr1) + j21;
-          const float4 h0 = *reinterpret_cast<const float4*>(c2hi + cp0 * 16 + tid * 4);
-          const float4 h1 = *reinterpret_cast<const float4*>(c2hi + cp1 * 16 + tid * 4);
-          float4 l0 = make_float4(0.f, 0.f, 0.f, 0.f), l1 = l0;
-          if (TERMS == 3) {
-            l0 = *reinterpret_cast<const float4*>(c2lo + cp0 * 16 + tid * 4);
-            l1 = *reinterpret_cast<const float4*>(c2lo + cp1 * 16 + tid * 4);
-          }
-          Frag<TERMS> af[2][4];
-          af[0][0].set_split(h0.x, l0.x);
-          af[0][1].set_split(h1.x, l1.x);
-          af[0][2].set_split(h0.y, l0.y);
-          af[0][3].set_split(h1.y, l1.y);
-          af[1][0].set_split(h0.z, l0.z);
-          af[1][1].set_split(h1.z, l1.z);
-          af[1][2].set_split(h0.w, l0.w);
-          af[1][3].set_split(h1.w, l1.w);
+          float* s0 = stage + r0 * D + sl0.j2 + 2 * tid * Q2;
+          float* s1 = stage + r1 * D + sl1.j2 + 2 * tid * Q2;
           float acc[NTL][4];
 #pragma unroll
-          for (int nt = 0; nt < NTL; ++nt) {
-            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+          for (int nt = 0; nt < NTL; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) mma_terms<TERMS>(acc[nt], af[ks], bt[nt][ks]);
-          }
-          float* s0 = stage + rr0 * D + j20;
-          float* s1 = stage + rr1 * D + j21;
+          for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+              for (int nt = 0; nt < NTL; ++nt) mma_term<TERMS>(term, acc[nt], af[ks], bt[nt][ks]);
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) {
-            const int col = 8 * nt + 2 * tid;
-            if (col < A) {
-              if (v0) s0[col * Q2] = acc[nt][0];
-              if (v1) s1[col * Q2] = acc[nt][2];
+            const bool cv = (8 * nt + 7 < A) || last_nt_ok;
+            if (cv && v0) {
+              s0[8 * nt * Q2] = acc[nt][0];
+              s0[8 * nt * Q2 + Q2] = acc[nt][1];
             }
-            if (col + 1 < A) {
-              if (v0) s0[(col + 1) * Q2] = acc[nt][1];
-              if (v1) s1[(col + 1) * Q2] = acc[nt][3];
+            if (cv && v1) {
+              s1[8 * nt * Q2] = acc[nt][2];
+              s1[8 * nt * Q2 + Q2] = acc[nt][3];
             }
           }
         }
@@ -354,7 +493,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
       fence_proxy_async();
       __syncwarp();
       {
-        const int src = h * RB + (lane & (RB - 1));
+        const int src = h * RB + (lane < RB ? lane : 0);
         const uint32_t k_r = __shfl_sync(0xffffffffu, key, src);
         const int32_t sr_r = __shfl_sync(0xffffffffu, sr, src);
         if (lane < nrows && k_r < total_rows) {
@@ -372,8 +511,10 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
 }
 
 // ------------------------------------------------------------------------------------------
-// backward rows.  Same work split as the FFMA kernel it replaces: a group belongs to the chunk
-// it starts in.  d_output rows arrive eight at a time through a two-slot ring per warp.
+// backward rows.  A group belongs to the chunk it starts in (chunks = equal runs of sorted rows,
+// one per warp).  d_output rows arrive RB at a time through a two-slot ring per warp.
+//   g2[k2, pair]   = sum_j  tr0[j, k2] dO[pair.row][j, pair.j2]        -> d_core2 (shared atomics)
+//   S^T[k2, j]    += sum_pair core2[pair.i2][k2, pair.j2] dO[pair.row][j, pair.j2]
 // ------------------------------------------------------------------------------------------
 template <int Q0, int Q1, int Q2, int R2, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -387,8 +528,10 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;       // n-tiles of S^T (columns j0 j1)
   constexpr int KSA = (A + 7) / 8;       // k-steps of g2 = tr0^T dO (k = j0 j1)
-  constexpr int RB = kBwdRB;
-  static_assert(R2 == 16, "backward fragment layout is written for r2 = 16");
+  constexpr int A4 = A / 4;              // j = tid + 4 m, m < A4
+  constexpr int TR = tile_rows(Q2);
+  constexpr int RB = bwd_rb(Q2);
+  static_assert(R2 == 16 && A % 4 == 0, "backward fragment layout is written for r2 = 16");
   extern __shared__ __align__(128) float smem[];
   float* c2s = smem;                                   // [npairs_c2][16], bwd_slot order
   float* acc2 = smem + (size_t)npairs_c2 * 16;         // d_core2 of this CTA, global layout
@@ -397,13 +540,13 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
-  for (int e = threadIdx.x; e < npairs_c2 * 16; e += kThreads) {
+  stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
     const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
     const int k2 = rem / Q2, j2 = rem % Q2;
     const int pair = i2row * Q2 + j2;
-    c2s[pair * 16 + bwd_slot(pair, k2)] = __ldg(tt.core[2] + e);
+    c2s[pair * 16 + bwd_slot(pair, k2)] = v;
     acc2[e] = 0.f;
-  }
+  });
   if (lane == 0) {
     mbar_init(bars + wib * 2, 1);
     mbar_init(bars + wib * 2 + 1, 1);
@@ -421,6 +564,19 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   const int64_t gw = (int64_t)blockIdx.x * kWarps + wib;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
 
+  // what this lane's fragment registers stand for, tile after tile
+  PairSlot sN[2], sC[2][2], sK[2][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    sN[h] = pair_slot<Q2>(8 * h + gid);                 // g2: column of the dO operand
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sC[h][e] = pair_slot<Q2>(8 * h + 2 * tid + e);    // g2: accumulator columns
+      sK[h][e] = pair_slot<Q2>(8 * h + tid + 4 * e);    // S: k index of both operands
+    }
+  }
+  const bool last_nt_ok = gid + 8 * (NTL - 1) < A;      // column j of the last n-tile of S^T exists
+
   for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
     const int64_t nom_begin = chunk * chunk_rows;
     const int64_t nom_end = (nom_begin + chunk_rows < nvalid) ? nom_begin + chunk_rows : nvalid;
@@ -435,38 +591,61 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
     }
     if (s >= e_run) continue;
 
-    // ---- prefetch of d_output rows: buffer k = rows [s + 8k, s + 8k + 8) into slot k & 1
-    auto issue = [&](int64_t row0, int slot) {
+    // ---- prefetch of d_output rows: buffer k = rows [s + RB k, s + RB k + RB) into slot k & 1
+    // (the caller passes the output row of sorted row row0 + lane, loaded one buffer earlier)
+    auto issue = [&](int64_t row0, int slot, int32_t r) {
       const int n = (int)((e_run - row0 < RB) ? (e_run - row0) : RB);
       if (n <= 0) return;
       if (lane == 0) mbar_expect_tx(bar + slot, (uint32_t)(n * D * 4));
       __syncwarp();
-      if (lane < n) {
-        const int32_t r = __ldg(srow + row0 + lane) & 0x7fffffff;
-        bulk_load(ring + ((size_t)slot * RB + lane) * D, d_output + (int64_t)r * D, D * 4, bar + slot);
+      if (lane < n)
+        bulk_load(ring + ((size_t)slot * RB + lane) * D, d_output + (int64_t)(r & 0x7fffffff) * D,
+                  D * 4, bar + slot);
+    };
+    // lanes [0, RB) look at the current / next buffer, lanes [RB, 2 RB) one buffer further
+    auto load_meta = [&](int64_t row0, uint32_t& k, int32_t& r) {
+      k = total_rows;
+      r = 0;
+      if (lane < 2 * RB && row0 + lane < e_run) {
+        k = __ldg(skeys + row0 + lane);
+        r = __ldg(srow + row0 + lane);
       }
     };
-    issue(s, 0);
+    uint32_t nkey;
+    int32_t nsr;
+    load_meta(s, nkey, nsr);
+    issue(s, 0, nsr);
 
-    uint32_t g_cur = kInvalid;
+    uint32_t g_cur = kInvalid, g_pref = kInvalid;
     Frag<TERMS> ta[KSA][4];          // tr0^T of g_cur as the M-side operand of g2
+    float traw[KSA][4];              // tr0^T of the group that comes next
+    // a0 = T[j][gid], a1 = T[j][gid + 8], a2 = T[j + 4][gid], a3 = T[j + 4][gid + 8], j = tid + 8 ks
+    auto load_T = [&](uint32_t gq) {
+      const float* tp = Ttab + (size_t)gq * (A * 16) + tid * 16 + gid;
+#pragma unroll
+      for (int ks = 0; ks < KSA; ++ks) {
+        const bool lo_ok = 2 * ks < A4, hi_ok = 2 * ks + 1 < A4;
+        traw[ks][0] = lo_ok ? __ldg(tp + ks * 128) : 0.f;
+        traw[ks][1] = lo_ok ? __ldg(tp + ks * 128 + 8) : 0.f;
+        traw[ks][2] = hi_ok ? __ldg(tp + ks * 128 + 64) : 0.f;
+        traw[ks][3] = hi_ok ? __ldg(tp + ks * 128 + 72) : 0.f;
+      }
+      g_pref = gq;
+    };
     float Sacc[NTL][4];
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt) Sacc[nt][0] = Sacc[nt][1] = Sacc[nt][2] = Sacc[nt][3] = 0.f;
 
     auto flush_S = [&]() {
       if (g_cur == kInvalid) return;
-      float* sp = Sbuf + (size_t)g_cur * (A * 16);
+      float* sp = Sbuf + (size_t)g_cur * (A * 16) + 2 * tid * 16 + gid;
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
-        const int col = 8 * nt + 2 * tid;
-        if (col < A) {
-          sp[col * 16 + gid] = Sacc[nt][0];
-          sp[col * 16 + gid + 8] = Sacc[nt][2];
-        }
-        if (col + 1 < A) {
-          sp[(col + 1) * 16 + gid] = Sacc[nt][1];
-          sp[(col + 1) * 16 + gid + 8] = Sacc[nt][3];
+        if ((8 * nt + 7 < A) || (8 * nt + 2 * tid + 1 < A)) {
+          sp[nt * 128] = Sacc[nt][0];
+          sp[nt * 128 + 8] = Sacc[nt][2];
+          sp[nt * 128 + 16] = Sacc[nt][1];
+          sp[nt * 128 + 24] = Sacc[nt][3];
         }
       }
     };
@@ -475,10 +654,10 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
 #pragma unroll 1
     for (int64_t w0 = s; w0 < e_run; w0 += RB, slot ^= 1) {
       const int nrows = (int)((e_run - w0 < RB) ? (e_run - w0) : RB);
-      // metadata of this buffer's rows: lane l < nrows owns row w0 + l
-      uint32_t key = total_rows;
-      if (lane < nrows) key = __ldg(skeys + w0 + lane);
-      issue(w0 + RB, slot ^ 1);
+      // metadata: lane l < RB owns row w0 + l, lane RB + l row w0 + RB + l (the next buffer)
+      const uint32_t key = nkey;
+      issue(w0 + RB, slot ^ 1, __shfl_sync(0xffffffffu, nsr, (lane < RB) ? lane + RB : 0));
+      load_meta(w0 + RB, nkey, nsr);
       const uint32_t g = (key < total_rows) ? key / p2 : kInvalid;
       const int c2pair = (key < total_rows) ? (int)((key / num_rows32) * p2 + (key - g * p2)) * Q2 : 0;
       const uint32_t gprev = __shfl_up_sync(0xffffffffu, g, 1);
@@ -502,75 +681,84 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
           g_cur = gs;
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) Sacc[nt][0] = Sacc[nt][1] = Sacc[nt][2] = Sacc[nt][3] = 0.f;
-          const float* tp = Ttab + (size_t)gs * (A * 16);
+          if (gs != g_pref) load_T(gs);   // first group of the run: nothing was prefetched
 #pragma unroll
-          for (int ks = 0; ks < KSA; ++ks) {
-            const int j = tid + 8 * ks;
-            ta[ks][0].set(j < A ? __ldg(tp + j * 16 + gid) : 0.f);
-            ta[ks][1].set(j < A ? __ldg(tp + j * 16 + gid + 8) : 0.f);
-            ta[ks][2].set(j + 4 < A ? __ldg(tp + (j + 4) * 16 + gid) : 0.f);
-            ta[ks][3].set(j + 4 < A ? __ldg(tp + (j + 4) * 16 + gid + 8) : 0.f);
-          }
+          for (int ks = 0; ks < KSA; ++ks)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ta[ks][i].set(traw[ks][i]);
         }
-        const int np = (b - a) * Q2;
-        const int P0 = a * Q2;
+        {
+          // the group after this segment: next boundary of this buffer, else the next buffer
+          const int nxt = m ? (__ffs(m) - 1) : RB;
+          const uint32_t gn = __shfl_sync(0xffffffffu, g, nxt);
+          if (gn != kInvalid && gn != g_cur) load_T(gn);
+        }
 #pragma unroll 1
-        for (int pt = 0; pt * 8 < np; ++pt) {
-          // ---- g2[k2, pair] = sum_j tr0[j, k2] dO[pair.row][j, pair.j2]
+        for (int rb = a; rb < b; rb += TR) {
+          const int nrem = b - rb;
+          const float* tb = buf + rb * D;
+          // ---- g2: two n-tiles of 8 pairs, HMMAs of the two interleaved
           {
-            const int pa = pt * 8 + gid;
-            const bool va = pa < np;
-            const int Pa = P0 + (va ? pa : 0);
-            const int rra = Pa / Q2, j2a = Pa - rra * Q2;
-            const float* dp = buf + rra * D + j2a;
-            float g2[4] = {0.f, 0.f, 0.f, 0.f};
+            Frag<TERMS> bf[2][KSA][2];
+            float g2[2][4];
 #pragma unroll
-            for (int ks = 0; ks < KSA; ++ks) {
-              const int j = tid + 8 * ks;
-              Frag<TERMS> bf[2];
-              bf[0].set((va && j < A) ? dp[j * Q2] : 0.f);
-              bf[1].set((va && j + 4 < A) ? dp[(j + 4) * Q2] : 0.f);
-              mma_terms<TERMS>(g2, ta[ks], bf);
+            for (int h = 0; h < 2; ++h) {
+              const bool vn = sN[h].row < nrem;
+              const float* dp = tb + (vn ? sN[h].row * D : 0) + sN[h].j2 + tid * Q2;
+#pragma unroll
+              for (int mm = 0; mm < 2 * KSA; ++mm)
+                bf[h][mm >> 1][mm & 1].set((mm < A4) ? dp[mm * 4 * Q2] : 0.f);
+              g2[h][0] = g2[h][1] = g2[h][2] = g2[h][3] = 0.f;
             }
-            // c0/c1: (k2 = gid, pairs 2 tid, 2 tid + 1), c2/c3: k2 = gid + 8
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int pc = pt * 8 + 2 * tid + e;
-              const bool vc = pc < np;
-              const int Pc = P0 + (vc ? pc : 0);
-              const int rrc = Pc / Q2, j2c = Pc - rrc * Q2;
-              const int cpc = __shfl_sync(0xffffffffu, c2pair, rrc);
-              if (vc) {
-                float* ap = acc2 + (size_t)cpc * 16 + j2c;
-                atomicAdd(ap + gid * Q2, g2[e]);
-                atomicAdd(ap + (gid + 8) * Q2, g2[2 + e]);
+            for (int ks = 0; ks < KSA; ++ks)
+#pragma unroll
+              for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) mma_term<TERMS>(term, g2[h], ta[ks], bf[h][ks]);
+            float* addr[8];
+            float val[8];
+            bool on[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const bool vc = sC[h][e].row < nrem;
+                const int cpc = __shfl_sync(0xffffffffu, c2pair, rb + (vc ? sC[h][e].row : 0));
+                const int i = 4 * h + 2 * e;
+                addr[i] = acc2 + (size_t)cpc * 16 + sC[h][e].j2 + gid * Q2;
+                addr[i + 1] = addr[i] + 8 * Q2;
+                val[i] = g2[h][e];
+                val[i + 1] = g2[h][2 + e];
+                on[i] = on[i + 1] = vc;
               }
-            }
+            shared_add_batch<8>(addr, val, on);
           }
-          // ---- S^T[k2, j] += sum_pairs core2[pair.i2][k2, pair.j2] dO[pair.row][j, pair.j2]
-          {
-            const int pb0 = pt * 8 + tid, pb1 = pb0 + 4;
-            const bool v0 = pb0 < np, v1 = pb1 < np;
-            const int Pa = P0 + (v0 ? pb0 : 0), Pb = P0 + (v1 ? pb1 : 0);
-            const int rr0 = Pa / Q2, j20 = Pa - rr0 * Q2;
-            const int rr1 = Pb / Q2, j21 = Pb - rr1 * Q2;
-            const int cp0 = __shfl_sync(0xffffffffu, c2pair, rr0) + j20;
-            const int cp1 = __shfl_sync(0xffffffffu, c2pair, rr1) + j21;
+          // ---- S^T: two k-steps of 8 pairs
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
             Frag<TERMS> af[4];
-            af[0].set(v0 ? c2s[cp0 * 16 + bwd_slot(cp0, gid)] : 0.f);
-            af[1].set(v0 ? c2s[cp0 * 16 + bwd_slot(cp0, gid + 8)] : 0.f);
-            af[2].set(v1 ? c2s[cp1 * 16 + bwd_slot(cp1, gid)] : 0.f);
-            af[3].set(v1 ? c2s[cp1 * 16 + bwd_slot(cp1, gid + 8)] : 0.f);
-            const float* d0 = buf + rr0 * D + j20;
-            const float* d1 = buf + rr1 * D + j21;
+            const float* db[2];
+#pragma unroll
+            for (int f = 0; f < 2; ++f) {
+              const bool vk = sK[h][f].row < nrem;
+              const int rowk = vk ? sK[h][f].row : 0;
+              const int cpk = __shfl_sync(0xffffffffu, c2pair, rb + rowk) + sK[h][f].j2;
+              af[2 * f].set(vk ? c2s[cpk * 16 + bwd_slot(cpk, gid)] : 0.f);
+              af[2 * f + 1].set(vk ? c2s[cpk * 16 + bwd_slot(cpk, gid + 8)] : 0.f);
+              db[f] = tb + rowk * D + sK[h][f].j2 + gid * Q2;
+            }
+            Frag<TERMS> bf[NTL][2];
 #pragma unroll
             for (int nt = 0; nt < NTL; ++nt) {
-              const int j = gid + 8 * nt;
-              Frag<TERMS> bf[2];
-              bf[0].set((v0 && j < A) ? d0[j * Q2] : 0.f);
-              bf[1].set((v1 && j < A) ? d1[j * Q2] : 0.f);
-              mma_terms<TERMS>(Sacc[nt], af, bf);
+              const bool cv = (8 * nt + 7 < A) || last_nt_ok;
+              bf[nt][0].set(cv ? db[0][nt * 8 * Q2] : 0.f);
+              bf[nt][1].set(cv ? db[1][nt * 8 * Q2] : 0.f);
             }
+#pragma unroll
+            for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+              for (int nt = 0; nt < NTL; ++nt) mma_term<TERMS>(term, Sacc[nt], af, bf[nt]);
           }
         }
       }
@@ -781,10 +969,11 @@ struct Shape {
   static constexpr int A = Q0 * Q1, D = Q0 * Q1 * Q2;
 
   static size_t fwd_smem(int npairs, int terms) {
-    return sizeof(float) * ((size_t)npairs * 16 * (terms == 3 ? 2 : 1) + (size_t)kWarps * kFwdRB * D);
+    return sizeof(float) * ((size_t)npairs * kC2Stride * (terms == 3 ? 2 : 1) +
+                            (size_t)kWarps * fwd_rb(Q2) * D);
   }
   static size_t bwd_smem(int npairs) {
-    return sizeof(float) * ((size_t)npairs * 32 + (size_t)kWarps * 2 * kBwdRB * D) +
+    return sizeof(float) * ((size_t)npairs * 32 + (size_t)kWarps * 2 * bwd_rb(Q2) * D) +
            sizeof(uint64_t) * kWarps * 2;
   }
 
@@ -815,10 +1004,11 @@ struct Shape {
       TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       set_smem = smem;
     }
+    constexpr int RB = fwd_rb(Q2);
     int64_t grid = kNumSMs;
-    if (grid * kWarps * kFwdRB > nnz) grid = ceil_div(nnz, kWarps * kFwdRB);
+    if (grid * kWarps * RB > nnz) grid = ceil_div(nnz, kWarps * RB);
     int64_t rpw = ceil_div(nnz, grid * kWarps);
-    rpw = ceil_div(rpw, kFwdRB) * kFwdRB;
+    rpw = ceil_div(rpw, RB) * RB;
     prof_begin(K_FWD, stream);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, pl.skeys, pl.srow, pl.Ttab,
                                                      output, (int)rpw, npairs);
