@@ -196,6 +196,7 @@ def run_ours(args, shape):
     from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
 
     lib = _ttg.lib()
+    te.EXTRA_FLAGS = int(args.flags)
     p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
     rr = [1] + ranks + [1]
     D = int(np.prod(q))
@@ -413,6 +414,9 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=16384,
                     help="rows per step of the --impl reference (CPU) arm")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--flags", type=int, default=0,
+                    help="TTG_FLAG_* bits OR-ed into every tt_forward / tt_backward call "
+                         "(8 = plain TF32 tensor-core mode, 16 = fp32 FFMA kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

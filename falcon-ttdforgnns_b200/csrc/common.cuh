@@ -127,7 +127,7 @@ struct MmaPlan {
   const int32_t* base;     // [groups + 1] exclusive scan of cnt
   float* Ttab;             // [groups][q0 q1][r2]
   float* S;                // [groups][q0 q1][r2]
-  float* d0parts;          // [4][core0 elements]
+  float* d0parts;          // [p1][core0 elements]: per-i1 partial products of d_core0
 };
 bool mma_supported(const TTDev& tt);
 int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream);

@@ -18,6 +18,10 @@
 // plain TF32 (about 1e-3 relative).  Rows move with the bulk-copy engine: d_output rows arrive
 // in shared memory by cp.async.bulk + mbarrier, finished output rows leave by cp.async.bulk /
 // cp.reduce.async.bulk (.add.f32 for bags with several indices).
+#include <stdlib.h>
+
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace ttg {
@@ -44,6 +48,15 @@ struct Frag {  // one operand register: hi part and (TERMS == 3) lo part
   __device__ __forceinline__ void set(float x) {
     if (TERMS == 3) {
       hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+      lo = __float_as_uint(x - __uint_as_float(hi));
+    } else {
+      hi = __float_as_uint(x) + 0x1000u;
+    }
+  }
+  // per-tile streaming operands: hi by truncation (one instruction less, about 1e-6 relative)
+  __device__ __forceinline__ void set_fast(float x) {
+    if (TERMS == 3) {
+      hi = __float_as_uint(x) & 0xffffe000u;
       lo = __float_as_uint(x - __uint_as_float(hi));
     } else {
       hi = __float_as_uint(x) + 0x1000u;
@@ -191,14 +204,21 @@ __device__ __forceinline__ void shared_add_batch(float* const (&addr)[N], const 
                                                  const bool (&on)[N]) {
   uint32_t old[N], got[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) old[i] = on[i] ? lds_volatile_u32(addr[i]) : 0u;
+  for (int i = 0; i < N; ++i) old[i] = lds_volatile_u32(addr[i]);
+  uint32_t lost = 0;
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    got[i] = on[i] ? cas_shared_u32(addr[i], old[i], __float_as_uint(__uint_as_float(old[i]) + val[i]))
-                   : old[i];
+  for (int i = 0; i < N; ++i) {
+    // lanes that are off write back what they read: a no-op unless somebody got in between,
+    // which then simply fails
+    const uint32_t want = on[i] ? __float_as_uint(__uint_as_float(old[i]) + val[i]) : old[i];
+    got[i] = cas_shared_u32(addr[i], old[i], want);
+    lost |= on[i] ? (got[i] ^ old[i]) : 0u;
+  }
+  if (lost != 0) {   // rare: another warp updated one of the targets between the read and the swap
 #pragma unroll
-  for (int i = 0; i < N; ++i)
-    if (got[i] != old[i]) atomicAdd(addr[i], val[i]);
+    for (int i = 0; i < N; ++i)
+      if (on[i] && got[i] != old[i]) atomicAdd(addr[i], val[i]);
+  }
 }
 
 // position of core2[i2][k2][j2] inside the shared-memory copies ("pair" = i2 * Q2 + j2 selects a
@@ -320,7 +340,7 @@ template <int Q0, int Q1, int Q2, int R2, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
 mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
                const int32_t* __restrict__ srow, const float* __restrict__ Ttab,
-               float* __restrict__ output, int rows_per_warp, int npairs_c2) {
+               float* __restrict__ output, int rows_per_warp, int npairs_c2, int dbg) {
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;
@@ -419,6 +439,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
         const int b = m ? (__ffs(m) - 1) : nrows;
         const uint32_t gs = __shfl_sync(0xffffffffu, g, h * RB + a);
         if (gs == kInvalid) break;  // invalid keys sort to the end
+        if (dbg & 4) continue;
         if (gs != g_held) {
           if (gs != g_pref) load_T(gs);   // first segment of the run: nothing was prefetched
           g_held = gs;
@@ -441,6 +462,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
         }
 #pragma unroll 1
         for (int rb = a; rb < b; rb += TR) {
+          if (dbg & 2) break;
           const int nrem = b - rb;
           const bool v0 = sl0.row < nrem, v1 = sl1.row < nrem;
           const int r0 = rb + (v0 ? sl0.row : 0), r1 = rb + (v1 ? sl1.row : 0);
@@ -496,7 +518,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
         const int src = h * RB + (lane < RB ? lane : 0);
         const uint32_t k_r = __shfl_sync(0xffffffffu, key, src);
         const int32_t sr_r = __shfl_sync(0xffffffffu, sr, src);
-        if (lane < nrows && k_r < total_rows) {
+        if (lane < nrows && k_r < total_rows && !(dbg & 1)) {
           float* dst = output + (int64_t)(sr_r & 0x7fffffff) * D;
           if (sr_r >= 0)
             bulk_store(dst, stage + lane * D, D * 4);
@@ -513,8 +535,13 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
 // ------------------------------------------------------------------------------------------
 // backward rows.  A group belongs to the chunk it starts in (chunks = equal runs of sorted rows,
 // one per warp).  d_output rows arrive RB at a time through a two-slot ring per warp.
-//   g2[k2, pair]   = sum_j  tr0[j, k2] dO[pair.row][j, pair.j2]        -> d_core2 (shared atomics)
+//   g2[k2, pair]   = sum_j  tr0[j, k2] dO[pair.row][j, pair.j2]        -> d_core2 (shared memory)
 //   S^T[k2, j]    += sum_pair core2[pair.i2][k2, pair.j2] dO[pair.row][j, pair.j2]
+// The k index of the second product is permuted so that the four pairs a lane contracts over
+// (k = tid, tid + 4, tid + 8, tid + 12) are the four pairs whose g2 columns it holds
+// (n = 2 tid, 2 tid + 1, 8 + 2 tid, 9 + 2 tid): one shuffle and one shared-memory offset per
+// pair then serve both the core2 operand load and the d_core2 accumulation, because the CTA's
+// d_core2 copy uses the same (pair-major, swizzled) layout as its core2 copy.
 // ------------------------------------------------------------------------------------------
 template <int Q0, int Q1, int Q2, int R2, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -523,7 +550,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ base,
                     const float* __restrict__ d_output, const float* __restrict__ Ttab,
                     float* __restrict__ Sbuf, float* __restrict__ dcore2, int npairs_c2,
-                    int chunk_rows) {
+                    int chunk_rows, int dbg) {
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;       // n-tiles of S^T (columns j0 j1)
@@ -534,7 +561,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   static_assert(R2 == 16 && A % 4 == 0, "backward fragment layout is written for r2 = 16");
   extern __shared__ __align__(128) float smem[];
   float* c2s = smem;                                   // [npairs_c2][16], bwd_slot order
-  float* acc2 = smem + (size_t)npairs_c2 * 16;         // d_core2 of this CTA, global layout
+  float* acc2 = smem + (size_t)npairs_c2 * 16;         // d_core2 of this CTA, same layout
   float* ring_all = acc2 + (size_t)npairs_c2 * 16;     // [warps][2][RB][D]
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring_all + (size_t)kWarps * 2 * RB * D);
 
@@ -545,13 +572,17 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
     const int k2 = rem / Q2, j2 = rem % Q2;
     const int pair = i2row * Q2 + j2;
     c2s[pair * 16 + bwd_slot(pair, k2)] = v;
-    acc2[e] = 0.f;
   });
+  // acc2 starts at zero; so does the ring, so that rows a partial buffer leaves untouched never
+  // hold NaN patterns (they only ever meet zero operands, but 0 * NaN would still poison S)
+  for (int i = threadIdx.x * 4; i < npairs_c2 * 16 + kWarps * 2 * RB * D; i += kThreads * 4)
+    *reinterpret_cast<float4*>(acc2 + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   if (lane == 0) {
     mbar_init(bars + wib * 2, 1);
     mbar_init(bars + wib * 2 + 1, 1);
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  fence_proxy_async();   // the zero-fill above is followed by bulk-copy writes to the ring
   __syncthreads();
 
   float* ring = ring_all + (size_t)wib * 2 * RB * D;
@@ -565,16 +596,12 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   const int64_t nw = (int64_t)gridDim.x * kWarps;
 
   // what this lane's fragment registers stand for, tile after tile
-  PairSlot sN[2], sC[2][2], sK[2][2];
+  const PairSlot sN0 = pair_slot<Q2>(gid), sN1 = pair_slot<Q2>(8 + gid);   // g2: dO operand column
+  PairSlot sC[2][2];                                                        // g2 columns == S k index
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    sN[h] = pair_slot<Q2>(8 * h + gid);                 // g2: column of the dO operand
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      sC[h][e] = pair_slot<Q2>(8 * h + 2 * tid + e);    // g2: accumulator columns
-      sK[h][e] = pair_slot<Q2>(8 * h + tid + 4 * e);    // S: k index of both operands
-    }
-  }
+    for (int e = 0; e < 2; ++e) sC[h][e] = pair_slot<Q2>(8 * h + 2 * tid + e);
   const bool last_nt_ok = gid + 8 * (NTL - 1) < A;      // column j of the last n-tile of S^T exists
 
   for (int64_t chunk = gw; chunk < nchunks; chunk += nw) {
@@ -596,6 +623,10 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
     auto issue = [&](int64_t row0, int slot, int32_t r) {
       const int n = (int)((e_run - row0 < RB) ? (e_run - row0) : RB);
       if (n <= 0) return;
+      if (dbg & 8) {
+        if (lane == 0) mbar_expect_tx(bar + slot, 0u);
+        return;
+      }
       if (lane == 0) mbar_expect_tx(bar + slot, (uint32_t)(n * D * 4));
       __syncwarp();
       if (lane < n)
@@ -650,6 +681,94 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
       }
     };
 
+    int c2pair = 0;            // lane l: (table, i2) * Q2 of row w0 + l of the current buffer
+    const float* buf = ring;
+
+    // ---- one tile of TR rows starting at buffer row rb; FULL: every row of the tile exists
+    auto tile = [&](auto full_tag, int rb, int nrem) {
+      constexpr bool FULL = decltype(full_tag)::value;
+      const float* tb = buf + rb * D;
+      // the four pairs of this lane: shared-memory offset of (pair, k2 = gid), validity
+      bool vC[2][2];
+      int offC[2][2];
+      const float* dC[2][2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          vC[h][e] = FULL ? (sC[h][e].row != 99) : (sC[h][e].row < nrem);
+          const int rsel = vC[h][e] ? sC[h][e].row : 0;
+          const int pair = __shfl_sync(0xffffffffu, c2pair, rb + rsel) + sC[h][e].j2;
+          offC[h][e] = pair * 16 + (gid ^ ((pair & 2) << 2));
+          dC[h][e] = tb + rsel * D + sC[h][e].j2 + gid * Q2;
+        }
+      const bool vN0 = FULL ? (sN0.row != 99) : (sN0.row < nrem);
+      const bool vN1 = FULL ? (sN1.row != 99) : (sN1.row < nrem);
+      const float* dN[2];
+      dN[0] = tb + (vN0 ? sN0.row * D : 0) + sN0.j2 + tid * Q2;
+      dN[1] = tb + (vN1 ? sN1.row * D : 0) + sN1.j2 + tid * Q2;
+
+      // ---- operands
+      Frag<TERMS> bn[2][KSA][2];    // g2: dO[pair][j = tid + 4 mm]
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int mm = 0; mm < 2 * KSA; ++mm)
+          bn[h][mm >> 1][mm & 1].set_fast((mm < A4) ? dN[h][mm * 4 * Q2] : 0.f);
+      Frag<TERMS> af[2][4];         // S: core2[pair][k2 = gid, gid + 8]
+      Frag<TERMS> bs[2][NTL][2];    // S: dO[pair][j = gid + 8 nt]
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          af[h][2 * e].set_fast(vC[h][e] ? c2s[offC[h][e]] : 0.f);
+          af[h][2 * e + 1].set_fast(vC[h][e] ? c2s[offC[h][e] ^ 8] : 0.f);
+#pragma unroll
+          for (int nt = 0; nt < NTL; ++nt) {
+            const bool cv = (8 * nt + 7 < A) || last_nt_ok;
+            bs[h][nt][e].set_fast(cv ? dC[h][e][nt * 8 * Q2] : 0.f);
+          }
+        }
+      // ---- tensor cores: five independent accumulator chains, term-major
+      float g2[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) g2[h][0] = g2[h][1] = g2[h][2] = g2[h][3] = 0.f;
+      if (!(dbg & 2)) {
+#pragma unroll
+        for (int ks = 0; ks < KSA; ++ks)
+#pragma unroll
+          for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) mma_term<TERMS>(term, g2[h], ta[ks], bn[h][ks]);
+      }
+      if (!(dbg & 4)) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+            for (int nt = 0; nt < NTL; ++nt) mma_term<TERMS>(term, Sacc[nt], af[h], bs[h][nt]);
+      }
+      // ---- g2 joins the CTA's d_core2: c0/c1 = (k2 = gid, pairs e = 0, 1), c2/c3 = k2 = gid + 8
+      if (!(dbg & 1)) {
+        float* addr[8];
+        float val[8];
+        bool on[8];
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int i = 4 * h + 2 * e;
+            addr[i] = acc2 + offC[h][e];
+            addr[i + 1] = acc2 + (offC[h][e] ^ 8);
+            val[i] = g2[h][e];
+            val[i + 1] = g2[h][2 + e];
+            on[i] = on[i + 1] = vC[h][e];
+          }
+        shared_add_batch<8>(addr, val, on);
+      }
+    };
+
     int slot = 0;
 #pragma unroll 1
     for (int64_t w0 = s; w0 < e_run; w0 += RB, slot ^= 1) {
@@ -659,7 +778,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
       issue(w0 + RB, slot ^ 1, __shfl_sync(0xffffffffu, nsr, (lane < RB) ? lane + RB : 0));
       load_meta(w0 + RB, nkey, nsr);
       const uint32_t g = (key < total_rows) ? key / p2 : kInvalid;
-      const int c2pair = (key < total_rows) ? (int)((key / num_rows32) * p2 + (key - g * p2)) * Q2 : 0;
+      c2pair = (key < total_rows) ? (int)((key / num_rows32) * p2 + (key - g * p2)) * Q2 : 0;
       const uint32_t gprev = __shfl_up_sync(0xffffffffu, g, 1);
       const bool bnd = (lane < nrows) && (lane == 0 || g != gprev);
       uint32_t m = __ballot_sync(0xffffffffu, bnd);
@@ -670,7 +789,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
         mbar_wait(bar + 1, phase1);
         phase1 ^= 1;
       }
-      const float* buf = ring + (size_t)slot * RB * D;
+      buf = ring + (size_t)slot * RB * D;
       while (m) {
         const int a = __ffs(m) - 1;
         m &= m - 1;
@@ -693,252 +812,230 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
           const uint32_t gn = __shfl_sync(0xffffffffu, g, nxt);
           if (gn != kInvalid && gn != g_cur) load_T(gn);
         }
+        int rb = a;
 #pragma unroll 1
-        for (int rb = a; rb < b; rb += TR) {
-          const int nrem = b - rb;
-          const float* tb = buf + rb * D;
-          // ---- g2: two n-tiles of 8 pairs, HMMAs of the two interleaved
-          {
-            Frag<TERMS> bf[2][KSA][2];
-            float g2[2][4];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const bool vn = sN[h].row < nrem;
-              const float* dp = tb + (vn ? sN[h].row * D : 0) + sN[h].j2 + tid * Q2;
-#pragma unroll
-              for (int mm = 0; mm < 2 * KSA; ++mm)
-                bf[h][mm >> 1][mm & 1].set((mm < A4) ? dp[mm * 4 * Q2] : 0.f);
-              g2[h][0] = g2[h][1] = g2[h][2] = g2[h][3] = 0.f;
-            }
-#pragma unroll
-            for (int ks = 0; ks < KSA; ++ks)
-#pragma unroll
-              for (int term = first_term(TERMS); term < 3; ++term)
-#pragma unroll
-                for (int h = 0; h < 2; ++h) mma_term<TERMS>(term, g2[h], ta[ks], bf[h][ks]);
-            float* addr[8];
-            float val[8];
-            bool on[8];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const bool vc = sC[h][e].row < nrem;
-                const int cpc = __shfl_sync(0xffffffffu, c2pair, rb + (vc ? sC[h][e].row : 0));
-                const int i = 4 * h + 2 * e;
-                addr[i] = acc2 + (size_t)cpc * 16 + sC[h][e].j2 + gid * Q2;
-                addr[i + 1] = addr[i] + 8 * Q2;
-                val[i] = g2[h][e];
-                val[i + 1] = g2[h][2 + e];
-                on[i] = on[i + 1] = vc;
-              }
-            shared_add_batch<8>(addr, val, on);
-          }
-          // ---- S^T: two k-steps of 8 pairs
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            Frag<TERMS> af[4];
-            const float* db[2];
-#pragma unroll
-            for (int f = 0; f < 2; ++f) {
-              const bool vk = sK[h][f].row < nrem;
-              const int rowk = vk ? sK[h][f].row : 0;
-              const int cpk = __shfl_sync(0xffffffffu, c2pair, rb + rowk) + sK[h][f].j2;
-              af[2 * f].set(vk ? c2s[cpk * 16 + bwd_slot(cpk, gid)] : 0.f);
-              af[2 * f + 1].set(vk ? c2s[cpk * 16 + bwd_slot(cpk, gid + 8)] : 0.f);
-              db[f] = tb + rowk * D + sK[h][f].j2 + gid * Q2;
-            }
-            Frag<TERMS> bf[NTL][2];
-#pragma unroll
-            for (int nt = 0; nt < NTL; ++nt) {
-              const bool cv = (8 * nt + 7 < A) || last_nt_ok;
-              bf[nt][0].set(cv ? db[0][nt * 8 * Q2] : 0.f);
-              bf[nt][1].set(cv ? db[1][nt * 8 * Q2] : 0.f);
-            }
-#pragma unroll
-            for (int term = first_term(TERMS); term < 3; ++term)
-#pragma unroll
-              for (int nt = 0; nt < NTL; ++nt) mma_term<TERMS>(term, Sacc[nt], af, bf[nt]);
-          }
-        }
+        for (; rb + TR <= b; rb += TR) tile(std::true_type{}, rb, TR);
+        if (rb < b) tile(std::false_type{}, rb, b - rb);
       }
       __syncwarp();  // every lane is done with this slot before it is refilled
     }
     flush_S();
   }
-  // ---- this CTA's share of d_core2 joins the others in global memory
+  // ---- this CTA's share of d_core2 joins the others in global memory (layout conversion back)
   __syncthreads();
-  for (int i = threadIdx.x * 4; i < npairs_c2 * 16; i += kThreads * 4)
-    red_add_v4(dcore2 + i, *reinterpret_cast<const float4*>(acc2 + i));
+  for (int i = threadIdx.x * 4; i < npairs_c2 * 16; i += kThreads * 4) {
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int e = i + c;
+      const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
+      const int k2 = rem / Q2, j2 = rem % Q2;
+      const int pair = i2row * Q2 + j2;
+      v[c] = acc2[pair * 16 + bwd_slot(pair, k2)];
+    }
+    red_add_v4(dcore2 + i, make_float4(v[0], v[1], v[2], v[3]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// cores: the two dense reductions over S.  Blocks [0, nb1) produce d_core1[i1]; blocks
-// [nb1, nb1 + nb0) produce one K-slice of d_core0 for 16 / Q0 consecutive i0 (summed by the
-// finalize kernel in a fixed order).
+// cores: both dense reductions over S in one pass.  CTA = (table, i1); its warps walk the
+// column S[:, i1] in chunks of 16 rows (i0 j0) = 16 / Q0 values of i0, staged in shared memory
+// by cp.async (groups no row touched are zero-filled, not read).  From one staged chunk:
+//   d_core1[i1][k1, c]   += sum_rows core0[row][k1] * S[row][c]            (kept in registers)
+//   P[i1][row][k1]        = sum_c    S[row][c] * core1[i1][k1, c]          (stored once)
+// d_core0 = sum_i1 P[i1] is taken by the finalize kernel in a fixed order, so neither gradient
+// depends on scheduling.
 // ------------------------------------------------------------------------------------------
-constexpr int kD0Split = 4;
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool on) {
+  const uint32_t sz = on ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem),
+               "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int C>
+constexpr int cores_row_stride() { return C + 8; }   // 88 / 72 floats: k-side reads conflict-free
 
 template <int Q0, int Q1, int R1, int R2, int TERMS>
 __global__ void __launch_bounds__(kCoreThreads)
 mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __restrict__ cnt,
-                     float* __restrict__ d0parts, float* __restrict__ dcore1, int nb1,
-                     size_t e0) {
+                     float* __restrict__ d0parts, float* __restrict__ dcore1, size_t e0) {
   constexpr int A = Q0 * Q1;
   constexpr int C = Q1 * R2;
-  constexpr int NTL = C / 8;
+  constexpr int NTL = C / 8;              // n-tiles of d_core1 / k-steps of P
   constexpr int SG = A * R2;              // floats of S per group
-  static_assert(R1 == 16 && 16 % Q0 == 0 && C % 8 == 0, "tile shapes");
-  extern __shared__ __align__(16) float red[];   // [warps][NTL * 4 * 32] (role 1) / [warps][256]
+  constexpr int IPC = 16 / Q0;            // i0 per chunk
+  constexpr int CS = cores_row_stride<C>();
+  constexpr int CH4 = C / 4;              // 16-byte pieces per row
+  static_assert(R1 == 16 && 16 % Q0 == 0 && C % 8 == 0 && NTL * 128 <= 2 * 16 * CS, "tile shapes");
+  extern __shared__ __align__(16) float smem[];
+  float* b1f = smem;                                       // [NTL][2][32][4]: core1[i1] fragments
+  float* stage_all = smem + NTL * 2 * 32 * 4;              // [warps][2][16][CS]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
   const int p0 = tt.p[0], p1 = tt.p[1];
-  if ((int)blockIdx.x < nb1) {
-    const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
-    const int K = p0 * Q0;
-    const int ksteps = (K + 7) / 8;
-    const float* a_base = tt.core[0] + (size_t)tix * K * R1;
-    float acc[NTL][4];
-#pragma unroll
-    for (int nt = 0; nt < NTL; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-#pragma unroll 2
-    for (int ks = wib; ks < ksteps; ks += kCoreWarps) {
-      const int k0 = 8 * ks + tid, k1 = k0 + 4;
-      Frag<TERMS> af[4];
-      af[0].set(k0 < K ? __ldg(a_base + (size_t)k0 * R1 + gid) : 0.f);
-      af[1].set(k0 < K ? __ldg(a_base + (size_t)k0 * R1 + gid + 8) : 0.f);
-      af[2].set(k1 < K ? __ldg(a_base + (size_t)k1 * R1 + gid) : 0.f);
-      af[3].set(k1 < K ? __ldg(a_base + (size_t)k1 * R1 + gid + 8) : 0.f);
-      const size_t ga = ((size_t)tix * p0 + (k0 < K ? k0 / Q0 : 0)) * p1 + i1;
-      const size_t gb = ((size_t)tix * p0 + (k1 < K ? k1 / Q0 : 0)) * p1 + i1;
-      const bool ona = k0 < K && __ldg(cnt + ga) > 0;
-      const bool onb = k1 < K && __ldg(cnt + gb) > 0;
-      const float* spa = Sbuf + ga * SG + (k0 % Q0) * C + gid;
-      const float* spb = Sbuf + gb * SG + (k1 % Q0) * C + gid;
-      float bv[NTL][2];
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) {
-        bv[nt][0] = ona ? spa[8 * nt] : 0.f;
-        bv[nt][1] = onb ? spb[8 * nt] : 0.f;
-      }
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) {
-        Frag<TERMS> bf[2];
-        bf[0].set(bv[nt][0]);
-        bf[1].set(bv[nt][1]);
-        mma_terms<TERMS>(acc[nt], af, bf);
+  const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
+  const int nchunks = (p0 + IPC - 1) / IPC;
+  float* stage = stage_all + (size_t)wib * 2 * 16 * CS;
+
+  // which groups of my chunks were touched: lane l holds chunk (l / IPC), i0 offset (l % IPC) of
+  // the current batch of MAXC chunks
+  constexpr int MAXC = 32 / IPC;
+  int on_l = 0;
+  auto issue = [&](int it, int buf) {     // it-th chunk of this warp
+    const int ch = wib + kCoreWarps * it;
+    if (it % MAXC == 0) {
+      const int c2 = wib + kCoreWarps * (it + lane / IPC);
+      const int i0m = c2 * IPC + lane % IPC;
+      on_l = 0;
+      if (c2 < nchunks && i0m < p0) on_l = __ldg(cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
+    }
+    if (ch < nchunks) {
+      float* dst = stage + buf * 16 * CS;
+      for (int x = lane; x < 16 * CH4; x += 32) {
+        const int row = x / CH4, c4 = x - row * CH4;
+        const int io = row / Q0, j0 = row - io * Q0;
+        const int i0 = ch * IPC + io;
+        const bool on = __shfl_sync(0xffffffffu, on_l, (it % MAXC) * IPC + io) != 0;
+        const float* src = Sbuf + (((size_t)tix * p0 + (i0 < p0 ? i0 : 0)) * p1 + i1) * SG + j0 * C + 4 * c4;
+        cp_async16_zfill(dst + row * CS + 4 * c4, src, on && i0 < p0);
       }
     }
+    cp_async_commit();
+  };
+  issue(0, 0);
+
+  // core1[i1] as the N-side operand of P: b0 = B1[k1 = gid + 8 nt][c = tid + 8 ks], b1: c + 4
+  {
+    const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
+    for (int x = threadIdx.x; x < NTL * 2 * 32; x += kCoreThreads) {
+      const int ks = x / 64, nt = (x / 32) & 1, l = x & 31;
+      const int k1 = (l >> 2) + 8 * nt, c = (l & 3) + 8 * ks;
+      const float v0 = __ldg(b1p + k1 * C + c), v1 = __ldg(b1p + k1 * C + c + 4);
+      const float h0 = tf32_hi(v0), h1 = tf32_hi(v1);
+      *reinterpret_cast<float4*>(b1f + x * 4) = make_float4(h0, v0 - h0, h1, v1 - h1);
+    }
+  }
+  __syncthreads();
+
+  float acc1[NTL][4];
+#pragma unroll
+  for (int nt = 0; nt < NTL; ++nt) acc1[nt][0] = acc1[nt][1] = acc1[nt][2] = acc1[nt][3] = 0.f;
+  const float* a_base = tt.core[0] + (size_t)tix * p0 * Q0 * R1;
+  const int K = p0 * Q0;
+
+  int it = 0;
+  for (int ch = wib; ch < nchunks; ch += kCoreWarps, ++it) {
+    issue(it + 1, (it + 1) & 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* sb = stage + (it & 1) * 16 * CS;
+    // core0 rows of this chunk as the M-side operand of d_core1: a0 = A0[row = tid + 8 ks][k1 = gid]
+    Frag<TERMS> a0f[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const int r0 = ch * 16 + tid + 8 * ks, r1 = r0 + 4;
+      a0f[ks][0].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + gid) : 0.f);
+      a0f[ks][1].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + gid + 8) : 0.f);
+      a0f[ks][2].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + gid) : 0.f);
+      a0f[ks][3].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + gid + 8) : 0.f);
+    }
+    // ---- P[row][k1] = sum_c S[row][c] B1[k1][c]: M = rows, N = k1 (2 tiles), K = c
+    float accp[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) accp[nt][0] = accp[nt][1] = accp[nt][2] = accp[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < NTL; ++ks) {
+      Frag<TERMS> af[4];
+      af[0].set_fast(sb[gid * CS + tid + 8 * ks]);
+      af[1].set_fast(sb[(gid + 8) * CS + tid + 8 * ks]);
+      af[2].set_fast(sb[gid * CS + tid + 8 * ks + 4]);
+      af[3].set_fast(sb[(gid + 8) * CS + tid + 8 * ks + 4]);
+      Frag<TERMS> bf[2][2];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float4 q = *reinterpret_cast<const float4*>(b1f + ((ks * 2 + nt) * 32 + lane) * 4);
+        bf[nt][0].set_split(q.x, q.y);
+        bf[nt][1].set_split(q.z, q.w);
+      }
+#pragma unroll
+      for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) mma_term<TERMS>(term, accp[nt], af, bf[nt]);
+    }
+    {
+      // c0/c1: (row gid, k1 = 2 tid, 2 tid + 1 (+ 8 nt)), c2/c3: row gid + 8
+      float* dp = d0parts + (size_t)i1 * e0 + (size_t)tix * K * R1;
+      const int r0 = ch * 16 + gid, r1 = r0 + 8;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        if (r0 < K)
+          *reinterpret_cast<float2*>(dp + (size_t)r0 * R1 + 8 * nt + 2 * tid) = make_float2(accp[nt][0], accp[nt][1]);
+        if (r1 < K)
+          *reinterpret_cast<float2*>(dp + (size_t)r1 * R1 + 8 * nt + 2 * tid) = make_float2(accp[nt][2], accp[nt][3]);
+      }
+    }
+    // ---- d_core1[k1][c] += sum_rows A0[row][k1] S[row][c]: M = k1, N = c, K = rows (2 steps)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      Frag<TERMS> bf[NTL][2];
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        bf[nt][0].set_fast(sb[(tid + 8 * ks) * CS + gid + 8 * nt]);
+        bf[nt][1].set_fast(sb[(tid + 8 * ks + 4) * CS + gid + 8 * nt]);
+      }
+#pragma unroll
+      for (int term = first_term(TERMS); term < 3; ++term)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) mma_term<TERMS>(term, acc1[nt], a0f[ks], bf[nt]);
+    }
+    __syncwarp();   // the buffer is refilled two iterations from now by this warp's own copies
+  }
+  cp_async_wait<0>();
+  // ---- sum the warps' d_core1 accumulators (fixed order) and store
+  __syncthreads();
+  float* red = stage_all;                 // [warps][NTL * 128]
+  {
     float* mine = red + (size_t)wib * (NTL * 128);
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) mine[(nt * 4 + e) * 32 + lane] = acc[nt][e];
-    __syncthreads();
-    float* dst = dcore1 + (size_t)blockIdx.x * (R1 * C);
-    for (int x = threadIdx.x; x < NTL * 128; x += kCoreThreads) {
-      float v = 0.f;
+      for (int e = 0; e < 4; ++e) mine[(nt * 4 + e) * 32 + lane] = acc1[nt][e];
+  }
+  __syncthreads();
+  float* dst = dcore1 + (size_t)blockIdx.x * (R1 * C);
+  for (int x = threadIdx.x; x < NTL * 128; x += kCoreThreads) {
+    float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < kCoreWarps; ++w) v += red[(size_t)w * (NTL * 128) + x];
-      const int l = x & 31, e = (x >> 5) & 3, nt = x >> 7;
-      const int row = (l >> 2) + 8 * (e >> 1), col = 8 * nt + 2 * (l & 3) + (e & 1);
-      dst[row * C + col] = v;
-    }
-  } else {
-    constexpr int IPB = 16 / Q0;           // i0 per block
-    const int nquads = (p0 + IPB - 1) / IPB;
-    const int b = blockIdx.x - nb1;
-    const int sl = b % kD0Split;
-    const int qd = (b / kD0Split) % nquads;
-    const int tix = b / (kD0Split * nquads);
-    const int per = (p1 + kD0Split - 1) / kD0Split;
-    const int i1_lo = sl * per, i1_hi = (i1_lo + per < p1) ? i1_lo + per : p1;
-    const int i0a = qd * IPB + gid / Q0, i0b = i0a + 8 / Q0;   // rows gid and gid + 8
-    const int j0 = gid % Q0;
-    float acc[2][4];
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-    for (int i1 = i1_lo + wib; i1 < i1_hi; i1 += kCoreWarps) {
-      const size_t ga = ((size_t)tix * p0 + (i0a < p0 ? i0a : 0)) * p1 + i1;
-      const size_t gb = ((size_t)tix * p0 + (i0b < p0 ? i0b : 0)) * p1 + i1;
-      const bool ona = i0a < p0 && __ldg(cnt + ga) > 0;
-      const bool onb = i0b < p0 && __ldg(cnt + gb) > 0;
-      const float* spa = Sbuf + ga * SG + j0 * C + tid;
-      const float* spb = Sbuf + gb * SG + j0 * C + tid;
-      const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C) + tid;
-#pragma unroll 5
-      for (int ks = 0; ks < NTL; ++ks) {
-        Frag<TERMS> af[4];
-        af[0].set(ona ? spa[8 * ks] : 0.f);
-        af[1].set(onb ? spb[8 * ks] : 0.f);
-        af[2].set(ona ? spa[8 * ks + 4] : 0.f);
-        af[3].set(onb ? spb[8 * ks + 4] : 0.f);
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          Frag<TERMS> bf[2];
-          bf[0].set(__ldg(b1p + (gid + 8 * nt) * C + 8 * ks));
-          bf[1].set(__ldg(b1p + (gid + 8 * nt) * C + 8 * ks + 4));
-          mma_terms<TERMS>(acc[nt], af, bf);
-        }
-      }
-    }
-    float* mine = red + (size_t)wib * 256;
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) mine[(nt * 4 + e) * 32 + lane] = acc[nt][e];
-    __syncthreads();
-    {
-      const int x = threadIdx.x;  // 256 outputs
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCoreWarps; ++w) v += red[(size_t)w * 256 + x];
-      const int l = x & 31, e = (x >> 5) & 3, nt = x >> 7;
-      const int row = (l >> 2) + 8 * (e >> 1), k1 = 8 * nt + 2 * (l & 3) + (e & 1);
-      const int i0 = qd * IPB + row / Q0;
-      if (i0 < p0)
-        d0parts[(size_t)sl * e0 + ((size_t)tix * p0 + i0) * (Q0 * R1) + (row % Q0) * R1 + k1] = v;
-    }
+    for (int w = 0; w < kCoreWarps; ++w) v += red[(size_t)w * (NTL * 128) + x];
+    const int l = x & 31, e = (x >> 5) & 3, nt = x >> 7;
+    const int row = (l >> 2) + 8 * (e >> 1), col = 8 * nt + 2 * (l & 3) + (e & 1);
+    dst[row * C + col] = v;
   }
 }
 
-// finalize: d_core0 = sum of its K-slices (fixed order); then the optional optimizer step on all
-// three cores.  SGD: core -= lr g;  Adagrad: state += g g, core -= lr g / (sqrt(state) + eps)
-// (FBTT/tt_embeddings_cuda.cu:381-419, applied to every row -- SURVEY 8a-6)
+// finalize: d_core0 = sum over i1 of the partial products (fixed order), then the optional
+// optimizer step on all three cores.  SGD: core -= lr g;  Adagrad: state += g g,
+// core -= lr g / (sqrt(state) + eps)  (FBTT/tt_embeddings_cuda.cu:381-419, applied to every row
+// -- SURVEY 8a-6)
 struct MmaFinalArgs {
   int64_t e0, e1, e2;
+  int nparts;                // p1 partial copies of d_core0
   const float* d0parts;
   float* dcore[3];
   float* core[3];
   float* state[3];
   int32_t optim;
   float lr, eps;
+  int nb0;                   // blocks that reduce d_core0 (32 float4 columns each)
 };
 
-__global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
-  const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
-  if (i >= a.e0 + a.e1 + a.e2) return;
-  int t;
-  int64_t o;
-  float4 g;
-  if (i < a.e0) {
-    t = 0;
-    o = i;
-    g = ldg4(a.d0parts + o);
-#pragma unroll
-    for (int s = 1; s < kD0Split; ++s) {
-      const float4 v = ldg4(a.d0parts + (size_t)s * a.e0 + o);
-      g.x += v.x;
-      g.y += v.y;
-      g.z += v.z;
-      g.w += v.w;
-    }
-    *reinterpret_cast<float4*>(a.dcore[0] + o) = g;
-  } else {
-    t = (i < a.e0 + a.e1) ? 1 : 2;
-    o = (t == 1) ? i - a.e0 : i - a.e0 - a.e1;
-    g = *reinterpret_cast<const float4*>(a.dcore[t] + o);
-  }
+__device__ __forceinline__ void final_update4(const MmaFinalArgs& a, int t, int64_t o, float4 g) {
   if (a.optim == TTG_OPTIM_DENSE) return;
   float4 c = *reinterpret_cast<float4*>(a.core[t] + o);
   if (a.optim == TTG_OPTIM_SGD) {
@@ -961,9 +1058,68 @@ __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
   *reinterpret_cast<float4*>(a.core[t] + o) = c;
 }
 
+__global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
+  __shared__ float4 sm[8][32];
+  if ((int)blockIdx.x < a.nb0) {
+    // 32 float4 columns x 8 slices of the i1 axis; each slice is summed in order, then the slices
+    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int64_t o = ((int64_t)blockIdx.x * 32 + col) * 4;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o < a.e0) {
+      const int per = (a.nparts + 7) / 8;
+      const int lo = sl * per, hi = (lo + per < a.nparts) ? lo + per : a.nparts;
+      int p = lo;
+      for (; p + 4 <= hi; p += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg4(a.d0parts + (size_t)(p + u) * a.e0 + o);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          g.x += v[u].x;
+          g.y += v[u].y;
+          g.z += v[u].z;
+          g.w += v[u].w;
+        }
+      }
+      for (; p < hi; ++p) {
+        const float4 v = ldg4(a.d0parts + (size_t)p * a.e0 + o);
+        g.x += v.x;
+        g.y += v.y;
+        g.z += v.z;
+        g.w += v.w;
+      }
+    }
+    sm[sl][col] = g;
+    __syncthreads();
+    if (sl == 0 && o < a.e0) {
+#pragma unroll
+      for (int q = 1; q < 8; ++q) {
+        g.x += sm[q][col].x;
+        g.y += sm[q][col].y;
+        g.z += sm[q][col].z;
+        g.w += sm[q][col].w;
+      }
+      *reinterpret_cast<float4*>(a.dcore[0] + o) = g;
+      final_update4(a, 0, o, g);
+    }
+  } else {
+    const int64_t i = ((int64_t)(blockIdx.x - a.nb0) * 256 + threadIdx.x) * 4;
+    if (i >= a.e1 + a.e2) return;
+    const int t = (i < a.e1) ? 1 : 2;
+    const int64_t o = (t == 1) ? i : i - a.e1;
+    final_update4(a, t, o, *reinterpret_cast<const float4*>(a.dcore[t] + o));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+// profiling knob (ablation of kernel phases); 0 in production
+inline int dbg_knob(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+
 template <int Q0, int Q1, int Q2, int R1, int R2>
 struct Shape {
   static constexpr int A = Q0 * Q1, D = Q0 * Q1 * Q2;
@@ -1011,7 +1167,7 @@ struct Shape {
     rpw = ceil_div(rpw, RB) * RB;
     prof_begin(K_FWD, stream);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, pl.skeys, pl.srow, pl.Ttab,
-                                                     output, (int)rpw, npairs);
+                                                     output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"));
     prof_end(K_FWD, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
@@ -1042,15 +1198,16 @@ struct Shape {
       prof_begin(K_BWD_ROWS, stream);
       kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, groups, pl.skeys, pl.srow,
                                                        pl.cnt, pl.base, d_output, pl.Ttab, pl.S,
-                                                       dcore[2], npairs, (int)chunk);
+                                                       dcore[2], npairs, (int)chunk,
+                                                       dbg_knob("TTG_DBG_BWD"));
       prof_end(K_BWD_ROWS, stream);
       TTG_LAUNCH_CHECK();
     }
     {
       constexpr int C = Q1 * R2;
       const int nb1 = tt.num_tables * tt.p[1];
-      const int nb0 = tt.num_tables * (int)ceil_div(tt.p[0], 16 / Q0) * kD0Split;
-      const size_t smem = sizeof(float) * kCoreWarps * (C / 8) * 128;
+      const size_t smem = sizeof(float) * ((C / 8) * 2 * 32 * 4 +
+                                           (size_t)kCoreWarps * 2 * 16 * cores_row_stride<C>());
       auto kern = mma_bwd_cores_kernel<Q0, Q1, R1, R2, TERMS>;
       static bool attr = false;
       if (!attr) {
@@ -1058,8 +1215,7 @@ struct Shape {
         attr = true;
       }
       prof_begin(K_BWD_CORES, stream);
-      kern<<<nb1 + nb0, kCoreThreads, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore[1], nb1,
-                                                      (size_t)e0);
+      kern<<<nb1, kCoreThreads, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore[1], (size_t)e0);
       prof_end(K_BWD_CORES, stream);
       TTG_LAUNCH_CHECK();
     }
@@ -1068,6 +1224,7 @@ struct Shape {
     a.e0 = e0;
     a.e1 = e1;
     a.e2 = e2;
+    a.nparts = tt.p[1];
     a.d0parts = pl.d0parts;
     for (int t = 0; t < 3; ++t) {
       a.dcore[t] = dcore[t];
@@ -1077,10 +1234,11 @@ struct Shape {
     a.optim = optim;
     a.lr = lr;
     a.eps = eps;
+    a.nb0 = (int)ceil_div(e0, 128);
     // dense mode only needs the d_core0 part
-    const int64_t elems = (optim == TTG_OPTIM_DENSE) ? e0 : e0 + e1 + e2;
+    const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(e1 + e2, 1024);
     prof_begin(K_REDUCE, stream);
-    mma_finalize_kernel<<<(unsigned)ceil_div(elems, 1024), 256, 0, stream>>>(a);
+    mma_finalize_kernel<<<a.nb0 + nb12, 256, 0, stream>>>(a);
     prof_end(K_REDUCE, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;

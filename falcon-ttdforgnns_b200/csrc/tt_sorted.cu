@@ -83,7 +83,7 @@ struct SortedWs {
   float* Ttab;         // [tables * p0 * p1][q0 q1 r2]  tr0 of every group (dense strategy)
   float* partials;     // [kBwdGrid][tables * p2 * cols2] or nullptr (FFMA kernels)
   float* cparts;       // [kCoreSplit][core0 + core1 elements]    (FFMA kernels)
-  float* d0parts;      // [4][core0 elements]                     (tensor-core kernels)
+  float* d0parts;      // [p1][core0 elements]                    (tensor-core kernels)
   int32_t* cnt;        // [cnt_elems] rows per group (+1: invalid keys), padded to scan tiles
   int32_t* rowcount;   // [tables * B] valid indices per output row; directly behind cnt
   size_t cnt_bytes;    // cnt alone (backward-only plan)
@@ -120,7 +120,7 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
                ? (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]))
                : nullptr;
   w.cparts = (float*)take(sizeof(float) * kCoreSplit * (e0 + e1));
-  w.d0parts = (float*)take(sizeof(float) * 4 * e0);
+  w.d0parts = (float*)take(sizeof(float) * (size_t)tt.p[1] * e0);
   // counters (padded to whole 4096-counter scan tiles) and the per-row counts share one memset
   const size_t cnt_elems = align_up(groups + 1, 4096);
   w.cnt_bytes = sizeof(int32_t) * cnt_elems;
