@@ -343,15 +343,22 @@ def run_ours(args, shape):
     hbm_peak, peak_src, sm_max = measured_peaks()
     bytes_fwd = nnz * (8 + 4 * D)
     bytes_bwd = nnz * (8 + 4 * D)
-    alg = {"sorted_fwd_kernel": bytes_fwd, "sorted_bwd_rows_kernel": bytes_bwd,
+    alg = {"fwd_rows_kernel": bytes_fwd, "bwd_rows_kernel": bytes_bwd,
            "generic_fwd_kernel": bytes_fwd, "generic_bwd_kernel": bytes_bwd}
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms"], default=None)
+    # DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this round
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if dom and os.path.exists(tpath) and args.shape == "products" and nnz == 262144:
+        t = json.load(open(tpath)).get(dom)
+        if t:
+            traffic, traffic_src = t["dram_bytes_per_launch"], t["source"]
     roofline = None
     if dom:
         achieved = alg[dom] / (kern[dom]["ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak,
-                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
-                    "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic,
+                    "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": kern[dom]["ms"]}
     step_bytes = nnz * (16 + 8 * D) + 2 * core_bytes
     q0, q1, q2 = q
@@ -359,15 +366,20 @@ def run_ours(args, shape):
     f_row = 2 * (q0 * q1) * r2 * q2 * 3            # per row: row product, d_core2 slice, d(tr0)
     f_grp = 2 * q0 * r1 * (q1 * r2) * 4            # per group: tr0 fwd, tr0 bwd, d_core1, d_core0
     step_flops = f_row * nnz + f_grp * groups
-    fp32_peak = 148 * 128 * 2 * sm_max * 1e6
+    # pipe ceilings measured on this pool's B200 (profiles/r1_pipe_peaks.txt): fp32 FFMA with
+    # three register operands 47 TFLOP/s, mma.sync TF32 m16n8k8 278 TFLOP/s
+    ffma_peak, tf32_peak = 47.0e12, 278.0e12
+    passes = 1 if (args.flags & 8) else 3          # 3xTF32 issues three tensor-core passes
+    uses_tensor = not (args.flags & 16)
     t_hbm = step_bytes / (hbm_peak * 1e9)
-    t_fp32 = step_flops / fp32_peak
-    bound_s = max(t_hbm, t_fp32)
+    t_pipe = step_flops * passes / tf32_peak if uses_tensor else step_flops / ffma_peak
+    bound_s = max(t_hbm, t_pipe)
     step_roofline = {
         "bytes_per_step": step_bytes, "flops_per_step_with_prefix_reuse": step_flops,
-        "unique_groups": groups, "t_hbm_us": t_hbm * 1e6, "t_fp32_ffma_us": t_fp32 * 1e6,
-        "fp32_peak_tflops_nominal": fp32_peak / 1e12,
-        "bound": "fp32" if t_fp32 > t_hbm else "hbm",
+        "unique_groups": groups, "t_hbm_us": t_hbm * 1e6, "t_pipe_us": t_pipe * 1e6,
+        "pipe": ("mma.sync tf32 x%d passes @ 278 TFLOP/s measured" % passes) if uses_tensor
+                else "fp32 ffma @ 47 TFLOP/s measured",
+        "bound": "pipe" if t_pipe > t_hbm else "hbm",
         "frac_of_bound": bound_s / (ms_step * 1e-3),
         "flops_per_step_no_reuse": nnz * (2 * q0 * r1 * q1 * r2 * 4 + 2 * q0 * q1 * r2 * q2 * 3),
     }
@@ -381,6 +393,9 @@ def run_ours(args, shape):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "rows_per_step_per_gpu": nnz,
+                   "arithmetic": ("plain TF32 tensor-core passes (TTG_FLAG_TF32)" if (args.flags & 8)
+                                  else "fp32 FFMA kernels (TTG_FLAG_FFMA)" if (args.flags & 16)
+                                  else "fp32 via 3xTF32 split on tensor cores, fp32 accumulation"),
                    "l2": "4 rotating batches, 212 MB touched per step (> 126 MB L2)",
                    "launch": "cuda_graph" if use_graph else "eager",
                    "parallelism": "dp%d, replicated cores%s" % (

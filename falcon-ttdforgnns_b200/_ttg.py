@@ -112,7 +112,13 @@ def ptr_array(tensors):
 
 
 def stream_of(device):
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    """torch's current stream on `device` as a raw cudaStream_t (the private getter skips the
+    Stream object construction, which costs more than a kernel launch)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(idx))
+    except AttributeError:  # older / newer torch without the private getter
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def require_cuda(t, name, dtype=None):

@@ -31,10 +31,12 @@ bool g_prof_on = false;
 ProfRec g_rec[K_COUNT][kMaxRec];
 int g_nrec[K_COUNT];
 int g_nalloc[K_COUNT];
-const char* kKernelNames[K_COUNT] = {"plan_kernel",       "radix_sort",        "zero_rows_kernel",
-                                     "sorted_fwd_kernel", "sorted_bwd_rows_kernel",
-                                     "sorted_bwd_cores_kernel", "reduce_partials_kernel",
-                                     "optimizer_kernel",  "generic_fwd_kernel", "generic_bwd_kernel",
+// one name per timed phase (the kernels behind a phase depend on the path: tensor-core, FFMA
+// or shape-generic)
+const char* kKernelNames[K_COUNT] = {"plan_kernel",        "bucket_scan_scatter", "zero_rows_kernel",
+                                     "fwd_rows_kernel",    "bwd_rows_kernel",
+                                     "bwd_cores_kernel",   "finalize_kernel",
+                                     "optimizer_kernel",   "generic_fwd_kernel", "generic_bwd_kernel",
                                      "group_table_kernel"};
 }  // namespace
 

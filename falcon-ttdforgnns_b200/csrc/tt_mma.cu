@@ -1032,7 +1032,7 @@ struct MmaFinalArgs {
   float* state[3];
   int32_t optim;
   float lr, eps;
-  int nb0;                   // blocks that reduce d_core0 (32 float4 columns each)
+  int nb0;                   // blocks that reduce d_core0 (kFinCols float4 columns each)
 };
 
 __device__ __forceinline__ void final_update4(const MmaFinalArgs& a, int t, int64_t o, float4 g) {
@@ -1058,42 +1058,40 @@ __device__ __forceinline__ void final_update4(const MmaFinalArgs& a, int t, int6
   *reinterpret_cast<float4*>(a.core[t] + o) = c;
 }
 
+constexpr int kFinSlices = 16;   // slices of the i1 axis per block
+constexpr int kFinCols = 256 / kFinSlices;
+constexpr int kFinPer = 12;      // partial copies one thread sums (all loads in flight at once)
+
 __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
-  __shared__ float4 sm[8][32];
+  __shared__ float4 sm[kFinSlices][kFinCols];
   if ((int)blockIdx.x < a.nb0) {
-    // 32 float4 columns x 8 slices of the i1 axis; each slice is summed in order, then the slices
-    const int col = threadIdx.x & 31, sl = threadIdx.x >> 5;
-    const int64_t o = ((int64_t)blockIdx.x * 32 + col) * 4;
+    // 16 float4 columns x 16 slices of the i1 axis; a slice is summed in order, then the slices
+    const int col = threadIdx.x % kFinCols, sl = threadIdx.x / kFinCols;
+    const int64_t o = ((int64_t)blockIdx.x * kFinCols + col) * 4;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (o < a.e0) {
-      const int per = (a.nparts + 7) / 8;
+      const int per = (a.nparts + kFinSlices - 1) / kFinSlices;
       const int lo = sl * per, hi = (lo + per < a.nparts) ? lo + per : a.nparts;
-      int p = lo;
-      for (; p + 4 <= hi; p += 4) {
-        float4 v[4];
+      for (int p = lo; p < hi; p += kFinPer) {
+        float4 v[kFinPer];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = ldg4(a.d0parts + (size_t)(p + u) * a.e0 + o);
+        for (int u = 0; u < kFinPer; ++u)
+          v[u] = (p + u < hi) ? ldg4(a.d0parts + (size_t)(p + u) * a.e0 + o)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kFinPer; ++u) {
           g.x += v[u].x;
           g.y += v[u].y;
           g.z += v[u].z;
           g.w += v[u].w;
         }
       }
-      for (; p < hi; ++p) {
-        const float4 v = ldg4(a.d0parts + (size_t)p * a.e0 + o);
-        g.x += v.x;
-        g.y += v.y;
-        g.z += v.z;
-        g.w += v.w;
-      }
     }
     sm[sl][col] = g;
     __syncthreads();
     if (sl == 0 && o < a.e0) {
 #pragma unroll
-      for (int q = 1; q < 8; ++q) {
+      for (int q = 1; q < kFinSlices; ++q) {
         g.x += sm[q][col].x;
         g.y += sm[q][col].y;
         g.z += sm[q][col].z;
@@ -1234,7 +1232,7 @@ struct Shape {
     a.optim = optim;
     a.lr = lr;
     a.eps = eps;
-    a.nb0 = (int)ceil_div(e0, 128);
+    a.nb0 = (int)ceil_div(e0, 4 * kFinCols);
     // dense mode only needs the d_core0 part
     const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(e1 + e2, 1024);
     prof_begin(K_REDUCE, stream);
