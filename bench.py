@@ -189,6 +189,8 @@ def run_ours(args, shape):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # the version banner goes to stdout; ours is one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import _ttg
     import dp
@@ -312,6 +314,8 @@ def run_ours(args, shape):
     target = [d.view(nnz, D) for d in d_out]
     losses = []
 
+    module.sparse = (world == 1)   # N > 1: dense gradients, all-reduce, then the update
+
     def e2e_step(i):
         k = i % NUM_ROT
         idx_stage.copy_(idx_host[k], non_blocking=True)
@@ -321,7 +325,6 @@ def run_ours(args, shape):
             loss = (out * target[k]).sum()
             loss.backward()
         else:  # data parallel: explicit exchange step instead of the fused update
-            module.sparse = False
             loss = (out * target[k]).sum()
             loss.backward()
             dp.dp_backward_step(module, [c.grad for c in module.tt_cores])

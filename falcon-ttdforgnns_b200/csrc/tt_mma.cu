@@ -1112,7 +1112,10 @@ __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// profiling knob (ablation of kernel phases); 0 in production
+// profiling knobs TTG_DBG_FWD / TTG_DBG_BWD: switch phases of the row kernels off to see what
+// each costs (profiles/tools/ablate.sh); results are then wrong by construction.  Unset (0) in
+// production.  fwd: 1 no stores, 2 no tiles, 4 no segments; bwd: 1 no d_core2 adds, 2 no g2
+// products, 4 no S products, 8 no d_output copies.
 inline int dbg_knob(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
