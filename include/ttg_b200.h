@@ -224,6 +224,28 @@ int ttg_spmm_csr_bwd(int64_t num_dst, int32_t F, const int64_t* indptr,
                      const int32_t* indices, const float* edge_weight, int32_t mean,
                      const float* dout, float* dx, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (f-1) neighbour sampling + block construction on the device, one GNN layer per call.
+ * replaces: dgl.dataloading.NeighborSampler (uniform, without replacement) + to_block as the
+ *           reference drives them, graphloader.py:245-261, sage_dgl_partition.py:141-154
+ *           (DGL 2.1 is un-vendored: semantics restated, see csrc/sampler.cu).
+ * Graph: CSR of in-neighbours, g_indptr int64 [num_nodes + 1], g_indices int32.
+ * For every destination node (unique global ids, dst_nodes int64 [num_dst]) all its
+ * in-neighbours are taken when there are at most `fanout`, else `fanout` distinct ones, the
+ * draw being a pure function of (seed, node id).  Outputs (device):
+ *   blk_indptr  int64 [num_dst + 1]              CSR by destination
+ *   blk_indices int32 [capacity num_dst*fanout]  source ids local to the block
+ *   src_nodes   int64 [capacity num_dst*(fanout+1)] global ids: the destination nodes first,
+ *                                                then the new nodes in increasing id
+ *   counts      int64 [2]                        {number of edges, number of source nodes}
+ * No synchronisation: the caller reads `counts` when it needs the sizes on the host.
+ * ---------------------------------------------------------------------------------- */
+size_t ttg_sample_block_workspace_bytes(int64_t num_dst, int32_t fanout);
+int ttg_sample_block(int64_t num_nodes, const int64_t* g_indptr, const int32_t* g_indices,
+                     int64_t num_dst, const int64_t* dst_nodes, int32_t fanout, uint64_t seed,
+                     int64_t* blk_indptr, int32_t* blk_indices, int64_t* src_nodes,
+                     int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
