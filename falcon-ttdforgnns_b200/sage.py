@@ -1,0 +1,103 @@
+"""GraphSAGE over TT-compressed node embeddings: the model of the reference's
+sage_dgl_partition.py (class SAGE, gnn_model.py:44-217) on this package's operators --
+TTEmbeddingBag for the input features, gnn_ops.SAGEConv for the layers, sampler.NeighborSampler
+for the minibatches -- plus the synthetic ogbn-products-shaped graph the benchmarks run on
+(there is no network for datasets; shapes from SURVEY 8d "G").
+"""
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+import dp
+from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
+from gnn_ops import Block, SAGEConv
+from sampler import CSRGraph
+
+
+class SAGE(nn.Module):
+    """n_layers SAGEConv('mean') layers (in -> hidden -> ... -> classes, gnn_model.py:76-81) on
+    top of a TTEmbeddingBag (gnn_model.py:113-125); forward as gnn_model.py:196-217."""
+
+    def __init__(self, num_nodes: int, in_feats: int, n_hidden: int, n_classes: int,
+                 n_layers: int = 3, dropout: float = 0.5, tt_rank: Sequence[int] = (16, 16),
+                 p_shapes: Optional[Sequence[int]] = None, q_shapes: Optional[Sequence[int]] = None,
+                 sparse: bool = True, learning_rate: float = 0.01):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        self.layers.append(SAGEConv(in_feats, n_hidden, "mean"))
+        for _ in range(1, n_layers - 1):
+            self.layers.append(SAGEConv(n_hidden, n_hidden, "mean"))
+        self.layers.append(SAGEConv(n_hidden, n_classes, "mean"))
+        self.dropout = nn.Dropout(dropout)
+        self.embed_layer = TTEmbeddingBag(
+            num_embeddings=num_nodes, embedding_dim=in_feats, tt_ranks=list(tt_rank),
+            tt_p_shapes=list(p_shapes) if p_shapes else None,
+            tt_q_shapes=list(q_shapes) if q_shapes else None, sparse=sparse,
+            optimizer=OptimType.SGD, learning_rate=learning_rate, use_cache=False,
+            weight_dist="normal")
+
+    def dense_parameters(self) -> List[nn.Parameter]:
+        return [p for layer in self.layers for p in layer.parameters()]
+
+    def forward(self, blocks: Sequence[Block], input_nodes: torch.Tensor) -> torch.Tensor:
+        offsets = torch.arange(input_nodes.numel() + 1, device=input_nodes.device)
+        h = self.embed_layer(input_nodes, offsets)
+        for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+            h = layer(block, (h, h[:block.num_dst]))
+            if l != len(self.layers) - 1:
+                h = self.dropout(F.relu(h))
+        return h
+
+
+def synthetic_graph(num_nodes: int, num_edges: int, device, seed: int = 0, alpha: float = 2.1
+                    ) -> CSRGraph:
+    """Power-law in-degrees (Pareto tail `alpha`, rescaled to `num_edges` in total, at least one
+    in-edge per node), uniformly random in-neighbours; int64 indptr, int32 indices."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand(num_nodes, generator=g, device=device, dtype=torch.float64)
+    w = (1.0 - u).clamp_min(1e-12).pow(-1.0 / alpha)
+    w = w.clamp_max(float(num_nodes) ** 0.5 * 10.0)
+    deg = torch.floor(w * (num_edges - num_nodes) / w.sum()).to(torch.int64) + 1
+    short = int(num_edges - int(deg.sum()))
+    if short > 0:   # hand the rounding remainder to the first nodes
+        deg[:short] += 1
+    indptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(deg, 0, out=indptr[1:])
+    indices = torch.randint(0, num_nodes, (int(indptr[-1]),), generator=g, device=device,
+                            dtype=torch.int32)
+    return CSRGraph(indptr, indices)
+
+
+class Trainer:
+    """One optimisation step of the reference's training loop (sage_dgl_partition.py:205-262):
+    Adam on the SAGE layers, the TT cores by their fused SGD (single GPU, --sparse) or -- data
+    parallel -- by one all-reduce of every gradient followed by the same update on all ranks."""
+
+    def __init__(self, model: SAGE, lr: float = 0.003, world: int = 1):
+        self.model, self.world = model, world
+        self.opt = torch.optim.Adam(model.dense_parameters(), lr=lr)
+        if world > 1:
+            model.embed_layer.sparse = False
+
+    def step(self, blocks, input_nodes, labels) -> torch.Tensor:
+        m = self.model
+        logits = m(blocks, input_nodes)
+        loss = F.cross_entropy(logits, labels)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if self.world > 1:
+            emb = m.embed_layer
+            dense = [p.grad for p in m.dense_parameters()]
+            cores = [c.grad for c in emb.tt_cores]
+            reduced = dp.allreduce_mean(dense + cores)
+            for p, gr in zip(m.dense_parameters(), reduced[:len(dense)]):
+                p.grad = gr.contiguous()
+            dp.apply_optimizer(emb.tt_p_shapes, emb.tt_q_shapes, emb.tt_ranks, list(emb.tt_cores),
+                               [gr.contiguous() for gr in reduced[len(dense):]], emb.learning_rate)
+            for c in emb.tt_cores:
+                c.grad = None
+        self.opt.step()
+        return loss
