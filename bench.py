@@ -167,8 +167,51 @@ def run_reference(args, shape):
                          "sample": "%d rows per step" % rows},
         "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_gpu": reference_gpu_rate(args, shape),
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_gpu_rate(args, shape, steps=5):
+    """The reference's own CUDA kernels (oracle/_ref, built unmodified for sm_100a) on the full
+    workload, device-resident inputs, CUDA events: reported beside the CPU number of the reference
+    arm.  None when there is no GPU or the extension was not built."""
+    try:
+        from oracle import ref_ext
+        rmod = ref_ext.load()
+        if rmod is None or not torch.cuda.is_available():
+            return None
+        dev = torch.device("cuda", 0)
+        p, q, rr, N = shape["p"], shape["q"], [1] + shape["ranks"] + [1], shape["n"]
+        D, nnz = int(np.prod(q)), args.nnz
+        g = torch.Generator().manual_seed(1000)
+        cores = [(torch.randn(1, p[t], rr[t] * q[t] * rr[t + 1], generator=g) / np.sqrt(N)).to(dev)
+                 for t in range(3)]
+        idx = [torch.randperm(N, generator=g)[:nnz].to(dev) for _ in range(NUM_ROT)]
+        dout = [((torch.rand(1, nnz, D, generator=g) - 0.5) * 0.2).to(dev) for _ in range(NUM_ROT)]
+        row = torch.arange(nnz, device=dev)
+        tb = torch.zeros(nnz, dtype=torch.int64, device=dev)
+        Lt = torch.tensor([p[1] * p[2], p[2], 1], dtype=torch.int64, device=dev)
+
+        def one(k):
+            rmod.tt_forward(1000, 1, nnz, D, p, q, rr, Lt, nnz, idx[k], row, tb, cores)
+            rmod.tt_sgd_backward(1000, D, LR, p, q, rr, Lt, nnz, idx[k], row, tb, dout[k], cores)
+
+        for i in range(2):
+            one(i % NUM_ROT)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(i % NUM_ROT)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": nnz / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms,
+                "what": "reference FBTT tt_forward + tt_sgd_backward (batch_count 1000), unmodified "
+                        "sources compiled for sm_100a, %d rows per step on one B200" % nnz}
+    except Exception as ex:   # the CPU arm must not fail because the GPU extra did
+        return {"unavailable": str(ex)[:200]}
 
 
 def workload_name(args):
@@ -391,6 +434,28 @@ def run_ours(args, shape):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = calibrated_cpu_baseline(shape)
+    # the reference's own CUDA kernels (unmodified, built for sm_100a by oracle/build_ref.py) on
+    # the same batches: a GPU baseline beside the CPU one; absent when oracle/_ref was not built
+    ref_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import ref_ext
+        rmod = ref_ext.load()
+        if rmod is not None:
+            Lt = torch.tensor([p[1] * p[2], p[2], 1], dtype=torch.int64, device=dev)
+            rcores = [c.clone() for c in cores]
+
+            def ref_step(i):
+                k = i % NUM_ROT
+                rmod.tt_forward(1000, 1, nnz, D, p, q, rr, Lt, nnz, idx_dev[k], rowidx, tableidx, rcores)
+                rmod.tt_sgd_backward(1000, D, LR, p, q, rr, Lt, nnz, idx_dev[k], rowidx, tableidx,
+                                     d_out[k], rcores)
+
+            for i in range(2):
+                ref_step(i)
+            rms = timed(ref_step, 5) / 5
+            ref_gpu = {"value": nnz / (rms * 1e-3), "unit": "rows/s", "ms_per_step": rms,
+                       "what": "reference FBTT tt_forward + tt_sgd_backward (batch_count 1000), "
+                               "unmodified sources compiled for sm_100a, same batches, CUDA events"}
     line = {
         "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -415,6 +480,7 @@ def run_ours(args, shape):
         "kernels_ms": {k: round(v["ms"], 5) for k, v in kern.items()},
         "kernel_share": {k: round(v / tot_k, 4) for k, v in kernel_share.items()},
         "cpu_baseline": cpu,
+        "reference_gpu": ref_gpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -40,6 +40,9 @@ def main():
     ap.add_argument("--hidden", type=int, default=256)
     ap.add_argument("--classes", type=int, default=47)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--matmul", default="fp32", choices=["fp32", "tf32"],
+                    help="precision of the dense SAGE layers (torch library GEMMs, not part of the "
+                         "TT path): fp32 is torch's and the reference's default")
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -59,6 +62,7 @@ def main():
     import sampler
     import tt_embeddings as te
     te.EXTRA_FLAGS = int(args.flags)
+    torch.backends.cuda.matmul.allow_tf32 = (args.matmul == "tf32")
 
     torch.manual_seed(0)
     graph = sage.synthetic_graph(args.nodes, args.edges, dev, seed=0)   # same graph on every rank
@@ -118,6 +122,7 @@ def main():
             "n_gpus": world, "higher_is_better": False, "scaling": "strong", "epochs_timed": secs,
             "steps_per_epoch_per_rank": steps, "ms_per_step": best / steps * 1e3,
             "seeds_per_s": args.train / best, "data": "synthetic", "dtype": "f32",
+            "dense_layer_matmul": args.matmul,
             "loss_last": losses[-1],
             "per_step_mean": {"layer0_input_nodes": st["input_nodes"] / steps,
                               "layer0_edges": st["edges0"] / steps},

@@ -1,0 +1,161 @@
+"""Parity of the CUDA path against the REFERENCE'S OWN CUDA KERNELS, built unmodified for sm_100a
+by oracle/build_ref.py (FBTT/tt_embeddings.cpp + tt_embeddings_cuda.cu, shipped to the GPU box
+as oracle/_ref/*.so).  Skipped when that build is absent.  Values: 1e-5 of the tensor's max
+(the reference accumulates with float atomics in no fixed order); index path: bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ext
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+SHAPES = {
+    "products": ([125, 140, 140], [4, 5, 5], [1, 16, 16, 1], 2449029),
+    "arxiv": ([55, 55, 56], [4, 4, 8], [1, 16, 16, 1], 169343),
+    "papers": ([481, 481, 481], [4, 4, 8], [1, 32, 32, 1], 111059956),
+}
+
+
+@pytest.fixture(scope="module")
+def ref():
+    m = ref_ext.load()
+    if m is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return m
+
+
+def _cores(p, q, r, seed):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(1, p[t], r[t] * q[t] * r[t + 1], generator=g) * (0.5 / np.sqrt(r[t]))).to(DEV)
+            for t in range(3)]
+
+
+def _L(p):
+    return torch.tensor([p[1] * p[2], p[2], 1], dtype=torch.int64, device=DEV)
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize("shape,nnz", [("products", 40000), ("arxiv", 20000), ("papers", 6000),
+                                       ("products", 3000)])
+def test_forward_and_dense_backward_match_reference_kernels(ttg_lib, ref, shape, nnz):
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES[shape]
+    D = int(np.prod(q))
+    cores = _cores(p, q, r, 5)
+    rng = np.random.default_rng(1)
+    hi = min(n_emb, 90000) if nnz > 10000 else n_emb
+    idx = torch.from_numpy(rng.integers(0, hi, size=nnz).astype(np.int64)).to(DEV)
+    row = torch.arange(nnz, device=DEV)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    L = _L(p)
+    want = ref.tt_forward(1000, 1, nnz, D, p, q, r, L, nnz, idx, row, tb, cores)
+    got = te.tt_forward(1000, 1, nnz, D, p, q, r, L, nnz, idx, row, tb, cores)
+    assert _rel(got, want) < TOL
+    dO = (torch.rand(1, nnz, D, generator=torch.Generator().manual_seed(2)) * 0.1).to(DEV)
+    wd = ref.tt_dense_backward(1000, D, p, q, r, L, nnz, idx, row, tb, dO, cores)
+    gd = te.tt_dense_backward(1000, D, p, q, r, L, nnz, idx, row, tb, dO, cores)
+    for t in range(3):
+        assert _rel(gd[t], wd[t]) < 5e-5, "core %d" % t     # float atomics in the reference
+
+
+def test_bags_with_several_indices_match_reference_kernels(ttg_lib, ref):
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["products"]
+    cores = _cores(p, q, r, 6)
+    rng = np.random.default_rng(3)
+    lengths = rng.integers(0, 6, size=4000)
+    offsets = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int64)
+    nnz, B = int(offsets[-1]), lengths.size
+    idx = torch.from_numpy(rng.integers(0, 50000, size=nnz).astype(np.int64)).to(DEV)
+    row = torch.from_numpy(np.repeat(np.arange(B), lengths).astype(np.int64)).to(DEV)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    L = _L(p)
+    want = ref.tt_forward(1000, 1, B, 100, p, q, r, L, nnz, idx, row, tb, cores)
+    got = te.tt_forward(1000, 1, B, 100, p, q, r, L, nnz, idx, row, tb, cores)
+    assert _rel(got, want) < TOL
+
+
+def test_fused_sgd_matches_reference_on_the_rows_it_updates(ttg_lib, ref):
+    """the reference's launch config never updates rows >= ceil(cols/ty)*ty of a core
+    with more rows than columns; on the rows it does update, the two agree."""
+    import tt_embeddings as te
+    from oracle import oracle as orc
+    p, q, r, n_emb = SHAPES["products"]
+    nnz = 30000
+    rng = np.random.default_rng(4)
+    idx = torch.from_numpy(rng.integers(0, n_emb, size=nnz).astype(np.int64)).to(DEV)
+    row = torch.arange(nnz, device=DEV)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    dO = (torch.rand(1, nnz, 100, generator=torch.Generator().manual_seed(5)) * 0.1).to(DEV)
+    L = _L(p)
+    c_ref = _cores(p, q, r, 7)
+    c_our = [c.clone() for c in c_ref]
+    before = [c.clone() for c in c_ref]
+    ref.tt_sgd_backward(1000, 100, 0.1, p, q, r, L, nnz, idx, row, tb, dO, c_ref)
+    te.tt_sgd_backward(1000, 100, 0.1, p, q, r, L, nnz, idx, row, tb, dO, c_our)
+    cols = [r[t] * q[t] * r[t + 1] for t in range(3)]
+    lim = orc.reference_sgd_rows_updated(p, cols)
+    for t in range(3):
+        n = lim[t]
+        assert _rel(c_our[t][:, :n], c_ref[t][:, :n]) < TOL
+        if n < p[t]:      # the tail the reference skips: untouched there, updated here
+            assert torch.equal(c_ref[t][:, n:], before[t][:, n:])
+            assert not torch.equal(c_our[t][:, n:], before[t][:, n:])
+
+
+def test_cache_index_path_matches_reference_kernels(ttg_lib, ref):
+    """update_cache_state -> cache_populate -> preprocess_indices_sync -> cache_forward, the
+    same calls on both extensions.  Insertion races make hash-table slots order dependent, so the
+    state is compared as key -> (frequency, cached) maps and the partitions as sets + order rules."""
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["arxiv"]
+    D = 128
+    cores = _cores(p, q, r, 8)
+    L = _L(p)
+    size, cache_size = 20011, 500
+    rng = np.random.default_rng(6)
+    pop = rng.permutation(n_emb)[:3000]
+    stream = np.repeat(pop, rng.integers(1, 12, size=pop.size))
+    rng.shuffle(stream)
+    state = {}
+    for name, ext in (("ref", ref), ("ours", te)):
+        ht = torch.full((size,), -1, dtype=torch.int64, device=DEV)
+        fr = torch.zeros(size, dtype=torch.int64, device=DEV)
+        cs = torch.full((size,), -1, dtype=torch.int32, device=DEV)
+        cw = torch.zeros(cache_size, D, device=DEV)
+        ext.update_cache_state(torch.from_numpy(stream).to(DEV), ht, fr)
+        ext.cache_populate(n_emb, p, q, r, cores, L, ht, fr, cs, cw)
+        state[name] = (ht, fr, cs, cw)
+    maps = {}
+    for name, (ht, fr, cs, cw) in state.items():
+        h, f, c = ht.cpu().numpy(), fr.cpu().numpy(), cs.cpu().numpy()
+        w = cw.cpu().numpy()
+        maps[name] = {int(k): (int(f[i]), None if c[i] < 0 else w[c[i]]) for i, k in enumerate(h) if k >= 0}
+    assert set(maps["ref"]) == set(maps["ours"])
+    ncached = 0
+    for k, (f, wrow) in maps["ref"].items():
+        f2, wrow2 = maps["ours"][k]
+        assert f == f2
+        if wrow is not None and wrow2 is not None:
+            ncached += 1
+            assert np.abs(wrow - wrow2).max() <= TOL * max(np.abs(wrow).max(), 1e-30)
+    assert ncached > 0
+    # lookups through each extension's own state give the same rows
+    q_idx = torch.from_numpy(rng.permutation(pop)[:2000].astype(np.int64)).to(DEV)
+    offs = torch.arange(q_idx.numel() + 1, device=DEV)
+    outs = {}
+    for name, ext in (("ref", ref), ("ours", te)):
+        ht, fr, cs, cw = state[name]
+        col, rowidx, tbl, n_tt, loc = ext.preprocess_indices_sync(q_idx, offs, 1, False, ht, cs)
+        B = q_idx.numel()
+        out = ext.tt_forward(1000, 1, B, D, p, q, r, L, n_tt, col, rowidx, tbl, cores)
+        if B - n_tt > 0:
+            ext.cache_forward(B, B - n_tt, loc[n_tt:], rowidx[n_tt:], cw, out)
+        outs[name] = (out, n_tt)
+    assert _rel(outs["ours"][0], outs["ref"][0]) < TOL
