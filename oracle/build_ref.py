@@ -2,7 +2,8 @@
 
     python oracle/build_ref.py [--ref /root/reference]
 
-Compiles FBTT/tt_embeddings.cpp + FBTT/tt_embeddings_cuda.cu where they lie under the reference
+Compiles FBTT/tt_embeddings.cpp + FBTT/tt_embeddings_cuda.cu and
+Efficient_TT/efficient_kernel_wrap.cpp + efficient_tt_cuda.cu where they lie under the reference
 tree (nothing is copied into the repo) with nvcc + g++ against this image's torch headers, the
 only change being the flags its setup.py hard-codes (FBTT/setup.py:24-31: compute_86 and a
 private CUB include path).  Output: oracle/_ref/tt_embeddings*.so (git-ignored; it travels to
@@ -21,27 +22,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 
 
-def build(ref):
+def _compile(ref, sub, cpp, cu, modname, stem):
     import torch
     from torch.utils import cpp_extension as ce
-    src_cpp = os.path.join(ref, "FBTT", "tt_embeddings.cpp")
-    src_cu = os.path.join(ref, "FBTT", "tt_embeddings_cuda.cu")
+    src_cpp = os.path.join(ref, sub, cpp)
+    src_cu = os.path.join(ref, sub, cu)
     for f in (src_cpp, src_cu):
         if not os.path.exists(f):
             raise RuntimeError("reference source missing: %s" % f)
     os.makedirs(OUT, exist_ok=True)
     ext = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
-    so = os.path.join(OUT, "tt_embeddings" + ext)
+    so = os.path.join(OUT, stem + ext)
     stamp = so + ".stamp"
     sig = "%s|%s|%s" % (torch.__version__, os.path.getmtime(src_cpp), os.path.getmtime(src_cu))
     if os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == sig:
         return so
     inc = ["-I" + p for p in ce.include_paths("cuda")] + ["-I" + sysconfig.get_paths()["include"],
-                                                          "-I" + os.path.join(ref, "FBTT")]
+                                                          "-I" + os.path.join(ref, sub)]
     abi = "-D_GLIBCXX_USE_CXX11_ABI=%d" % int(torch._C._GLIBCXX_USE_CXX11_ABI)
-    common = ["-DTORCH_EXTENSION_NAME=tt_embeddings", "-DTORCH_API_INCLUDE_EXTENSION_H", abi]
-    obj_cpp, obj_cu = os.path.join(OUT, "tt_embeddings.o"), os.path.join(OUT, "tt_embeddings_cuda.o")
-    subprocess.run(["g++", "-O3", "-fPIC", "-std=c++17", "-c", src_cpp, "-o", obj_cpp] + inc + common,
+    common = ["-DTORCH_EXTENSION_NAME=" + modname, "-DTORCH_API_INCLUDE_EXTENSION_H", abi]
+    obj_cpp, obj_cu = os.path.join(OUT, stem + "_cpp.o"), os.path.join(OUT, stem + "_cu.o")
+    subprocess.run(["g++", "-O3", "-fPIC", "-std=c++17", "-w", "-c", src_cpp, "-o", obj_cpp] + inc + common,
                    check=True)
     subprocess.run(["nvcc", "-O3", "--expt-relaxed-constexpr", "-D__CUDA_NO_HALF_OPERATORS__",
                     "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-Xcompiler", "-fPIC",
@@ -58,8 +59,19 @@ def build(ref):
     return so
 
 
+def build(ref):
+    """FBTT extension (module name fixed by the source: tt_embeddings) and the Efficient_TT one
+    (module name = TORCH_EXTENSION_NAME, built as efficient_tt_ref)."""
+    a = _compile(ref, "FBTT", "tt_embeddings.cpp", "tt_embeddings_cuda.cu", "tt_embeddings",
+                 "tt_embeddings")
+    b = _compile(ref, "Efficient_TT", "efficient_kernel_wrap.cpp", "efficient_tt_cuda.cu",
+                 "efficient_tt_ref", "efficient_tt_ref")
+    return a, b
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default=os.environ.get("TTG_REFERENCE", "/root/reference"))
     a = ap.parse_args()
-    print(build(a.ref))
+    for so in build(a.ref):
+        print(so)

@@ -24,3 +24,24 @@ def load():
     loader.exec_module(mod)
     _mod = mod
     return mod
+
+
+_eff = None
+
+
+def load_efficient():
+    """The reference's Efficient_TT extension (init_cuda, Eff_TT_forward,
+    Fused_Extra_Eff_TT_backward, ...) or None."""
+    global _eff
+    if _eff is not None:
+        return _eff
+    hits = sorted(glob.glob(os.path.join(_HERE, "_ref", "efficient_tt_ref*.so")))
+    if not hits:
+        return None
+    import torch  # noqa: F401
+    loader = importlib.machinery.ExtensionFileLoader("efficient_tt_ref", hits[0])
+    spec = importlib.util.spec_from_file_location("efficient_tt_ref", hits[0], loader=loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    _eff = mod
+    return mod

@@ -159,3 +159,45 @@ def test_cache_index_path_matches_reference_kernels(ttg_lib, ref):
             ext.cache_forward(B, B - n_tt, loc[n_tt:], rowidx[n_tt:], cw, out)
         outs[name] = (out, n_tt)
     assert _rel(outs["ours"][0], outs["ref"][0]) < TOL
+
+
+def test_efficient_tt_matches_reference_kernels(ttg_lib):
+    """Efficient_TT: Eff_TT_forward and Fused_Extra_Eff_TT_backward of the
+    reference's own extension (efficient_tt_cuda.cu:243-377, :1011-1247) against the drop-in, on
+    the products shape (the only BASELINE config its float index math is exact for)."""
+    eff_ref = ref_ext.load_efficient()
+    if eff_ref is None:
+        pytest.skip("oracle/_ref Efficient_TT extension not built")
+    import effi_tt_embeddings as eff
+    p, q, r, n_emb = SHAPES["products"]
+    D, batch = 100, 4096
+    g = torch.Generator().manual_seed(9)
+    cores0 = [(torch.rand(p[t], r[t] * q[t] * r[t + 1], generator=g) * 0.3).to(DEV) for t in range(3)]
+    rng = np.random.default_rng(7)
+    idx_np = rng.integers(0, 120000, size=batch).astype(np.int64)     # clustered: shared prefixes
+    idx_np[:64] = idx_np[64:128]                                      # duplicates in the batch
+    idx = torch.from_numpy(idx_np).to(DEV)
+    tp = torch.tensor(p).to(DEV)
+    tq = torch.tensor(q).to(DEV)
+    tr = torch.tensor(r).to(DEV)
+    eff_ref.init_cuda(0, q, r, batch, D)
+    eff.init_cuda(0, q, r, batch, D)
+    c_ref = [c.clone() for c in cores0]
+    c_our = [c.clone() for c in cores0]
+    want = eff_ref.Eff_TT_forward(batch, n_emb, D, idx, p, q, r, tp, tq, tr, c_ref)
+    got = eff.Eff_TT_forward(batch, n_emb, D, idx, p, q, r, tp, tq, tr, c_our)
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (batch, D)
+    assert _rel(got, want) < TOL
+    dO = (torch.rand(batch, D, generator=g) * 0.1).to(DEV)
+    uniq, inv = idx.unique(sorted=True, return_inverse=True)
+    eff_ref.Fused_Extra_Eff_TT_backward(batch, n_emb, D, 0.1, idx, p, q, r, tp, tq, tr, dO.clone(),
+                                        c_ref, uniq, inv)
+    eff.Fused_Extra_Eff_TT_backward(batch, n_emb, D, 0.1, idx, p, q, r, tp, tq, tr, dO.clone(),
+                                    c_our, uniq, inv)
+    torch.cuda.synchronize()
+    for t in range(3):
+        assert not torch.equal(c_our[t], cores0[t])
+        # compare the UPDATE (cores are O(0.3), the step is much smaller)
+        du, dr = c_our[t] - cores0[t], c_ref[t] - cores0[t]
+        assert float((du - dr).abs().max() / dr.abs().max()) < 1e-4, "core %d" % t
