@@ -84,7 +84,15 @@ def check(rc, what):
         raise RuntimeError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
+_shape_cache = {}
+
+
 def make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables=1):
+    """ttg_shape struct for (p, q, ranks, num_tables); built once per distinct table."""
+    key = (tuple(tt_p_shapes), tuple(tt_q_shapes), tuple(tt_ranks), int(num_tables))
+    s = _shape_cache.get(key)
+    if s is not None:
+        return s
     T = len(tt_p_shapes)
     ranks = [int(x) for x in tt_ranks]
     if len(ranks) == T - 1:
@@ -99,7 +107,42 @@ def make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables=1):
         s.q[t] = int(tt_q_shapes[t])
     for t in range(T + 1):
         s.r[t] = ranks[t]
+    s.key = key          # python-side identity of the table shape (plan keys, size caches)
+    if len(_shape_cache) < 256:
+        _shape_cache[key] = s
     return s
+
+
+_ws_bytes_cache = {}
+
+
+def tt_workspace_bytes(shape, B, nnz):
+    """ttg_tt_workspace_bytes, memoised (the size is a pure function of its arguments)."""
+    key = (getattr(shape, "key", None), int(B), int(nnz))
+    n = _ws_bytes_cache.get(key) if key[0] is not None else None
+    if n is None:
+        n = lib().ttg_tt_workspace_bytes(C.byref(shape), B, nnz)
+        if key[0] is not None and len(_ws_bytes_cache) < 4096:
+            _ws_bytes_cache[key] = n
+    return n
+
+
+class on_device:
+    """`with torch.cuda.device(dev)` that does nothing when dev is already current (the usual
+    case: one process per GPU); switching devices through torch costs ~10 us per call."""
+
+    def __init__(self, dev):
+        idx = dev.index
+        self.ctx = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
 
 
 def ptr(t):

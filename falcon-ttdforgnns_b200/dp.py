@@ -72,7 +72,7 @@ def apply_optimizer(tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores: Sequence[torch
     sp = None
     if optim == _ttg.OPTIM_ADAGRAD:
         sp = _ttg.ptr_array(optimizer_state)
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         cp, dp = _ttg.ptr_array(cores), _ttg.ptr_array(list(d_cores))
         rc = _ttg.lib().ttg_apply_optimizer(C.byref(shape), optim, float(learning_rate), float(eps),
                                             cp, sp, dp, _ttg.stream_of(dev))

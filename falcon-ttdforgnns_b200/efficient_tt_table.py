@@ -50,7 +50,7 @@ def Eff_TT_forward(batch_size: int, table_length: int, feature_dim: int, index: 
     cores = _cores(tt_cores)
     dev = cores[0].device
     shape = _shape3(tt_p_shapes, tt_q_shapes, tt_ranks)
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         raw = index
         index = _ttg.require_cuda(index.long().contiguous(), "index", torch.int64)
         if index.numel() < batch_size:
@@ -86,7 +86,7 @@ def Fused_Extra_Eff_TT_backward(batch_size: int, table_length: int, feature_dim:
     cores = _cores(tt_cores)
     dev = cores[0].device
     shape = _shape3(tt_p_shapes, tt_q_shapes, tt_ranks)
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         indices = _ttg.require_cuda(indices.long().contiguous(), "indices", torch.int64)
         g = d_output.to(torch.float32).contiguous()
         if g.dim() != 2 or g.size(0) < batch_size or g.size(1) != feature_dim:

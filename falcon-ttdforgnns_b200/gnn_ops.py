@@ -56,7 +56,7 @@ class _SpMM(torch.autograd.Function):
         x = _ttg.require_cuda(x.contiguous(), "x", torch.float32)
         dev = x.device
         F = x.size(1)
-        with torch.cuda.device(dev):
+        with _ttg.on_device(dev):
             out = torch.empty((num_dst, F), dtype=torch.float32, device=dev)
             rc = _ttg.lib().ttg_spmm_csr_fwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices),
                                              _ttg.ptr(edge_weight), 1 if mean else 0, _ttg.ptr(x),
@@ -71,7 +71,7 @@ class _SpMM(torch.autograd.Function):
         indptr, indices, edge_weight = ctx.saved_tensors
         num_src, num_dst, F, mean = ctx.cfg
         dev = dout.device
-        with torch.cuda.device(dev):
+        with _ttg.on_device(dev):
             dout = dout.to(torch.float32).contiguous()
             dx = torch.zeros((num_src, F), dtype=torch.float32, device=dev)
             rc = _ttg.lib().ttg_spmm_csr_bwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices),

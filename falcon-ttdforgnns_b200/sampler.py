@@ -48,7 +48,7 @@ def sample_block(g: CSRGraph, dst_nodes: torch.Tensor, fanout: int, seed: int
     dev = dst_nodes.device
     num_dst = dst_nodes.numel()
     lib = _ttg.lib()
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         indptr = torch.empty(num_dst + 1, dtype=torch.int64, device=dev)
         indices = torch.empty(max(num_dst * fanout, 1), dtype=torch.int32, device=dev)
         src = torch.empty(max(num_dst * (fanout + 1), 1), dtype=torch.int64, device=dev)

@@ -24,6 +24,7 @@ __all__ = [
 ]
 
 _scratch = _ttg._Workspace()  # everything that is not the sorted TT plan
+_grad_scratch = {}             # (device, table shape) -> d_cores of the fused-update ops
 
 # test / debugging knob: OR-ed into the flags of tt_forward / tt_*_backward
 # (_ttg.FLAG_FORCE_GENERIC selects the shape-generic kernels)
@@ -60,7 +61,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
     shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
     if cores[0].size(0) != num_tables:
         raise RuntimeError("tt_forward: num_tables does not match tt_cores[0].size(0)")
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         output = torch.empty((num_tables, B, D), dtype=torch.float32, device=dev)
         nnz = int(nnz)
         if nnz > 0:
@@ -70,7 +71,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
             if min(indices.numel(), rowidx.numel(), tableidx.numel()) < nnz:
                 raise RuntimeError("tt_forward: nnz exceeds the index arrays")
         lib = _ttg.lib()
-        nbytes = lib.ttg_tt_workspace_bytes(C.byref(shape), B, nnz)
+        nbytes = _ttg.tt_workspace_bytes(shape, B, nnz)
         ws = _ttg.workspace.get(dev, nbytes)
         cp = _ttg.ptr_array(cores)
         rc = lib.ttg_tt_forward(C.byref(shape), B, nnz, _ttg.ptr(indices), _ttg.ptr(rowidx),
@@ -80,7 +81,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
         if nnz > 0:
             _ttg.workspace.set_plan(dev, _ttg.plan_key_of(
                 _plan_tag(), indices, rowidx, nnz, B,
-                _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables), cores),
+                shape.key, cores),
                 keep=(indices, rowidx))
     return output
 
@@ -91,7 +92,7 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
     dev = cores[0].device
     num_tables = cores[0].size(0)
     shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         if not isinstance(d_output, torch.Tensor) or not d_output.is_cuda:
             raise RuntimeError("tt_backward: d_output must be a CUDA tensor")
         d_output = d_output.to(torch.float32).contiguous()
@@ -99,7 +100,16 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
             raise RuntimeError("tt_backward: d_output must be [num_tables, B, D]")
         B = d_output.size(1)
         nnz = int(nnz)
-        d_cores = [torch.empty_like(c) for c in cores]
+        if optim == _ttg.OPTIM_DENSE:
+            d_cores = [torch.empty_like(c) for c in cores]
+        else:
+            # fused update: the dense gradients are scratch, keep one set per (device, table)
+            ck = (dev.index, shape.key)
+            d_cores = _grad_scratch.get(ck)
+            if d_cores is None or any(g.shape != c.shape for g, c in zip(d_cores, cores)):
+                d_cores = [torch.empty_like(c) for c in cores]
+                if len(_grad_scratch) < 64:
+                    _grad_scratch[ck] = d_cores
         if nnz > 0:
             _ttg.require_cuda(indices, "indices", torch.int64)
             _ttg.require_cuda(rowidx, "rowidx", torch.int64)
@@ -114,13 +124,13 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
                     raise RuntimeError("tt_adagrad_backward: optimizer_state shape mismatch")
             sp = _ttg.ptr_array(states)
         lib = _ttg.lib()
-        nbytes = lib.ttg_tt_workspace_bytes(C.byref(shape), B, nnz)
+        nbytes = _ttg.tt_workspace_bytes(shape, B, nnz)
         ws = _ttg.workspace.get(dev, nbytes)
         flags = 0
         key = None
         if nnz > 0:
             key = _ttg.plan_key_of(_plan_tag(), indices, rowidx, nnz, B,
-                                   _shape_tuple(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables),
+                                   shape.key,
                                    cores)
             if _ttg.workspace.plan(dev) == key:
                 flags |= _ttg.FLAG_PLAN_VALID  # the forward's sort is still in the workspace
@@ -181,7 +191,7 @@ def update_cache_state(indices: torch.Tensor, hashtbl: torch.Tensor,
         raise RuntimeError("update_cache_state: hashtbl and cache_freq must be non-empty and of "
                            "equal length")
     dev = indices.device
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         rc = _ttg.lib().ttg_update_cache_state(indices.numel(), _ttg.ptr(indices), hashtbl.numel(),
                                                _ttg.ptr(hashtbl), _ttg.ptr(cache_freq),
                                                _ttg.stream_of(dev))
@@ -205,7 +215,7 @@ def cache_populate(num_embeddings: int, tt_p_shapes: List[int], tt_q_shapes: Lis
         raise RuntimeError("cache_populate: hashtbl smaller than the cache")
     dev = hashtbl.device
     shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, cores[0].size(0))
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         lib = _ttg.lib()
         nbytes = lib.ttg_cache_populate_workspace_bytes(C.byref(shape), hashtbl.numel(), cw.size(0))
         ws = _scratch.get(dev, nbytes)
@@ -225,7 +235,7 @@ def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tab
     _ttg.require_cuda(offsets, "offsets", torch.int64)
     dev = colidx.device
     nnz = colidx.numel()
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         rowidx = torch.empty_like(colidx)
         tableidx = torch.empty_like(colidx)
         if nnz == 0:
@@ -271,7 +281,7 @@ def cache_forward(B: int, nnz: int, cache_locations: torch.Tensor, rowidx: torch
     cw = _cache_args(nnz, output, cache_locations, rowidx, cache_weight)
     _ttg.require_cuda(output, "output", torch.float32)
     dev = output.device
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         rc = _ttg.lib().ttg_cache_forward(int(nnz), cw.size(1), _ttg.ptr(cache_locations),
                                           _ttg.ptr(rowidx), _ttg.ptr(cw), _ttg.ptr(output),
                                           _ttg.stream_of(dev))
@@ -284,7 +294,7 @@ def cache_backward_sgd(nnz: int, grad_output: torch.Tensor, cache_locations: tor
     """cache_backward_sgd_cuda (FBTT/tt_embeddings_cuda.cu:1634-1668)."""
     cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
     dev = cw.device
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         g = grad_output.to(torch.float32).contiguous()
         rc = _ttg.lib().ttg_cache_backward_sgd(int(nnz), cw.size(1), _ttg.ptr(g),
                                                _ttg.ptr(cache_locations), _ttg.ptr(rowidx),
@@ -299,7 +309,7 @@ def cache_backward_dense(nnz: int, grad_output: torch.Tensor, cache_locations: t
     """cache_backward_dense_cuda (FBTT/tt_embeddings_cuda.cu:1710-1744)."""
     cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
     dev = cw.device
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         grad = torch.zeros_like(cw)
         g = grad_output.to(torch.float32).contiguous()
         rc = _ttg.lib().ttg_cache_backward_dense(int(nnz), cw.size(1), _ttg.ptr(g),
@@ -318,7 +328,7 @@ def cache_backward_rowwise_adagrad_approx(nnz: int, grad_output: torch.Tensor,
     cw = _cache_args(nnz, grad_output, cache_locations, rowidx, cache_weight)
     _ttg.require_cuda(cache_optimizer_state, "cache_optimizer_state", torch.float32)
     dev = cw.device
-    with torch.cuda.device(dev):
+    with _ttg.on_device(dev):
         g = grad_output.to(torch.float32).contiguous()
         rc = _ttg.lib().ttg_cache_backward_rowwise_adagrad_approx(
             int(nnz), cw.size(1), _ttg.ptr(g), _ttg.ptr(cache_locations), _ttg.ptr(rowidx),
