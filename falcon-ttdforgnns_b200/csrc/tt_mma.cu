@@ -30,7 +30,9 @@ namespace {
 
 constexpr int kThreads = 512;            // row kernels: one CTA per SM, 16 warps
 constexpr int kWarps = kThreads / 32;
-constexpr int kCoreThreads = 256;        // table / cores kernels
+constexpr int kCoreThreads = 256;        // table kernel
+constexpr int kCoresThreads = 512;       // cores kernel: 16 warps, two 16-row chunks of S[:, i1] each
+constexpr int kCoresWarps = kCoresThreads / 32;
 constexpr int kCoreWarps = kCoreThreads / 32;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr size_t kSmemMax = 227 * 1024;
@@ -248,6 +250,7 @@ mma_table_kernel(TTDev tt, float* __restrict__ Ttab, int mtiles_per_cta) {
   const int gid = lane >> 2, tid = lane & 3;
   {
     const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
+#pragma unroll   // a handful of iterations: all loads in flight before the first split
     for (int e = threadIdx.x; e < KS * NTL * 64; e += kCoreThreads) {
       const int ks = e / (NTL * 64), r = e % (NTL * 64);
       const int nt = r / 64, l = (r % 64) >> 1, h = r & 1;
@@ -862,7 +865,7 @@ template <int C>
 constexpr int cores_row_stride() { return C + 8; }   // 88 / 72 floats: k-side reads conflict-free
 
 template <int Q0, int Q1, int R1, int R2, int TERMS>
-__global__ void __launch_bounds__(kCoreThreads)
+__global__ void __launch_bounds__(kCoresThreads)
 mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __restrict__ cnt,
                      float* __restrict__ d0parts, float* __restrict__ dcore1, size_t e0) {
   constexpr int A = Q0 * Q1;
@@ -888,9 +891,9 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   constexpr int MAXC = 32 / IPC;
   int on_l = 0;
   auto issue = [&](int it, int buf) {     // it-th chunk of this warp
-    const int ch = wib + kCoreWarps * it;
+    const int ch = wib + kCoresWarps * it;
     if (it % MAXC == 0) {
-      const int c2 = wib + kCoreWarps * (it + lane / IPC);
+      const int c2 = wib + kCoresWarps * (it + lane / IPC);
       const int i0m = c2 * IPC + lane % IPC;
       on_l = 0;
       if (c2 < nchunks && i0m < p0) on_l = __ldg(cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
@@ -913,7 +916,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   // core1[i1] as the N-side operand of P: b0 = B1[k1 = gid + 8 nt][c = tid + 8 ks], b1: c + 4
   {
     const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
-    for (int x = threadIdx.x; x < NTL * 2 * 32; x += kCoreThreads) {
+    for (int x = threadIdx.x; x < NTL * 2 * 32; x += kCoresThreads) {
       const int ks = x / 64, nt = (x / 32) & 1, l = x & 31;
       const int k1 = (l >> 2) + 8 * nt, c = (l & 3) + 8 * ks;
       const float v0 = __ldg(b1p + k1 * C + c), v1 = __ldg(b1p + k1 * C + c + 4);
@@ -930,7 +933,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   const int K = p0 * Q0;
 
   int it = 0;
-  for (int ch = wib; ch < nchunks; ch += kCoreWarps, ++it) {
+  for (int ch = wib; ch < nchunks; ch += kCoresWarps, ++it) {
     issue(it + 1, (it + 1) & 1);
     cp_async_wait<1>();
     __syncwarp();
@@ -1009,10 +1012,10 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   }
   __syncthreads();
   float* dst = dcore1 + (size_t)blockIdx.x * (R1 * C);
-  for (int x = threadIdx.x; x < NTL * 128; x += kCoreThreads) {
+  for (int x = threadIdx.x; x < NTL * 128; x += kCoresThreads) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < kCoreWarps; ++w) v += red[(size_t)w * (NTL * 128) + x];
+    for (int w = 0; w < kCoresWarps; ++w) v += red[(size_t)w * (NTL * 128) + x];
     const int l = x & 31, e = (x >> 5) & 3, nt = x >> 7;
     const int row = (l >> 2) + 8 * (e >> 1), col = 8 * nt + 2 * (l & 3) + (e & 1);
     dst[row * C + col] = v;
@@ -1208,7 +1211,7 @@ struct Shape {
       constexpr int C = Q1 * R2;
       const int nb1 = tt.num_tables * tt.p[1];
       const size_t smem = sizeof(float) * ((C / 8) * 2 * 32 * 4 +
-                                           (size_t)kCoreWarps * 2 * 16 * cores_row_stride<C>());
+                                           (size_t)kCoresWarps * 2 * 16 * cores_row_stride<C>());
       auto kern = mma_bwd_cores_kernel<Q0, Q1, R1, R2, TERMS>;
       static bool attr = false;
       if (!attr) {
@@ -1216,7 +1219,7 @@ struct Shape {
         attr = true;
       }
       prof_begin(K_BWD_CORES, stream);
-      kern<<<nb1, kCoreThreads, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore[1], (size_t)e0);
+      kern<<<nb1, kCoresThreads, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore[1], (size_t)e0);
       prof_end(K_BWD_CORES, stream);
       TTG_LAUNCH_CHECK();
     }
