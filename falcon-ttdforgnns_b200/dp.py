@@ -34,8 +34,25 @@ def epoch_permutation(n: int, epoch: int, seed: int = 0) -> torch.Tensor:
     return torch.randperm(n, generator=g)
 
 
+def _shared_flat(tensors: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The tensors as ONE flat view when they already sit back to back in one storage (what
+    tt_dense_backward returns), else None."""
+    if not tensors or any(not t.is_contiguous() for t in tensors):
+        return None
+    t0 = tensors[0]
+    st = t0.untyped_storage().data_ptr()
+    off = t0.storage_offset()
+    for t in tensors:
+        if t.dtype != t0.dtype or t.untyped_storage().data_ptr() != st or t.storage_offset() != off:
+            return None
+        off += t.numel()
+    total = off - t0.storage_offset()
+    return torch.as_strided(t0, (total,), (1,), t0.storage_offset())
+
+
 def flatten(tensors: Sequence[torch.Tensor]) -> torch.Tensor:
-    return torch.cat([t.reshape(-1) for t in tensors])
+    flat = _shared_flat(tensors)
+    return flat if flat is not None else torch.cat([t.reshape(-1) for t in tensors])
 
 
 def unflatten(flat: torch.Tensor, like: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -50,8 +67,9 @@ def allreduce_mean(tensors: Sequence[torch.Tensor], group=None) -> List[torch.Te
     """One collective for all tensors; returns views into the reduced flat buffer."""
     flat = flatten(tensors)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.div_(dist.get_world_size(group))
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG if flat.is_cuda else dist.ReduceOp.SUM, group=group)
+        if not flat.is_cuda:                       # gloo has no AVG
+            flat.div_(dist.get_world_size(group))
     return unflatten(flat, tensors)
 
 

@@ -101,7 +101,14 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
         B = d_output.size(1)
         nnz = int(nnz)
         if optim == _ttg.OPTIM_DENSE:
-            d_cores = [torch.empty_like(c) for c in cores]
+            # one allocation, views per core: a data-parallel caller all-reduces the flat buffer
+            # without a concatenation (dp.flatten recognises the layout); 16-byte aligned views
+            sizes = [(c.numel() + 3) // 4 * 4 for c in cores]
+            flat = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            d_cores, off = [], 0
+            for c, n in zip(cores, sizes):
+                d_cores.append(flat[off:off + c.numel()].view_as(c))
+                off += n
         else:
             # fused update: the dense gradients are scratch, keep one set per (device, table)
             ck = (dev.index, shape.key)
