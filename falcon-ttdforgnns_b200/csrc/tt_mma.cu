@@ -670,18 +670,39 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt) Sacc[nt][0] = Sacc[nt][1] = Sacc[nt][2] = Sacc[nt][3] = 0.f;
 
+    // The tensor core adds into its fp32 accumulator with truncation, a bias that grows with
+    // the length of the chain; a group with thousands of rows would lose three digits.  So the
+    // accumulators are spilled to S every kSpillTiles tiles: the first spill of a group stores,
+    // later ones add with ordinary (rounded) fp32 adds -- the group belongs to this warp alone.
+    constexpr int kSpillTiles = 8;
+    int tiles_since_spill = 0;
+    bool spilled = false;
     auto flush_S = [&]() {
       if (g_cur == kInvalid) return;
       float* sp = Sbuf + (size_t)g_cur * (A * 16) + 2 * tid * 16 + gid;
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
         if ((8 * nt + 7 < A) || (8 * nt + 2 * tid + 1 < A)) {
-          sp[nt * 128] = Sacc[nt][0];
-          sp[nt * 128 + 8] = Sacc[nt][2];
-          sp[nt * 128 + 16] = Sacc[nt][1];
-          sp[nt * 128 + 24] = Sacc[nt][3];
+          if (spilled) {
+            sp[nt * 128] += Sacc[nt][0];
+            sp[nt * 128 + 8] += Sacc[nt][2];
+            sp[nt * 128 + 16] += Sacc[nt][1];
+            sp[nt * 128 + 24] += Sacc[nt][3];
+          } else {
+            sp[nt * 128] = Sacc[nt][0];
+            sp[nt * 128 + 8] = Sacc[nt][2];
+            sp[nt * 128 + 16] = Sacc[nt][1];
+            sp[nt * 128 + 24] = Sacc[nt][3];
+          }
         }
       }
+    };
+    auto spill_S = [&]() {   // mid-group
+      flush_S();
+      spilled = true;
+      tiles_since_spill = 0;
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) Sacc[nt][0] = Sacc[nt][1] = Sacc[nt][2] = Sacc[nt][3] = 0.f;
     };
 
     int c2pair = 0;            // lane l: (table, i2) * Q2 of row w0 + l of the current buffer
@@ -801,6 +822,8 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
         if (gs != g_cur) {
           flush_S();
           g_cur = gs;
+          spilled = false;
+          tiles_since_spill = 0;
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) Sacc[nt][0] = Sacc[nt][1] = Sacc[nt][2] = Sacc[nt][3] = 0.f;
           if (gs != g_pref) load_T(gs);   // first group of the run: nothing was prefetched
@@ -819,6 +842,9 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
 #pragma unroll 1
         for (; rb + TR <= b; rb += TR) tile(std::true_type{}, rb, TR);
         if (rb < b) tile(std::false_type{}, rb, b - rb);
+        // a segment is at most RB / TR tiles: checking per segment keeps the chain bounded
+        tiles_since_spill += (b - a + TR - 1) / TR;
+        if (tiles_since_spill >= kSpillTiles) spill_S();
       }
       __syncwarp();  // every lane is done with this slot before it is refilled
     }

@@ -448,3 +448,70 @@ def test_spmm(ttg_lib, F, mean):
     dout = rng.normal(size=(num_dst, F)).astype(np.float32)
     out.backward(_t(dout))
     assert rel_err(xt.grad.cpu().numpy(), orc.spmm_csr_bwd(indptr, indices, dout, num_src, mean)) < TOL
+
+
+# --------------------------------------------------------------------------------------------
+# tensor-core path: adversarial index distributions (chunk ownership, tails, invalid keys)
+# --------------------------------------------------------------------------------------------
+def _mma_case(te, shape, idx, B=None, row=None, dO_seed=1, tol=TOL):
+    p, q, r, n_emb = SHAPES[shape]
+    D = int(np.prod(q))
+    cores_cpu = _random_cores(p, q, r, n_emb, 31)
+    cores = [c.to(DEV) for c in cores_cpu]
+    cn = [c.numpy() for c in cores_cpu]
+    nnz = idx.size
+    row = np.arange(nnz, dtype=np.int64) if row is None else row
+    B = nnz if B is None else B
+    valid = (idx >= 0) & (idx < int(np.prod(p)))
+    want = orc.tt_forward(p, q, r, cn, idx[valid], row[valid], B)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    got = te.tt_forward(1000, 1, B, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+    assert rel_err(got.cpu().numpy(), want) < tol
+    dO = (np.random.default_rng(dO_seed).random(size=(1, B, D)).astype(np.float32) * 0.1)
+    wd = orc.tt_backward_dense(p, q, r, cn, idx[valid], row[valid], dO)
+    gd = te.tt_dense_backward(1000, D, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), cores)
+    for t in range(3):
+        assert rel_err(gd[t].cpu().numpy(), wd[t]) < tol, "core %d" % t
+
+
+@pytest.mark.parametrize("shape", ["products", "arxiv"])
+def test_mma_one_giant_group_and_duplicates(ttg_lib, shape):
+    """All rows in one (i0, i1) group -- a single warp owns the whole batch's group -- and a
+    batch that is one index repeated; plus both mixed with a uniform background."""
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES[shape]
+    rng = np.random.default_rng(17)
+    g0 = 37 * p[2]
+    one_group = (g0 + rng.integers(0, p[2], size=9000)).astype(np.int64)
+    _mma_case(te, shape, one_group)
+    same = np.full(7000, g0 + 3, dtype=np.int64)
+    _mma_case(te, shape, same)
+    ngroups = p[0] * p[1]
+    mixed = np.concatenate([one_group[:4000], same[:1000],
+                            rng.integers(0, n_emb, size=max(ngroups, 6000))]).astype(np.int64)
+    rng.shuffle(mixed)
+    _mma_case(te, shape, mixed)
+
+
+def test_mma_tiny_and_ragged_batches(ttg_lib):
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["cora"]       # 196 groups: the table strategy starts at nnz = 196
+    rng = np.random.default_rng(23)
+    for nnz in (196, 197, 211, 255, 513, 1000):
+        _mma_case(te, "cora", rng.integers(0, n_emb, size=nnz).astype(np.int64))
+
+
+def test_mma_invalid_indices_and_bags(ttg_lib):
+    """Out-of-range / negative ids sort behind every valid key and contribute nothing; bags with
+    0..7 indices exercise the zero-fill and the accumulate path of the bulk-copy stores."""
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["arxiv"]
+    rng = np.random.default_rng(29)
+    lengths = rng.integers(0, 8, size=3000)
+    nnz = int(lengths.sum())
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    bad = rng.permutation(nnz)[:200]
+    idx[bad[:100]] = -1 - rng.integers(0, 5, size=100)
+    idx[bad[100:]] = int(np.prod(p)) + rng.integers(0, 1000, size=100)
+    row = np.repeat(np.arange(lengths.size), lengths).astype(np.int64)
+    _mma_case(te, "arxiv", idx, B=lengths.size, row=row)
