@@ -354,6 +354,19 @@ def run_ours(args, shape):
             i += 1
         lib.ttg_profile_enable(0)
 
+    # ---- the same step in the two other arithmetic modes (eager launches, CUDA events): context
+    # for the headline number, not part of it
+    alt_modes = None
+    if world == 1 and not args.no_cpu_baseline and args.flags == 0:
+        alt_modes = {}
+        for name, fl in (("default_3xtf32", 0), ("tf32_single_pass", 8), ("fp32_ffma_kernels", 16)):
+            te.EXTRA_FLAGS = fl
+            for i in range(3):
+                raw_step(i % NUM_ROT)
+            ms_alt = timed(lambda i: raw_step(i % NUM_ROT), 10) / 10
+            alt_modes[name] = {"ms_per_step_eager": ms_alt, "rows_per_s": nnz / (ms_alt * 1e-3)}
+        te.EXTRA_FLAGS = int(args.flags)
+
     # ---- end to end through the module API (host indices in, scalar loss out)
     idx_stage = torch.empty(nnz, dtype=torch.int64, device=dev)
     off_stage = torch.empty(nnz + 1, dtype=torch.int64, device=dev)
@@ -484,6 +497,7 @@ def run_ours(args, shape):
         "kernel_share": {k: round(v / tot_k, 4) for k, v in kernel_share.items()},
         "cpu_baseline": cpu,
         "reference_gpu": ref_gpu,
+        "alt_modes": alt_modes,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
