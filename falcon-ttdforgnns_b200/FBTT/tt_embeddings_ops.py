@@ -333,8 +333,22 @@ class TableBatchedTTEmbeddingBag(nn.Module):
     # -- weights ------------------------------------------------------------------------------
     def full_weight(self) -> torch.Tensor:
         assert self.num_tables == 1, "full_weight() only supported for num_tables == 1 for now"
+        if not torch.is_grad_enabled():   # no autograd wanted: the row kernel on implicit keys
+            w = self.rows_range(0, int(np.prod(self.tt_p_shapes)))
+            if w is not None:
+                return w
         return tt_matrix_to_full(self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
                                  list(self.tt_cores), [1, 0, 2, 3])
+
+    def rows_range(self, first_row: int, num_rows: int) -> Optional[torch.Tensor]:
+        """Rows [first_row, first_row + num_rows) in order, not differentiable: what the
+        full-graph drivers and SAGE.inference request as forward(arange(N), arange(N + 1))
+        (gcn_gat_partition.py:93-96, gnn_model.py:228-231), without index arrays or plan.
+        None when the shape has no tensor-core kernels (use forward on an arange then)."""
+        if self.num_tables != 1 or self.tt_ndim != 3:
+            return None
+        return tt_embeddings.tt_rows_range(first_row, num_rows, self.tt_p_shapes, self.tt_q_shapes,
+                                           self.tt_ranks, [c.data for c in self.tt_cores])
 
     def reset_parameters(self, weight_dist: str) -> None:
         """Core initialisers (reference :629-808)."""

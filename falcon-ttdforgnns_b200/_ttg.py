@@ -39,6 +39,8 @@ SIGNATURES = {
     "ttg_tt_forward": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "ttg_tt_backward": (C.c_int, [_SP, _i32, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _sz, _i32, _vp]),
+    "ttg_tt_rows_range_workspace_bytes": (_sz, [_SP]),
+    "ttg_tt_rows_range": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _sz, _i32, _vp]),
     "ttg_update_cache_state": (C.c_int, [_i64, _vp, _i64, _vp, _vp, _vp]),
     "ttg_cache_populate_workspace_bytes": (_sz, [_SP, _i64, _i64]),
     "ttg_cache_populate": (C.c_int, [_SP, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _sz, _vp]),

@@ -253,6 +253,25 @@ extern "C" int ttg_tt_backward(const ttg_shape* shape, int32_t optim, float lr, 
                               lr, eps, host_state_ptrs, workspace, workspace_bytes, flags, stream);
 }
 
+extern "C" size_t ttg_tt_rows_range_workspace_bytes(const ttg_shape* shape) {
+  TTDev tt;
+  const float* dummy[TTG_MAX_CORES] = {nullptr, nullptr, nullptr, nullptr};
+  if (make_ttdev(shape, dummy, &tt) != TTG_OK || tt.T != 3) return 0;
+  return sorted_workspace_bytes(tt, 1, (int64_t)tt.p[0] * tt.p[1]);
+}
+
+extern "C" int ttg_tt_rows_range(const ttg_shape* shape, int64_t first_row, int64_t num_rows,
+                                 const float* const* host_core_ptrs, float* output, void* workspace,
+                                 size_t workspace_bytes, int32_t flags, void* stream) {
+  TTDev tt;
+  int rc = make_ttdev(shape, host_core_ptrs, &tt);
+  if (rc != TTG_OK) return rc;
+  TTG_CHECK_ARG(output != nullptr || num_rows == 0, "rows_range: null output");
+  for (int t = 0; t < tt.T; ++t) TTG_CHECK_ARG(tt.core[t] != nullptr, "rows_range: null core %d", t);
+  return sorted_rows_range(tt, first_row, num_rows, output, workspace, workspace_bytes, flags,
+                           (cudaStream_t)stream);
+}
+
 extern "C" size_t ttg_eff_workspace_bytes(const ttg_shape* shape, int64_t batch) {
   TTDev tt;
   const float* dummy[TTG_MAX_CORES] = {nullptr, nullptr, nullptr, nullptr};

@@ -119,6 +119,9 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
                     float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
                     void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream);
 
+int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* output, void* ws,
+                      size_t ws_bytes, int32_t flags, cudaStream_t stream);
+
 // tensor-core kernels for the group-table strategy, tt_mma.cu (plan built by tt_sorted.cu)
 struct MmaPlan {
   const uint32_t* skeys;   // keys grouped by (i0, i1), invalid keys last
@@ -128,6 +131,7 @@ struct MmaPlan {
   float* Ttab;             // [groups][q0 q1][r2]
   float* S;                // [groups][q0 q1][r2]
   float* d0parts;          // [p1][core0 elements]: per-i1 partial products of d_core0
+  uint32_t first_key;      // skeys == nullptr: the keys are first_key, first_key + 1, ...
 };
 bool mma_supported(const TTDev& tt);
 int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream);

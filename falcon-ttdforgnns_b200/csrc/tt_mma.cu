@@ -343,7 +343,10 @@ template <int Q0, int Q1, int Q2, int R2, int TERMS>
 __global__ void __launch_bounds__(kThreads, 1)
 mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
                const int32_t* __restrict__ srow, const float* __restrict__ Ttab,
-               float* __restrict__ output, int rows_per_warp, int npairs_c2, int dbg) {
+               float* __restrict__ output, int rows_per_warp, int npairs_c2, int dbg,
+               uint32_t first_key) {
+  // skeys == nullptr: the rows are first_key, first_key + 1, ... in order (full-table / range
+  // reconstruction): no plan, output row n = n-th key, a buffer leaves as ONE copy
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;
@@ -408,8 +411,8 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
   uint32_t nkey = total_rows;
   int32_t nsr = 0;
   if (lane < 2 * RB && s_begin + lane < s_end) {
-    nkey = __ldg(skeys + s_begin + lane);
-    nsr = __ldg(srow + s_begin + lane);
+    nkey = skeys ? __ldg(skeys + s_begin + lane) : first_key + (uint32_t)(s_begin + lane);
+    nsr = skeys ? __ldg(srow + s_begin + lane) : (int32_t)(s_begin + lane);
   }
   for (int64_t w0 = s_begin; w0 < s_end; w0 += 2 * RB) {
     const uint32_t key = nkey;
@@ -417,8 +420,8 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
     nkey = total_rows;
     nsr = 0;
     if (lane < 2 * RB && w0 + 2 * RB + lane < s_end) {
-      nkey = __ldg(skeys + w0 + 2 * RB + lane);
-      nsr = __ldg(srow + w0 + 2 * RB + lane);
+      nkey = skeys ? __ldg(skeys + w0 + 2 * RB + lane) : first_key + (uint32_t)(w0 + 2 * RB + lane);
+      nsr = skeys ? __ldg(srow + w0 + 2 * RB + lane) : (int32_t)(w0 + 2 * RB + lane);
     }
     const int nwin = (int)((s_end - w0 < 2 * RB) ? (s_end - w0) : 2 * RB);
     const bool kvalid = key < total_rows;
@@ -517,6 +520,13 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
       }
       fence_proxy_async();
       __syncwarp();
+      if (skeys == nullptr) {   // consecutive output rows: the whole buffer in one bulk copy
+        if (lane == 0 && !(dbg & 1)) {
+          bulk_store(output + (w0 + h * RB) * D, stage, (uint32_t)(nrows * D * 4));
+          bulk_commit();
+        }
+        continue;
+      }
       {
         const int src = h * RB + (lane < RB ? lane : 0);
         const uint32_t k_r = __shfl_sync(0xffffffffu, key, src);
@@ -1197,7 +1207,8 @@ struct Shape {
     rpw = ceil_div(rpw, RB) * RB;
     prof_begin(K_FWD, stream);
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, pl.skeys, pl.srow, pl.Ttab,
-                                                     output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"));
+                                                     output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
+                                                     pl.first_key);
     prof_end(K_FWD, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;

@@ -1469,6 +1469,7 @@ MmaPlan mma_plan(const SortedWs& w) {
   pl.Ttab = w.Ttab;
   pl.S = w.S;
   pl.d0parts = w.d0parts;
+  pl.first_key = 0;
   return pl;
 }
 
@@ -1542,6 +1543,40 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
                   output, zero_only, stream);
   if (rc != TTG_OK) return rc;
   return e->fwd(tt, nnz, total_rows, w, output, stream);
+}
+
+// rows [first_row, first_row + num) of table 0 in order, no index arrays and no plan
+int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* output, void* ws,
+                      size_t ws_bytes, int32_t flags, cudaStream_t stream) {
+  if (!find_entry(tt) || !mma_supported(tt) || tt.num_tables != 1) {
+    set_error("rows_range: shape has no tensor-core kernels");
+    return TTG_ENOTSUP;
+  }
+  if (first_row < 0 || num < 0 || first_row + num > tt.num_rows) {
+    set_error("rows_range: [%lld, %lld) outside the table", (long long)first_row,
+              (long long)(first_row + num));
+    return TTG_EINVAL;
+  }
+  if (num == 0) return TTG_OK;
+  if (((uintptr_t)output & 15) != 0) {
+    set_error("rows_range: output must be 16-byte aligned");
+    return TTG_EINVAL;
+  }
+  // the group table is the only scratch: lay the workspace out as for a dense batch
+  const int64_t groups = (int64_t)tt.p[0] * tt.p[1];
+  SortedWs w = carve(tt, 1, groups, (char*)ws);
+  if (ws == nullptr || ws_bytes < w.total || w.Ttab == nullptr) {
+    set_error("rows_range: workspace %zu < %zu bytes", ws_bytes, w.total);
+    return TTG_ENOMEM;
+  }
+  MmaPlan pl = mma_plan(w);
+  const bool tf32 = (flags & TTG_FLAG_TF32) != 0;
+  int rc = mma_table(tt, pl, tf32, stream);
+  if (rc != TTG_OK) return rc;
+  pl.skeys = nullptr;
+  pl.srow = nullptr;
+  pl.first_key = (uint32_t)first_row;
+  return mma_forward(tt, num, (uint32_t)tt.num_rows, pl, output, tf32, stream);
 }
 
 int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,

@@ -86,6 +86,37 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
     return output
 
 
+def tt_rows_range(first_row: int, num_rows: int, tt_p_shapes: List[int], tt_q_shapes: List[int],
+                  tt_ranks: List[int], tt_cores: List[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Rows [first_row, first_row + num_rows) of a single-table TT matrix, in order, without index
+    arrays (ttg_tt_rows_range; not an op of the reference, which gets the same rows from
+    tt_forward(arange) -- gcn_gat_partition.py:93-96).  Returns None when the shape has no
+    tensor-core kernels; the caller then uses tt_forward on an explicit range."""
+    cores = _cores_ok(tt_cores, len(tt_p_shapes))
+    if len(tt_p_shapes) != 3 or cores[0].size(0) != 1:
+        return None
+    dev = cores[0].device
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, 1)
+    D = 1
+    for x in tt_q_shapes:
+        D *= int(x)
+    with _ttg.on_device(dev):
+        lib = _ttg.lib()
+        nbytes = lib.ttg_tt_rows_range_workspace_bytes(C.byref(shape))
+        if nbytes == 0:
+            return None
+        out = torch.empty((int(num_rows), D), dtype=torch.float32, device=dev)
+        ws = _ttg.workspace.get(dev, nbytes)
+        _ttg.workspace.set_plan(dev, None)          # the workspace no longer holds a batch's plan
+        rc = lib.ttg_tt_rows_range(C.byref(shape), int(first_row), int(num_rows), _ttg.ptr_array(cores),
+                                   _ttg.ptr(out), _ttg.ptr(ws), ws.numel(), EXTRA_FLAGS,
+                                   _ttg.stream_of(dev))
+        if rc == -4:                                # TTG_ENOTSUP
+            return None
+        _ttg.check(rc, "tt_rows_range")
+    return out
+
+
 def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indices, rowidx,
               tableidx, d_output, optimizer_state, tt_cores):
     cores = _cores_ok(tt_cores, len(tt_p_shapes))

@@ -118,6 +118,17 @@ int ttg_tt_backward(const ttg_shape* shape, int32_t optim, float lr, float eps, 
                     float* const* host_dcore_ptrs,     /* T device pointers (outputs)        */
                     void* workspace, size_t workspace_bytes, int32_t flags, void* stream);
 
+/* (f-2) rows [first_row, first_row + num_rows) of a single-table TT matrix, in order: what the
+ * reference obtains with forward(arange(N), arange(N + 1)) in its full-graph GCN / GAT steps and
+ * in SAGE.inference (gcn_gat_partition.py:93-96, gnn_model.py:228-231).  No index arrays, no plan:
+ * group table, then the forward row kernel on implicit keys; every staging buffer leaves as one
+ * bulk copy.  Only for shapes with tensor-core kernels (TTG_ENOTSUP otherwise: the caller falls
+ * back to ttg_tt_forward on an explicit index range). */
+size_t ttg_tt_rows_range_workspace_bytes(const ttg_shape* shape);
+int ttg_tt_rows_range(const ttg_shape* shape, int64_t first_row, int64_t num_rows,
+                      const float* const* host_core_ptrs, float* output, void* workspace,
+                      size_t workspace_bytes, int32_t flags, void* stream);
+
 /* The optimizer step alone (what ttg_tt_backward fuses), for data-parallel training where the
  * dense gradients are all-reduced between the backward and the update.
  * replaces: update_tt_cores_sgd_kernel / update_tt_cores_adagrad_kernel

@@ -170,3 +170,28 @@ def test_sageconv_and_graphconv_against_dense_torch(ttg_lib):
     ref = ((A @ (h.double() / odeg.sqrt()[:, None])) / deg.sqrt()[:, None]) @ conv.weight.double() \
         + conv.bias.double()
     torch.testing.assert_close(out, ref.float(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("cfg", [
+    (169343, 128, [16, 16], [55, 55, 56], [4, 4, 8]),
+    (2708, 128, [16, 16], [14, 14, 14], [4, 4, 8]),
+    (60000, 100, [16, 16], [30, 40, 50], [4, 5, 5]),
+])
+def test_rows_range_equals_tt_matrix_to_full(ttg_lib, cfg):
+    """the plan-free range reconstruction against the reference's pure-PyTorch
+    contraction (FBTT/tt_embeddings_ops.py:80-127), whole table and an unaligned slice."""
+    from FBTT.tt_embeddings_ops import tt_matrix_to_full
+    n_emb, D, ranks, p, q = cfg
+    m = _make(n_emb, D, ranks, p, q, sparse=False)
+    W = tt_matrix_to_full(p, q, [1] + ranks + [1], [c.detach() for c in m.tt_cores], [1, 0, 2, 3])
+    with torch.no_grad():
+        full = m.full_weight()
+    assert full.shape == W.shape
+    assert float((full - W).abs().max() / W.abs().max()) < 1e-5
+    a, n = 1237, 20011 if n_emb > 30000 else 997
+    part = m.rows_range(a, n)
+    assert torch.equal(part, full[a:a + n])
+    # and the same rows through the indexed forward
+    idx = torch.arange(a, a + n, device=full.device)
+    out = m(idx, torch.arange(n + 1, device=full.device))
+    assert float((out - part).abs().max() / W.abs().max()) < 1e-6
