@@ -144,3 +144,197 @@ class GraphConv(nn.Module):
         if self.bias is not None:
             rst = rst + self.bias
         return rst
+
+
+# --------------------------------------------------------------------------------------------
+# GAT (reference: class GATConv / GAT, gnn_model.py:300-497)
+# --------------------------------------------------------------------------------------------
+class _EdgeSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, indptr, score, num_dst):
+        score = _ttg.require_cuda(score.contiguous(), "score", torch.float32)
+        dev, H = score.device, score.size(1)
+        with _ttg.on_device(dev):
+            a = torch.empty_like(score)
+            rc = _ttg.lib().ttg_edge_softmax_csr_fwd(num_dst, H, _ttg.ptr(indptr), _ttg.ptr(score),
+                                                     _ttg.ptr(a), _ttg.stream_of(dev))
+            _ttg.check(rc, "edge_softmax_csr_fwd")
+        ctx.save_for_backward(indptr, a)
+        ctx.num_dst = num_dst
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        indptr, a = ctx.saved_tensors
+        dev, H = a.device, a.size(1)
+        with _ttg.on_device(dev):
+            da = da.to(torch.float32).contiguous()
+            ds = torch.empty_like(a)
+            rc = _ttg.lib().ttg_edge_softmax_csr_bwd(ctx.num_dst, H, _ttg.ptr(indptr), _ttg.ptr(a),
+                                                     _ttg.ptr(da), _ttg.ptr(ds), _ttg.stream_of(dev))
+            _ttg.check(rc, "edge_softmax_csr_bwd")
+        return None, ds, None
+
+
+class _HeadSpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, indptr, indices, a, ft, num_dst):
+        a = _ttg.require_cuda(a.contiguous(), "a", torch.float32)
+        ft = _ttg.require_cuda(ft.contiguous(), "ft", torch.float32)      # [num_src][H][F]
+        dev, H, F = ft.device, ft.size(1), ft.size(2)
+        with _ttg.on_device(dev):
+            out = torch.empty((num_dst, H, F), dtype=torch.float32, device=dev)
+            rc = _ttg.lib().ttg_head_spmm_csr_fwd(num_dst, H, F, _ttg.ptr(indptr), _ttg.ptr(indices),
+                                                  _ttg.ptr(a), _ttg.ptr(ft), _ttg.ptr(out),
+                                                  _ttg.stream_of(dev))
+            _ttg.check(rc, "head_spmm_csr_fwd")
+        ctx.save_for_backward(indptr, indices, a, ft)
+        ctx.num_dst = num_dst
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        indptr, indices, a, ft = ctx.saved_tensors
+        dev, H, F = ft.device, ft.size(1), ft.size(2)
+        with _ttg.on_device(dev):
+            dout = dout.to(torch.float32).contiguous()
+            dft = torch.zeros_like(ft)
+            da = torch.empty_like(a)
+            rc = _ttg.lib().ttg_head_spmm_csr_bwd(ctx.num_dst, H, F, _ttg.ptr(indptr),
+                                                  _ttg.ptr(indices), _ttg.ptr(a), _ttg.ptr(ft),
+                                                  _ttg.ptr(dout), _ttg.ptr(dft), _ttg.ptr(da),
+                                                  _ttg.stream_of(dev))
+            _ttg.check(rc, "head_spmm_csr_bwd")
+        return None, None, da, dft, None
+
+
+def edge_softmax(block: Block, score: torch.Tensor) -> torch.Tensor:
+    """softmax of score [E][H] over the in-edges of every destination node, per head."""
+    return _EdgeSoftmax.apply(block.indptr, score, block.num_dst)
+
+
+def attention_aggregate(block: Block, a: torch.Tensor, ft: torch.Tensor) -> torch.Tensor:
+    """out[v, h, :] = sum_{e in N_in(v)} a[e, h] * ft[src(e), h, :]"""
+    return _HeadSpMM.apply(block.indptr, block.indices, a, ft, block.num_dst)
+
+
+class GATConv(nn.Module):
+    """The reference's GATConv (gnn_model.py:318-440; same constructor keywords, parameter names
+    and initialisation): attention scores by "first projection then addition", LeakyReLU, softmax
+    over the in-edges, attention-weighted sum, optional symmetric degree normalisation
+    (norm="both"), residual and activation.  Returns [num_dst, num_heads, out_feats]."""
+
+    def __init__(self, in_feats, out_feats, num_heads=1, feat_drop=0.0, attn_drop=0.0,
+                 negative_slope=0.2, residual=False, activation=None, allow_zero_in_degree=False,
+                 norm="none"):
+        super().__init__()
+        if norm not in ("none", "both"):
+            raise ValueError('Invalid norm value. Must be either "none", "both". But got "%s".' % norm)
+        self._num_heads, self._out_feats, self._norm = num_heads, out_feats, norm
+        self._in_src_feats, self._in_dst_feats = (in_feats if isinstance(in_feats, tuple)
+                                                  else (in_feats, in_feats))
+        self._allow_zero_in_degree = allow_zero_in_degree
+        if isinstance(in_feats, tuple):
+            self.fc_src = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
+            self.fc_dst = nn.Linear(self._in_dst_feats, out_feats * num_heads, bias=False)
+        else:
+            self.fc = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop = nn.Dropout(feat_drop)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.leaky_relu = nn.LeakyReLU(negative_slope)
+        if residual:
+            self.res_fc = (nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=False)
+                           if self._in_dst_feats != out_feats else nn.Identity())
+        else:
+            self.register_buffer("res_fc", None)
+        self._activation = activation
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        gain = nn.init.calculate_gain("relu")
+        if hasattr(self, "fc"):
+            nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        else:
+            nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
+            nn.init.xavier_normal_(self.fc_dst.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+        if isinstance(self.res_fc, nn.Linear):
+            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+
+    def set_allow_zero_in_degree(self, set_value):
+        self._allow_zero_in_degree = set_value
+
+    def forward(self, block: Block, feat):
+        H, F = self._num_heads, self._out_feats
+        if isinstance(feat, tuple):
+            h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
+            fc_src = self.fc_src if hasattr(self, "fc_src") else self.fc
+            fc_dst = self.fc_dst if hasattr(self, "fc_dst") else self.fc
+            feat_src = fc_src(h_src).view(-1, H, F)
+            feat_dst = fc_dst(h_dst).view(-1, H, F)
+        else:
+            h_src = h_dst = self.feat_drop(feat)
+            feat_src = self.fc(h_src).view(-1, H, F)
+            feat_dst = feat_src[:block.num_dst]
+            h_dst = h_dst[:block.num_dst]
+        if self._norm == "both":
+            degs = block.out_degrees().float().clamp(min=1)
+            feat_src = feat_src * degs.pow(-0.5).view(-1, 1, 1)
+        el = (feat_src * self.attn_l).sum(dim=-1)              # [num_src][H]
+        er = (feat_dst * self.attn_r).sum(dim=-1)              # [num_dst][H]
+        deg_in = block.in_degrees()
+        dst_of_edge = torch.repeat_interleave(torch.arange(block.num_dst, device=el.device), deg_in)
+        e = self.leaky_relu(el[block.indices.long()] + er[dst_of_edge])      # u_add_v
+        a = self.attn_drop(edge_softmax(block, e))
+        rst = attention_aggregate(block, a, feat_src)
+        if self._norm == "both":
+            rst = rst * deg_in.float().clamp(min=1).pow(0.5).view(-1, 1, 1)
+        if self.res_fc is not None:
+            rst = rst + self.res_fc(h_dst).view(h_dst.shape[0], -1, F)
+        if self._activation is not None:
+            rst = self._activation(rst)
+        return rst
+
+
+class _Bias(nn.Module):
+    def __init__(self, size):
+        super().__init__()
+        self.bias = nn.Parameter(torch.zeros(size))
+
+    def forward(self, x):
+        return x + self.bias
+
+
+class GAT(nn.Module):
+    """The reference's GAT model (gnn_model.py:444-497): GATConv + a parallel Linear per layer,
+    BatchNorm / activation / dropout between layers, mean over heads and a bias at the end."""
+
+    def __init__(self, in_feats, n_classes, n_hidden, n_layers, n_heads, activation, dropout=0.0,
+                 attn_drop=0.0, norm="none"):
+        super().__init__()
+        self.n_layers, self.num_heads = n_layers, n_heads
+        self.convs, self.linear, self.bns = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        for i in range(n_layers):
+            in_hidden = n_heads * n_hidden if i > 0 else in_feats
+            out_hidden = n_hidden if i < n_layers - 1 else n_classes
+            self.convs.append(GATConv(in_hidden, out_hidden, num_heads=n_heads, attn_drop=attn_drop,
+                                      norm=norm))
+            self.linear.append(nn.Linear(in_hidden, n_heads * out_hidden, bias=False))
+            if i < n_layers - 1:
+                self.bns.append(nn.BatchNorm1d(n_heads * out_hidden))
+        self.bias_last = _Bias(n_classes)
+        self.dropout0 = nn.Dropout(min(0.1, dropout))
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def forward(self, graph: Block, feat):
+        h = self.dropout0(feat)
+        for i in range(self.n_layers):
+            conv = self.convs[i](graph, h)
+            h = conv + self.linear[i](h[:graph.num_dst]).view(conv.shape)
+            if i < self.n_layers - 1:
+                h = self.dropout(self.activation(self.bns[i](h.flatten(1))))
+        return self.bias_last(h.mean(1))

@@ -236,6 +236,28 @@ int ttg_spmm_csr_bwd(int64_t num_dst, int32_t F, const int64_t* indptr,
                      const float* dout, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-4) the sparse part of GATConv on a CSR-by-destination block.
+ * replaces: apply_edges(u_add_v) + leaky_relu + edge_softmax and update_all(u_mul_e, sum) of
+ *           the reference's GATConv, gnn_model.py:413-420 (DGL 2.1, un-vendored: restated).
+ * score / a / da / dscore fp32 [E][H] (edge-major), ft / dft fp32 [num_src][H*F],
+ * out / dout fp32 [num_dst][H*F]; H <= 8.
+ *   edge_softmax : a[e,h] = softmax over the in-edges of dst(e), per head
+ *   head_spmm    : out[v,h,:] = sum_{e in N_in(v)} a[e,h] * ft[src(e),h,:]
+ *   backward     : dscore = a * (da - sum_e a da);  dft += a * dout (dft zeroed by the caller),
+ *                  da[e,h] = <dout[v,h,:], ft[src(e),h,:]>
+ * ---------------------------------------------------------------------------------- */
+int ttg_edge_softmax_csr_fwd(int64_t num_dst, int32_t H, const int64_t* indptr, const float* score,
+                             float* out, void* stream);
+int ttg_edge_softmax_csr_bwd(int64_t num_dst, int32_t H, const int64_t* indptr, const float* a,
+                             const float* da, float* dscore, void* stream);
+int ttg_head_spmm_csr_fwd(int64_t num_dst, int32_t H, int32_t F, const int64_t* indptr,
+                          const int32_t* indices, const float* a, const float* ft, float* out,
+                          void* stream);
+int ttg_head_spmm_csr_bwd(int64_t num_dst, int32_t H, int32_t F, const int64_t* indptr,
+                          const int32_t* indices, const float* a, const float* ft,
+                          const float* dout, float* dft, float* da, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (f-1) neighbour sampling + block construction on the device, one GNN layer per call.
  * replaces: dgl.dataloading.NeighborSampler (uniform, without replacement) + to_block as the
  *           reference drives them, graphloader.py:245-261, sage_dgl_partition.py:141-154
