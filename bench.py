@@ -237,6 +237,7 @@ def run_ours(args, shape):
         dist.init_process_group("nccl", device_id=dev)
     import _ttg
     import dp
+    import pipeline
     import tt_embeddings as te
     from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
 
@@ -367,34 +368,87 @@ def run_ours(args, shape):
             alt_modes[name] = {"ms_per_step_eager": ms_alt, "rows_per_s": nnz / (ms_alt * 1e-3)}
         te.EXTRA_FLAGS = int(args.flags)
 
-    # ---- end to end through the module API (host indices in, scalar loss out)
-    idx_stage = torch.empty(nnz, dtype=torch.int64, device=dev)
-    off_stage = torch.empty(nnz + 1, dtype=torch.int64, device=dev)
-    target = [d.view(nnz, D) for d in d_out]
-    losses = []
-
+    # ---- end to end through the module API (host indices in, scalar loss out).  Every step's
+    # index arrays go pinned host -> device inside the timed region (on the copy stream of
+    # pipeline.HostBatchPipeline, one step ahead of the kernels) and every step's loss comes back
+    # to the host inside it (pipeline.DeferredScalars, read one step late; the last one is
+    # drained before the closing event).  `e2e_sync` is the same loop with the copies on the
+    # compute stream and loss.item() every step.
+    # the loss is <out, target>: the cheapest one whose gradient (d_output = target) is arbitrary
+    target = [d.view(-1) for d in d_out]
     module.sparse = (world == 1)   # N > 1: dense gradients, all-reduce, then the update
 
-    def e2e_step(i):
-        k = i % NUM_ROT
-        idx_stage.copy_(idx_host[k], non_blocking=True)
-        off_stage.copy_(off_host, non_blocking=True)
-        out = module(idx_stage, off_stage)
-        if world == 1:
-            loss = (out * target[k]).sum()
-            loss.backward()
-        else:  # data parallel: explicit exchange step instead of the fused update
-            loss = (out * target[k]).sum()
-            loss.backward()
+    def module_step(indices, offsets, k):
+        out = module(indices, offsets)
+        loss = torch.dot(out.view(-1), target[k])
+        loss.backward()
+        if world > 1:  # data parallel: explicit exchange step instead of the fused update
             dp.dp_backward_step(module, [c.grad for c in module.tt_cores])
             for c in module.tt_cores:
                 c.grad = None
-        losses.append(float(loss.item()))
+        return loss
 
-    for i in range(3):
-        e2e_step(i)
-    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    pipe = pipeline.HostBatchPipeline(dev, depth=2)
+    graphed = {}     # (staging slot, batch) -> the module step captured as a CUDA graph
+    e2e_graph = (world == 1 and not args.no_graph)   # N > 1 stays eager (NCCL, see above)
+
+    def e2e_pipelined(nsteps, use_graphs):
+        reader = pipeline.DeferredScalars(dev, delay=1)
+        got, h0 = [], pipe.h2d_bytes
+        pipe.put(idx_host[0], off_host)
+        for i in range(nsteps):
+            k = i % NUM_ROT
+            indices, offsets = pipe.get()
+            if i + 1 < nsteps:
+                pipe.put(idx_host[(i + 1) % NUM_ROT], off_host)
+            if use_graphs:
+                gk = (indices.data_ptr(), k)
+                gs = graphed.get(gk)
+                if gs is None:   # warm-up only: NUM_ROT is a multiple of the pipeline depth
+                    gs = graphed[gk] = pipeline.GraphedStep(
+                        lambda: module_step(indices, offsets, k), dev)
+                loss = gs()
+            else:
+                loss = module_step(indices, offsets, k)
+            pipe.release()
+            got += reader.push(loss)
+        got += reader.drain()
+        assert len(got) == nsteps
+        return got, (pipe.h2d_bytes - h0) // nsteps, reader.d2h_bytes // nsteps
+
+    idx_stage = torch.empty(nnz, dtype=torch.int64, device=dev)
+    off_stage = torch.empty(nnz + 1, dtype=torch.int64, device=dev)
+
+    def e2e_sync_step(i):
+        k = i % NUM_ROT
+        idx_stage.copy_(idx_host[k], non_blocking=True)
+        off_stage.copy_(off_host, non_blocking=True)
+        return float(module_step(idx_stage, off_stage, k).item())
+
+    res = {}
+    e2e_pipelined(NUM_ROT, False)
+    e2e_eager_ms = timed(lambda i: res.update(r=e2e_pipelined(args.steps, False)), 1) / args.steps
+    if e2e_graph:
+        try:
+            e2e_pipelined(NUM_ROT, True)      # captures the NUM_ROT graphs
+            e2e_pipelined(NUM_ROT, True)
+            n_before = len(graphed)
+            e2e_ms = timed(lambda i: res.update(r=e2e_pipelined(args.steps, True)), 1) / args.steps
+            assert len(graphed) == n_before, "a graph was captured inside the timed region"
+        except Exception as ex:   # capture is an optimisation of the launch path, not a fallback
+            print("bench.py: e2e graph capture failed (%s); reporting eager launches" % ex,
+                  file=sys.stderr)
+            e2e_graph = False
+            sync_all()
+            res.clear()
+            e2e_eager_ms = timed(lambda i: res.update(r=e2e_pipelined(args.steps, False)), 1) / args.steps
+    if not e2e_graph:
+        e2e_ms = e2e_eager_ms
+    losses, h2d_per_step, d2h_per_step = res["r"]
     e2e_value = world * nnz / (e2e_ms * 1e-3)
+    for i in range(3):
+        e2e_sync_step(i)
+    e2e_sync_ms = timed(e2e_sync_step, args.steps) / args.steps
 
     if rank != 0:
         if world > 1:
@@ -486,8 +540,16 @@ def run_ours(args, shape):
                        world, ", NCCL all-reduce of d_cores per step" if world > 1 else "")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(nnz * 8 + (nnz + 1) * 8), "d2h_bytes_per_step": 4,
-                "api": "TTEmbeddingBag.forward(indices, offsets) + loss.backward(), loss.item()",
+                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
+                "api": "TTEmbeddingBag.forward(indices, offsets), loss = dot(out, target), loss.backward(); indices and "
+                       "offsets staged from pinned host memory one step ahead on a copy stream "
+                       "(pipeline.HostBatchPipeline), the loss read back every step, one step "
+                       "late (pipeline.DeferredScalars)" + (
+                           "; the module step replayed as a CUDA graph (pipeline.GraphedStep)"
+                           if e2e_graph else ""),
+                "launch": "cuda_graph" if e2e_graph else "eager",
+                "ms_per_step_eager_pipelined": e2e_eager_ms,
+                "ms_per_step_eager_unpipelined": e2e_sync_ms,
                 "loss_last": losses[-1] if losses else None},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,

@@ -482,4 +482,7 @@ class TTEmbeddingBag(TableBatchedTTEmbeddingBag):
 
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor,
                 warmup: bool = True) -> torch.Tensor:
-        return super().forward(indices, offsets, warmup)[0]
+        # squeeze, not [0]: autograd's select-backward allocates a zero-filled [1, B, D] tensor and
+        # copies the gradient into it (three passes over B * D floats per step); the adjoint of
+        # squeeze is a view
+        return super().forward(indices, offsets, warmup).squeeze(0)
