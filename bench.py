@@ -231,9 +231,13 @@ def run_ours(args, shape):
                            "use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = sys.stdout
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # the version banner goes to stdout; ours is one JSON line
+        # libraries write to file descriptor 1 (NCCL's version banner at NCCL_DEBUG=VERSION / WARN);
+        # ours is ONE JSON line: keep a private copy of stdout for it and point fd 1 at stderr
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     import _ttg
     import dp
@@ -262,6 +266,16 @@ def run_ours(args, shape):
     d_out = [((torch.rand(1, nnz, D, generator=g) - 0.5) * 0.2).to(dev) for _ in range(NUM_ROT)]
     groups = int(torch.unique(idx_host[0] // p[2]).numel())
 
+    # N > 1: the exchange step is one kernel over NVLink peer memory (dp.PeerExchange); NCCL
+    # all-reduce + optimizer launch only if the peers cannot be mapped (--exchange nccl forces it)
+    xchg = None
+    if world > 1 and args.exchange == "peer":
+        try:
+            xchg = dp.PeerExchange(cores)
+        except Exception as ex:
+            print("bench.py: peer exchange unavailable (%s); using the NCCL all-reduce" % ex,
+                  file=sys.stderr)
+
     def raw_step(k):
         out = te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx, cores)
         if world == 1:
@@ -270,7 +284,10 @@ def run_ours(args, shape):
         else:
             dc = te.tt_dense_backward(1000, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx,
                                       d_out[k], cores)
-            dp.apply_optimizer(p, q, rr, cores, dp.allreduce_mean(dc), LR)
+            if xchg is not None:
+                xchg.step(dc, cores, "sgd", LR)
+            else:
+                dp.apply_optimizer(p, q, rr, cores, dp.allreduce_mean(dc), LR)
         return out
 
     def sync_all():
@@ -287,10 +304,10 @@ def run_ours(args, shape):
     raw_step(0)
     launches_per_step = int(lib.ttg_launch_count() - l0)
     sync_all()
-    # N > 1 stays eager: capturing the NCCL all-reduce into the graph works and is 8 % faster
-    # (0.2105 vs 0.2276 ms/step on 2 GPUs), but the process then hangs in
-    # destroy_process_group at exit (measured once, 2026-10-18)
-    graphs, use_graph = [], (world == 1 and not args.no_graph)
+    # with the NCCL all-reduce the step stays eager: capturing it works and is 8 % faster (0.2105
+    # vs 0.2276 ms/step on 2 GPUs), but the process then hangs in destroy_process_group at exit
+    # (measured once, 2026-10-18).  The peer-memory exchange is an ordinary kernel and captures.
+    graphs, use_graph = [], ((world == 1 or xchg is not None) and not args.no_graph)
     if use_graph:
         try:
             side = torch.cuda.Stream(dev)
@@ -383,14 +400,14 @@ def run_ours(args, shape):
         loss = torch.dot(out.view(-1), target[k])
         loss.backward()
         if world > 1:  # data parallel: explicit exchange step instead of the fused update
-            dp.dp_backward_step(module, [c.grad for c in module.tt_cores])
+            dp.dp_backward_step(module, [c.grad for c in module.tt_cores], exchange=xchg)
             for c in module.tt_cores:
                 c.grad = None
         return loss
 
     pipe = pipeline.HostBatchPipeline(dev, depth=2)
     graphed = {}     # (staging slot, batch) -> the module step captured as a CUDA graph
-    e2e_graph = (world == 1 and not args.no_graph)   # N > 1 stays eager (NCCL, see above)
+    e2e_graph = use_graph   # with NCCL in the step it stays eager (see above)
 
     def e2e_pipelined(nsteps, use_graphs):
         reader = pipeline.DeferredScalars(dev, delay=1)
@@ -450,10 +467,17 @@ def run_ours(args, shape):
         e2e_sync_step(i)
     e2e_sync_ms = timed(e2e_sync_step, args.steps) / args.steps
 
+    exchange_failed, peer_exchange = 0, xchg is not None
+    if xchg is not None:          # collective: before the ranks part ways
+        exchange_failed = xchg.failed_epoch()
+        xchg.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if exchange_failed:
+        print("bench.py: a peer did not arrive at exchange step %d; the numbers are invalid"
+              % exchange_failed, file=sys.stderr)
 
     # ---- roofline
     hbm_peak, peak_src, sm_max = measured_peaks()
@@ -537,7 +561,9 @@ def run_ours(args, shape):
                    "l2": "4 rotating batches, 212 MB touched per step (> 126 MB L2)",
                    "launch": "cuda_graph" if use_graph else "eager",
                    "parallelism": "dp%d, replicated cores%s" % (
-                       world, ", NCCL all-reduce of d_cores per step" if world > 1 else "")},
+                       world, "" if world == 1 else
+                       ", d_cores exchanged and the update applied by one kernel over NVLink peer memory"
+                       if peer_exchange else ", NCCL all-reduce of d_cores per step")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
@@ -561,7 +587,7 @@ def run_ours(args, shape):
         "reference_gpu": ref_gpu,
         "alt_modes": alt_modes,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -577,6 +603,8 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=16384,
                     help="rows per step of the --impl reference (CPU) arm")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: how the core gradients are exchanged")
     ap.add_argument("--flags", type=int, default=0,
                     help="TTG_FLAG_* bits OR-ed into every tt_forward / tt_backward call "
                          "(8 = plain TF32 tensor-core mode, 16 = fp32 FFMA kernels)")

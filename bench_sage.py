@@ -53,9 +53,12 @@ def main():
         raise RuntimeError("bench_sage.py needs CUDA devices (the product has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    json_out = sys.stdout
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # libraries write to fd 1 (NCCL's version banner); keep a private copy for the JSON line
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     import dp
     import sage
@@ -132,7 +135,7 @@ def main():
                                    (args.hidden, args.classes, args.batch, args.train, args.nodes,
                                     args.edges),
                        "parallelism": "dp%d, replicated model, one NCCL all-reduce per step" % world
-                       if world > 1 else "dp1, fused TT SGD"}}), flush=True)
+                       if world > 1 else "dp1, fused TT SGD"}}), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libttg_b200.so")
 _lib = None
 
 TTG_MAX_CORES = 4
+TTG_MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
 FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC, FLAG_TF32, FLAG_FFMA = 1, 2, 4, 8, 16
 
@@ -35,6 +37,15 @@ SIGNATURES = {
     "ttg_profile_read": (C.c_int, [_i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ttg_profile_name": (C.c_char_p, [_i32]),
     "ttg_apply_optimizer": (C.c_int, [_SP, _i32, _f32, _f32, _vp, _vp, _vp, _vp]),
+    "ttg_peer_buffer_bytes": (_sz, [_i64]),
+    "ttg_peer_alloc": (C.c_int, [_sz, C.POINTER(C.c_void_p)]),
+    "ttg_peer_free": (C.c_int, [_vp]),
+    "ttg_peer_export": (C.c_int, [_vp, _vp]),
+    "ttg_peer_open": (C.c_int, [_vp, C.POINTER(C.c_void_p)]),
+    "ttg_peer_close": (C.c_int, [_vp]),
+    "ttg_peer_status": (C.c_int, [_vp, _i64, C.POINTER(C.c_uint32)]),
+    "ttg_dp_exchange_update": (C.c_int, [_i32, _i32, _vp, _i32, C.POINTER(C.c_int64), _vp, _vp, _vp,
+                                         _i32, _f32, _f32, _vp, _vp]),
     "ttg_tt_workspace_bytes": (_sz, [_SP, _i64, _i64]),
     "ttg_tt_forward": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "ttg_tt_backward": (C.c_int, [_SP, _i32, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,

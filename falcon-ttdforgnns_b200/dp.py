@@ -97,12 +97,125 @@ def apply_optimizer(tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores: Sequence[torch
         _ttg.check(rc, "apply_optimizer")
 
 
-def dp_backward_step(module, d_cores: Sequence[torch.Tensor], group=None):
+class PeerExchange:
+    """The exchange step without NCCL: gradient slots that every GPU of the node has mapped, and
+    one kernel per step that publishes this rank's gradients, waits for the peers, sums the copies
+    in rank order and applies the optimizer (ttg_dp_exchange_update, csrc/peer.cu).  One object
+    per replicated TT table.
+
+        xchg = PeerExchange(module.tt_cores)          # collective: every rank of `group`
+        ... loss.backward()                           # dense gradients, anywhere
+        xchg.step(grads, module.tt_cores, "sgd", lr)  # every rank, same sequence of calls
+
+    step() has no per-step host state (the step counter lives on the device), so it can be
+    captured in a CUDA graph together with the forward and backward.  Raises RuntimeError when
+    the ranks are not GPUs of one node with peer access."""
+
+    def __init__(self, tt_cores: Sequence[torch.Tensor], group=None):
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange: torch.distributed is not initialised")
+        cores = [c.data if isinstance(c, torch.nn.Parameter) else c for c in tt_cores]
+        for i, c in enumerate(cores):
+            _ttg.require_cuda(c, "tt_cores[%d]" % i, torch.float32)
+            if c.numel() % 4:
+                raise RuntimeError("PeerExchange: core %d has %d elements, not a multiple of 4"
+                                   % (i, c.numel()))
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > _ttg.TTG_MAX_PEERS:
+            raise RuntimeError("PeerExchange: at most %d ranks" % _ttg.TTG_MAX_PEERS)
+        self.device = cores[0].device
+        self.sizes = [c.numel() for c in cores]
+        self.total = sum(self.sizes)
+        self.seg = (C.c_int64 * len(self.sizes))(*self.sizes)
+        lib = _ttg.lib()
+        self.nbytes = lib.ttg_peer_buffer_bytes(self.total)
+        own = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _ttg.check(lib.ttg_peer_alloc(self.nbytes, C.byref(own)), "peer_alloc")
+            self.own = own.value
+            handle = (C.c_ubyte * _ttg.PEER_HANDLE_BYTES)()
+            _ttg.check(lib.ttg_peer_export(own, handle), "peer_export")
+            import socket
+            mine = (socket.gethostname(), bytes(handle))
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=group)
+            if any(h[0] != mine[0] for h in everyone):
+                lib.ttg_peer_free(own)
+                self.own = None
+                raise RuntimeError("PeerExchange: the ranks are not on one node")
+            self.ptrs = (C.c_void_p * _ttg.TTG_MAX_PEERS)()
+            self.opened = []
+            for r, (_, h) in enumerate(everyone):
+                if r == self.rank:
+                    self.ptrs[r] = self.own
+                    continue
+                p = C.c_void_p()
+                buf = (C.c_ubyte * _ttg.PEER_HANDLE_BYTES).from_buffer_copy(h)
+                _ttg.check(lib.ttg_peer_open(buf, C.byref(p)), "peer_open(rank %d)" % r)
+                self.ptrs[r] = p.value
+                self.opened.append(p.value)
+        dist.barrier(group=group)      # every buffer is mapped everywhere before the first signal
+
+    def step(self, d_cores: Sequence[torch.Tensor], tt_cores: Sequence[torch.Tensor],
+             optimizer: str = "sgd", learning_rate: float = 0.0, eps: float = 1e-10,
+             optimizer_state: Optional[Sequence[torch.Tensor]] = None,
+             mean_out: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """optimizer: "sgd" | "adagrad" | "dense" (only the mean gradient, returned as a flat
+        tensor).  Every rank must call step() the same number of times."""
+        optim = {"sgd": _ttg.OPTIM_SGD, "adagrad": _ttg.OPTIM_ADAGRAD, "dense": _ttg.OPTIM_DENSE}[optimizer]
+        cores = [c.data if isinstance(c, torch.nn.Parameter) else c for c in tt_cores]
+        grads = []
+        for i, (g, n) in enumerate(zip(d_cores, self.sizes)):
+            g = _ttg.require_cuda(g.detach(), "d_cores[%d]" % i, torch.float32)
+            if g.numel() != n:
+                raise RuntimeError("PeerExchange.step: gradient %d has the wrong size" % i)
+            grads.append(g)
+        if optim == _ttg.OPTIM_DENSE and mean_out is None:
+            mean_out = torch.empty(self.total, dtype=torch.float32, device=self.device)
+        sp = _ttg.ptr_array(optimizer_state) if optim == _ttg.OPTIM_ADAGRAD else None
+        with _ttg.on_device(self.device):
+            rc = _ttg.lib().ttg_dp_exchange_update(
+                self.world, self.rank, self.ptrs, len(self.sizes), self.seg, _ttg.ptr_array(grads),
+                _ttg.ptr_array(cores), sp, optim, float(learning_rate), float(eps),
+                _ttg.ptr(mean_out), _ttg.stream_of(self.device))
+            _ttg.check(rc, "dp_exchange_update")
+        return mean_out
+
+    def failed_epoch(self) -> int:
+        """0, or the step at which a peer did not arrive within the kernel's wait budget
+        (synchronises the device)."""
+        v = C.c_uint32(0)
+        torch.cuda.synchronize(self.device)
+        _ttg.check(_ttg.lib().ttg_peer_status(C.c_void_p(self.own), self.total, C.byref(v)), "peer_status")
+        return int(v.value)
+
+    def close(self) -> None:
+        if self.own is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)               # nobody still reads what is about to go away
+        lib = _ttg.lib()
+        for p in self.opened:
+            lib.ttg_peer_close(C.c_void_p(p))
+        self.opened = []
+        lib.ttg_peer_free(C.c_void_p(self.own))
+        self.own = None
+
+
+def dp_backward_step(module, d_cores: Sequence[torch.Tensor], group=None,
+                     exchange: Optional[PeerExchange] = None):
     """All-reduce the dense core gradients of a TTEmbeddingBag and apply its own optimizer:
-    the data-parallel equivalent of the fused --sparse update."""
+    the data-parallel equivalent of the fused --sparse update.  With `exchange` the whole step is
+    one kernel over NVLink peer memory, otherwise one NCCL all-reduce plus the update."""
     from FBTT.tt_embeddings_ops import OptimType
-    reduced = allreduce_mean(d_cores, group)
     sgd = module.optimizer in (OptimType.SGD, OptimType.EXACT_SGD)
+    if exchange is not None:
+        exchange.step(d_cores, list(module.tt_cores), "sgd" if sgd else "adagrad",
+                      module.learning_rate, module.eps, None if sgd else list(module.optimizer_state))
+        return None
+    reduced = allreduce_mean(d_cores, group)
     apply_optimizer(module.tt_p_shapes, module.tt_q_shapes, module.tt_ranks, list(module.tt_cores),
                     reduced, module.learning_rate, "sgd" if sgd else "adagrad", module.eps,
                     None if sgd else list(module.optimizer_state))

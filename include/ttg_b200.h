@@ -33,6 +33,8 @@ extern "C" {
 #endif
 
 #define TTG_MAX_CORES 4
+#define TTG_MAX_PEERS 8           /* GPUs of one NVSwitch node                  */
+#define TTG_PEER_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t)                 */
 
 enum {
   TTG_OK = 0,
@@ -136,6 +138,38 @@ int ttg_tt_rows_range(const ttg_shape* shape, int64_t first_row, int64_t num_row
 int ttg_apply_optimizer(const ttg_shape* shape, int32_t optim, float lr, float eps,
                         float* const* host_core_ptrs, float* const* host_state_ptrs,
                         float* const* host_dcore_ptrs, void* stream);
+
+/* Data-parallel exchange step over NVLink peer memory: the replacement of
+ * DistributedDataParallel's all-reduce of the core gradients + the optimizer step
+ * (sage_dgl_partition.py:235, FBTT/tt_embeddings_cuda.cu:381-419) by ONE kernel per step.
+ *
+ * Every rank (one process per GPU of one node) owns an exchange buffer of
+ * ttg_peer_buffer_bytes(slot_floats) bytes: two gradient slots of slot_floats floats (each
+ * rounded up to 256 bytes) followed by 64 flag words.  ttg_peer_alloc / _export on the owner,
+ * ttg_peer_open on every other rank (the 64-byte handle travels by any host channel, e.g.
+ * torch.distributed.all_gather_object); peer_buffers[r] is rank r's buffer as mapped HERE
+ * (own allocation at r == rank).
+ *
+ * ttg_dp_exchange_update, called once per step on every rank after ttg_tt_backward(
+ * TTG_OPTIM_DENSE) on the same stream: copies the dense gradients host_dcore_ptrs[t]
+ * (seg_floats[t] floats each, a multiple of 4) into the slot of this step, signals the peers,
+ * waits for all of them (bounded: after about 10 s the kernel gives up and records the step, see
+ * ttg_peer_status), sums the `world` copies in rank order (bit-identical on all ranks), divides by
+ * `world` and applies `optim` to the local cores (TTG_OPTIM_DENSE: only writes the mean to
+ * mean_out, segments back to back; mean_out may also be given with the other modes).  The step
+ * counter lives in the buffer: the call has no per-step argument and can be captured in a CUDA
+ * graph.  Every rank must issue the same sequence of calls. */
+size_t ttg_peer_buffer_bytes(int64_t slot_floats);
+int ttg_peer_alloc(size_t bytes, void** ptr);
+int ttg_peer_free(void* ptr);
+int ttg_peer_export(void* ptr, void* handle64);
+int ttg_peer_open(const void* handle64, void** ptr);
+int ttg_peer_close(void* ptr);
+int ttg_peer_status(const void* own_buffer, int64_t slot_floats, uint32_t* failed_epoch);
+int ttg_dp_exchange_update(int32_t world, int32_t rank, void* const* peer_buffers, int32_t nseg,
+                           const int64_t* seg_floats, const float* const* host_dcore_ptrs,
+                           float* const* host_core_ptrs, float* const* host_state_ptrs,
+                           int32_t optim, float lr, float eps, float* mean_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (c) index path: LFU hash-table cache.
