@@ -71,6 +71,33 @@ def synthetic_graph(num_nodes: int, num_edges: int, device, seed: int = 0, alpha
     return CSRGraph(indptr, indices)
 
 
+def synthetic_community_graph(num_nodes: int, num_edges: int, k: int, p_in: float, device,
+                              seed: int = 0):
+    """Symmetric graph with k equal communities (an undirected edge stays inside its community
+    with probability p_in) whose node ids are scrambled -- what a raw dataset looks like before
+    graphloader.py:399-454 reorders it.  Returns (graph, community id of every node)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    half = num_edges // 2
+    size = (num_nodes + k - 1) // k
+    src = torch.randint(0, num_nodes, (half,), generator=g, device=device)
+    inside = torch.rand(half, generator=g, device=device) < p_in
+    lo = (src // size) * size
+    width = torch.minimum(torch.full_like(lo, size), num_nodes - lo)
+    near = lo + (torch.rand(half, generator=g, device=device, dtype=torch.float64) * width).long()
+    far = torch.randint(0, num_nodes, (half,), generator=g, device=device)
+    dst = torch.where(inside, near, far)
+    scramble = torch.randperm(num_nodes, generator=g, device=device)
+    s, d = scramble[torch.cat([src, dst])], scramble[torch.cat([dst, src])]
+    order = torch.sort(d * num_nodes + s).indices
+    s, d = s[order], d[order]
+    indptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(torch.bincount(d, minlength=num_nodes), 0, out=indptr[1:])
+    comm = torch.empty(num_nodes, dtype=torch.int64, device=device)
+    comm[scramble] = torch.arange(num_nodes, device=device) // size
+    return CSRGraph(indptr, s.to(torch.int32)), comm
+
+
 class Trainer:
     """One optimisation step of the reference's training loop (sage_dgl_partition.py:205-262):
     Adam on the SAGE layers, the TT cores by their fused SGD (single GPU, --sparse) or -- data

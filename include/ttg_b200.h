@@ -313,6 +313,32 @@ int ttg_sample_block(int64_t num_nodes, const int64_t* g_indptr, const int32_t* 
                      int64_t* blk_indptr, int32_t* blk_indices, int64_t* src_nodes,
                      int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * (f-3) node reordering of a CSR graph (in-neighbour lists: indptr int64 [n + 1], indices int32).
+ * replaces: dgl.reorder_graph(graph, 'custom' | 'rcmk' | 'metis', ...) as called at
+ *           graphloader.py:370, 432, 440, 449 (DGL 2.1, un-vendored)
+ *
+ * ttg_permute_csr: the graph under the node permutation `perm` (new node i = old node perm[i],
+ * DGL's nodes_perm convention); neighbour lists keep their order, ids are mapped through the
+ * inverse permutation (also written to inverse_out when not NULL).  *bad_flag (device int32) is
+ * set to 1 when perm holds an id outside [0, n); the outputs are then undefined.
+ *
+ * ttg_partition_grow: k parts grown from `seeds` by capacity-bounded label propagation over the
+ * in-neighbour lists -- the stand-in for METIS-k (NOT the same partition; connected parts of at
+ * most `cap` nodes).  Runs `sweeps` (even) synchronous sweeps; *changed (device int32) tells
+ * whether any node joined a part in this call: call again with seeds == NULL (continue from
+ * labels_a / sizes) until it stays 0.  labels_a holds the part of every node, -1 for nodes no
+ * part could take.
+ * ---------------------------------------------------------------------------------- */
+size_t ttg_permute_csr_workspace_bytes(int64_t num_nodes);
+int ttg_permute_csr(int64_t num_nodes, const int64_t* indptr, const int32_t* indices,
+                    const int64_t* perm, int64_t* new_indptr, int32_t* new_indices,
+                    int64_t* inverse_out, int32_t* bad_flag, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int ttg_partition_grow(int64_t num_nodes, const int64_t* indptr, const int32_t* indices, int32_t k,
+                       int32_t cap, const int64_t* seeds, int32_t sweeps, int32_t* labels_a,
+                       int32_t* labels_b, int32_t* sizes, int32_t* changed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
