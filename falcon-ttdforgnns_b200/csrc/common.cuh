@@ -133,7 +133,8 @@ struct MmaPlan {
   float* d0parts;          // [p1][core0 elements]: per-i1 partial products of d_core0
   uint32_t first_key;      // skeys == nullptr: the keys are first_key, first_key + 1, ...
 };
-bool mma_supported(const TTDev& tt);
+bool mma_supported(const TTDev& tt);       // table, forward and backward
+bool mma_fwd_supported(const TTDev& tt);   // table and forward (ranks 32: the backward stays FFMA)
 int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream);
 int mma_forward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl, float* output,
                 bool tf32, cudaStream_t stream);

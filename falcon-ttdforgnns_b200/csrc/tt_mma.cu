@@ -339,7 +339,7 @@ __device__ __forceinline__ PairSlot pair_slot(int p) {
 // forward rows.  Persistent CTAs, one contiguous run of sorted rows per warp.  M side = pairs,
 // N side = (j0 j1), K side = k2:  out[(n j2), (j0 j1)] = sum_k2 core2[i2_n][k2, j2] tr0[(j0 j1), k2]
 // ------------------------------------------------------------------------------------------
-template <int Q0, int Q1, int Q2, int R2, int TERMS>
+template <int Q0, int Q1, int Q2, int R2, int TERMS, bool C2S>
 __global__ void __launch_bounds__(kThreads, 1)
 mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __restrict__ skeys,
                const int32_t* __restrict__ srow, const float* __restrict__ Ttab,
@@ -347,34 +347,39 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
                uint32_t first_key) {
   // skeys == nullptr: the rows are first_key, first_key + 1, ... in order (full-table / range
   // reconstruction): no plan, output row n = n-th key, a buffer leaves as ONE copy
+  // C2S: core2 sits in shared memory (split once); otherwise (ranks 32: 492 KB at papers100M
+  // shape) its fragments come from global memory / L2 and are split per tile
   constexpr int A = Q0 * Q1;
   constexpr int D = A * Q2;
   constexpr int NTL = (A + 7) / 8;
+  constexpr int KS = R2 / 8;
   constexpr int TR = tile_rows(Q2);
   constexpr int RB = fwd_rb(Q2);
   constexpr int CS = kC2Stride;
-  static_assert(R2 == 16, "forward fragment layout is written for r2 = 16");
+  static_assert(R2 % 8 == 0 && (!C2S || R2 == 16), "shared-memory core2 layout is written for r2 = 16");
   static_assert(D % 4 == 0 && A % 2 == 0 && 2 * RB <= 32, "layout");
   extern __shared__ __align__(128) float smem[];
   float* c2hi = smem;                                            // [npairs_c2][CS]
   float* c2lo = smem + (size_t)npairs_c2 * CS;                   // TERMS == 3 only
-  float* stage_all = smem + (size_t)npairs_c2 * CS * (TERMS == 3 ? 2 : 1);
+  float* stage_all = smem + (C2S ? (size_t)npairs_c2 * CS * (TERMS == 3 ? 2 : 1) : 0);
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
-  stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
-    const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
-    const int k2 = rem / Q2, j2 = rem % Q2;
-    const int dst = (i2row * Q2 + j2) * CS + k2;
-    if (TERMS == 3) {
-      const float hi = tf32_hi(v);
-      c2hi[dst] = hi;
-      c2lo[dst] = v - hi;
-    } else {
-      c2hi[dst] = __uint_as_float(__float_as_uint(v) + 0x1000u);
-    }
-  });
-  __syncthreads();
+  if (C2S) {
+    stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
+      const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
+      const int k2 = rem / Q2, j2 = rem % Q2;
+      const int dst = (i2row * Q2 + j2) * CS + k2;
+      if (TERMS == 3) {
+        const float hi = tf32_hi(v);
+        c2hi[dst] = hi;
+        c2lo[dst] = v - hi;
+      } else {
+        c2hi[dst] = __uint_as_float(__float_as_uint(v) + 0x1000u);
+      }
+    });
+    __syncthreads();
+  }
 
   const uint32_t p2 = tt.p[2];
   const uint32_t num_rows32 = (uint32_t)tt.num_rows;
@@ -389,19 +394,19 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
   // last n-tile: columns (j0 j1) >= A do not exist
   const bool last_nt_ok = (8 * (NTL - 1) + 2 * tid + 1) < A;
 
-  Frag<TERMS> bt[NTL][2][2];   // tr0 of the group held, N-side operand
-  float traw[NTL][2][2];       // tr0 of the group that comes next, loaded one segment ahead
+  Frag<TERMS> bt[NTL][KS][2];  // tr0 of the group held, N-side operand
+  float traw[NTL][KS][2];      // tr0 of the group that comes next, loaded one segment ahead
   uint32_t g_held = kInvalid, g_pref = kInvalid;
   // b0 = T[col][tid + 8 ks], b1 = T[col][tid + 4 + 8 ks], col = gid + 8 nt
   auto load_T = [&](uint32_t gq) {
-    const float* tp = Ttab + (size_t)gq * (A * 16) + gid * 16 + tid;
+    const float* tp = Ttab + (size_t)gq * (A * R2) + gid * R2 + tid;
 #pragma unroll
     for (int nt = 0; nt < NTL; ++nt) {
       const bool cv = (8 * nt + 7 < A) || (gid + 8 * nt < A);
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        traw[nt][ks][0] = cv ? __ldg(tp + nt * 128 + 8 * ks) : 0.f;
-        traw[nt][ks][1] = cv ? __ldg(tp + nt * 128 + 8 * ks + 4) : 0.f;
+      for (int ks = 0; ks < KS; ++ks) {
+        traw[nt][ks][0] = cv ? __ldg(tp + nt * 8 * R2 + 8 * ks) : 0.f;
+        traw[nt][ks][1] = cv ? __ldg(tp + nt * 8 * R2 + 8 * ks + 4) : 0.f;
       }
     }
     g_pref = gq;
@@ -452,7 +457,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
               bt[nt][ks][0].set(traw[nt][ks][0]);
               bt[nt][ks][1].set(traw[nt][ks][1]);
             }
@@ -476,9 +481,27 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
           const int cp1 = __shfl_sync(0xffffffffu, c2pair, h * RB + r1) + sl1.j2;
           const float* ph0 = c2hi + cp0 * CS + tid;
           const float* ph1 = c2hi + cp1 * CS + tid;
-          Frag<TERMS> af[2][4];
+          Frag<TERMS> af[KS][4];
+          if (!C2S) {
+            // core2[c2row][k2][j2] in global memory: cp = c2row * Q2 + j2, so the element sits at
+            // (cp - j2) * R2 + k2 * Q2 + j2
+            const float* g0 = tt.core[2] + (size_t)(cp0 - sl0.j2) * R2 + sl0.j2 + tid * Q2;
+            const float* g1 = tt.core[2] + (size_t)(cp1 - sl1.j2) * R2 + sl1.j2 + tid * Q2;
+            float raw[KS][4];
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {
+              raw[ks][0] = __ldg(g0 + 8 * ks * Q2);
+              raw[ks][1] = __ldg(g1 + 8 * ks * Q2);
+              raw[ks][2] = __ldg(g0 + (8 * ks + 4) * Q2);
+              raw[ks][3] = __ldg(g1 + (8 * ks + 4) * Q2);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) af[ks][i].set(raw[ks][i]);
+          }
+#pragma unroll
+          for (int ks = 0; ks < (C2S ? KS : 0); ++ks) {
             if (TERMS == 3) {
               const float* pl0 = ph0 + (size_t)npairs_c2 * CS;
               const float* pl1 = ph1 + (size_t)npairs_c2 * CS;
@@ -499,7 +522,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks)
+          for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
             for (int term = first_term(TERMS); term < 3; ++term)
 #pragma unroll
@@ -1163,9 +1186,11 @@ inline int dbg_knob(const char* name) {
 template <int Q0, int Q1, int Q2, int R1, int R2>
 struct Shape {
   static constexpr int A = Q0 * Q1, D = Q0 * Q1 * Q2;
+  static constexpr bool kC2S = (R2 == 16);      // forward: core2 in shared memory
+  static constexpr bool kHasBwd = (R1 == 16 && R2 == 16);
 
   static size_t fwd_smem(int npairs, int terms) {
-    return sizeof(float) * ((size_t)npairs * kC2Stride * (terms == 3 ? 2 : 1) +
+    return sizeof(float) * ((kC2S ? (size_t)npairs * kC2Stride * (terms == 3 ? 2 : 1) : 0) +
                             (size_t)kWarps * fwd_rb(Q2) * D);
   }
   static size_t bwd_smem(int npairs) {
@@ -1194,7 +1219,7 @@ struct Shape {
                  cudaStream_t stream) {
     const int npairs = tt.num_tables * tt.p[2] * Q2;
     const size_t smem = fwd_smem(npairs, TERMS);
-    auto kern = mma_fwd_kernel<Q0, Q1, Q2, R2, TERMS>;
+    auto kern = mma_fwd_kernel<Q0, Q1, Q2, R2, TERMS, kC2S>;
     static size_t set_smem = 0;
     if (set_smem < smem) {
       TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1218,6 +1243,18 @@ struct Shape {
   static int bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl,
                  const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
                  float* const* state, cudaStream_t stream) {
+    if constexpr (!kHasBwd) {
+      set_error("mma_backward: no tensor-core backward for ranks %d, %d", R1, R2);
+      return TTG_ENOTSUP;
+    } else {
+      return bwd_impl<TERMS>(tt, nnz, total_rows, pl, d_output, dcore, optim, lr, eps, state, stream);
+    }
+  }
+
+  template <int TERMS>
+  static int bwd_impl(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl,
+                      const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
+                      float* const* state, cudaStream_t stream) {
     const int npairs = tt.num_tables * tt.p[2] * Q2;
     const int64_t e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
     const int64_t e1 = (int64_t)tt.num_tables * tt.p[1] * tt.cols[1];
@@ -1289,6 +1326,7 @@ struct Shape {
 struct MmaEntry {
   int q0, q1, q2, r1, r2;
   int a, d;
+  bool has_bwd;
   int (*table[2])(const TTDev&, const MmaPlan&, cudaStream_t);
   int (*fwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, float*, cudaStream_t);
   int (*bwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, const float*, float* const*,
@@ -1299,7 +1337,7 @@ struct MmaEntry {
 
 #define TTG_MMA_SHAPE(Q0, Q1, Q2, R1, R2)                                                       \
   {                                                                                             \
-    Q0, Q1, Q2, R1, R2, Q0 * Q1, Q0 * Q1 * Q2,                                                  \
+    Q0, Q1, Q2, R1, R2, Q0 * Q1, Q0 * Q1 * Q2, Shape<Q0, Q1, Q2, R1, R2>::kHasBwd,              \
         {Shape<Q0, Q1, Q2, R1, R2>::table<3>, Shape<Q0, Q1, Q2, R1, R2>::table<1>},             \
         {Shape<Q0, Q1, Q2, R1, R2>::fwd<3>, Shape<Q0, Q1, Q2, R1, R2>::fwd<1>},                 \
         {Shape<Q0, Q1, Q2, R1, R2>::bwd<3>, Shape<Q0, Q1, Q2, R1, R2>::bwd<1>},                 \
@@ -1309,6 +1347,7 @@ struct MmaEntry {
 const MmaEntry kMmaEntries[] = {
     TTG_MMA_SHAPE(4, 5, 5, 16, 16),   // ogbn-products, D = 100   (BASELINE configs 2, 3)
     TTG_MMA_SHAPE(4, 4, 8, 16, 16),   // cora / ogbn-arxiv, D = 128 (configs 1, 4)
+    TTG_MMA_SHAPE(4, 4, 8, 32, 32),   // ogbn-papers100M, D = 128 (config 5): table + forward only
 };
 
 const MmaEntry* find_mma(const TTDev& tt) {
@@ -1316,7 +1355,7 @@ const MmaEntry* find_mma(const TTDev& tt) {
   for (const MmaEntry& e : kMmaEntries) {
     if (e.q0 == tt.q[0] && e.q1 == tt.q[1] && e.q2 == tt.q[2] && e.r1 == tt.r[1] && e.r2 == tt.r[2]) {
       const int npairs = tt.num_tables * tt.p[2] * e.q2;
-      if (e.fwd_smem(npairs, 3) > kSmemMax || e.bwd_smem(npairs) > kSmemMax) return nullptr;
+      if (e.fwd_smem(npairs, 3) > kSmemMax || (e.has_bwd && e.bwd_smem(npairs) > kSmemMax)) return nullptr;
       return &e;
     }
   }
@@ -1325,7 +1364,11 @@ const MmaEntry* find_mma(const TTDev& tt) {
 
 }  // namespace
 
-bool mma_supported(const TTDev& tt) { return find_mma(tt) != nullptr; }
+bool mma_fwd_supported(const TTDev& tt) { return find_mma(tt) != nullptr; }
+bool mma_supported(const TTDev& tt) {
+  const MmaEntry* e = find_mma(tt);
+  return e != nullptr && e->has_bwd;
+}
 
 int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream) {
   const MmaEntry* e = find_mma(tt);

@@ -49,10 +49,10 @@ constexpr int kCoreSplit = 4;        // split of the reduction axis in the cores
 // sparse in groups (papers100M) tr0 is computed inside the row kernels, once per group run.
 inline bool use_group_table(const TTDev& tt, int64_t nnz) {
   const double groups = (double)tt.num_tables * tt.p[0] * tt.p[1];
-  if ((tt.q[0] * tt.q[1]) % 2 != 0 || tt.r[2] > 16) return false;
   // tensor-core kernels: the table costs one small GEMM per i1; worth it as soon as a group
   // has a row on average
-  if (mma_supported(tt)) return groups <= (double)nnz;
+  if (mma_fwd_supported(tt)) return groups <= (double)nnz;
+  if ((tt.q[0] * tt.q[1]) % 2 != 0 || tt.r[2] > 16) return false;
   const double cost_group = 2.0 * tt.q[0] * tt.r[1] * tt.q[1] * tt.r[2];
   const double cost_row = 2.0 * tt.q[0] * tt.q[1] * tt.r[2] * tt.q[2];
   return 2.0 * groups * cost_group <= (double)nnz * cost_row;
@@ -1459,6 +1459,9 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
 bool use_mma(const TTDev& tt, const SortedWs& w, int32_t flags) {
   return w.Ttab != nullptr && !(flags & TTG_FLAG_FFMA) && mma_supported(tt);
 }
+bool use_mma_fwd(const TTDev& tt, const SortedWs& w, int32_t flags) {
+  return w.Ttab != nullptr && !(flags & TTG_FLAG_FFMA) && mma_fwd_supported(tt);
+}
 
 MmaPlan mma_plan(const SortedWs& w) {
   MmaPlan pl;
@@ -1531,7 +1534,7 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
   const bool zero_only = (flags & TTG_FLAG_PLAN_VALID) != 0;
-  if (use_mma(tt, w, flags)) {
+  if (use_mma_fwd(tt, w, flags)) {
     if (zero_only)  // plan and table of this batch are still in the workspace
       rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, false, output, true, stream);
     else
@@ -1548,7 +1551,7 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
 // rows [first_row, first_row + num) of table 0 in order, no index arrays and no plan
 int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* output, void* ws,
                       size_t ws_bytes, int32_t flags, cudaStream_t stream) {
-  if (!find_entry(tt) || !mma_supported(tt) || tt.num_tables != 1) {
+  if (!find_entry(tt) || !mma_fwd_supported(tt) || tt.num_tables != 1) {
     set_error("rows_range: shape has no tensor-core kernels");
     return TTG_ENOTSUP;
   }

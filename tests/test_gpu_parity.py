@@ -515,3 +515,76 @@ def test_mma_invalid_indices_and_bags(ttg_lib):
     idx[bad[100:]] = int(np.prod(p)) + rng.integers(0, 1000, size=100)
     row = np.repeat(np.arange(lengths.size), lengths).astype(np.int64)
     _mma_case(te, "arxiv", idx, B=lengths.size, row=row)
+
+
+def test_rank32_tensor_core_forward_small_against_oracle(ttg_lib):
+    """ranks 32, 32 (papers100M recipe) on a table small enough that every group has rows: the
+    group table + tensor-core forward (core2 fragments from global memory) against the oracle,
+    then the FFMA backward on the plan the forward left behind."""
+    import tt_embeddings as te
+    p, q, r = [5, 6, 7], [4, 4, 8], [1, 32, 32, 1]
+    n_emb, D = 5 * 6 * 7, 128
+    cores_cpu = _random_cores(p, q, r, n_emb, 21)
+    cores = [c.to(DEV) for c in cores_cpu]
+    rng = np.random.default_rng(8)
+    nnz = 700
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = rng.permutation(nnz).astype(np.int64)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    cn = [c.numpy() for c in cores_cpu]
+    want = orc.tt_forward(p, q, r, cn, idx, row, nnz)
+    got = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+    assert rel_err(got.cpu().numpy(), want) < TOL
+    te.EXTRA_FLAGS = 16
+    try:
+        got_ffma = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+    finally:
+        te.EXTRA_FLAGS = 0
+    assert rel_err(got_ffma.cpu().numpy(), want) < TOL
+    dO = rng.random(size=(1, nnz, D)).astype(np.float32) * 0.1
+    wd = orc.tt_backward_dense(p, q, r, cn, idx, row, dO)
+    gd = te.tt_dense_backward(1000, D, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), cores)
+    for t in range(3):
+        assert rel_err(gd[t].cpu().numpy(), wd[t]) < TOL, "core %d" % t
+
+
+def test_full_size_papers_forward_properties(ttg_lib):
+    """BASELINE config 5 size (262,144 ids of 111,059,956, ids above 2^24 and duplicates included):
+    tensor-core forward == FFMA forward == generic kernels; permutation equivariance."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["papers"]
+    D = 128
+    cores = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 13)]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    nnz = 262144
+    idx = torch.randint(0, n_emb, (nnz,), generator=g)
+    idx[:1000] = idx[1000:2000]                       # duplicates
+    idx[2000:2200] = torch.arange(n_emb - 200, n_emb)  # the last rows of the table
+    idx = idx.to(DEV)
+    row = torch.arange(nnz, device=DEV)
+    tb = torch.zeros_like(idx)
+    out = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx, row, tb, cores)
+    outs = {}
+    for name, fl in (("ffma", 16), ("generic", _ttg.FLAG_FORCE_GENERIC)):
+        te.EXTRA_FLAGS = fl
+        try:
+            outs[name] = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx, row, tb, cores)
+        finally:
+            te.EXTRA_FLAGS = 0
+    for name, o in outs.items():
+        assert float((out - o).abs().max() / o.abs().max()) < TOL, name
+    perm = torch.randperm(nnz, generator=g).to(DEV)
+    out_p = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx[perm].contiguous(), row, tb, cores)
+    assert torch.equal(out_p[0], out[0][perm])
+    # the backward (FFMA kernels at these ranks) on the plan the tensor-core forward left behind
+    dO = torch.rand(1, nnz, D, generator=g).to(DEV) * 0.1
+    out = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx, row, tb, cores)
+    gs = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
+    te.EXTRA_FLAGS = _ttg.FLAG_FORCE_GENERIC
+    try:
+        gg = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
+    finally:
+        te.EXTRA_FLAGS = 0
+    for t in range(3):
+        assert float((gs[t] - gg[t]).abs().max() / gg[t].abs().max()) < 5e-5, "core %d" % t
