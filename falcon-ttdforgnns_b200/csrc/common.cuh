@@ -142,4 +142,9 @@ int mma_backward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPla
                  const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
                  float* const* state, bool tf32, cudaStream_t stream);
 
+// the two dense reductions over S (d_core1, d_core0) + optimizer, for an S any row kernel wrote
+// (d_core2 must be complete): ranks 32 pair the FFMA row kernel with these
+int mma_cores_finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, int32_t optim, float lr,
+                       float eps, float* const* state, bool tf32, cudaStream_t stream);
+
 }  // namespace ttg

@@ -31,8 +31,7 @@ namespace {
 constexpr int kThreads = 512;            // row kernels: one CTA per SM, 16 warps
 constexpr int kWarps = kThreads / 32;
 constexpr int kCoreThreads = 256;        // table kernel
-constexpr int kCoresThreads = 512;       // cores kernel: 16 warps, two 16-row chunks of S[:, i1] each
-constexpr int kCoresWarps = kCoresThreads / 32;
+constexpr int cores_warps(int c) { return c <= 80 ? 16 : 8; }   // cores kernel: staging must fit
 constexpr int kCoreWarps = kCoreThreads / 32;
 constexpr uint32_t kInvalid = 0xffffffffu;
 constexpr size_t kSmemMax = 227 * 1024;
@@ -923,10 +922,14 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int C>
 constexpr int cores_row_stride() { return C + 8; }   // 88 / 72 floats: k-side reads conflict-free
 
-template <int Q0, int Q1, int R1, int R2, int TERMS>
-__global__ void __launch_bounds__(kCoresThreads)
+template <int Q0, int Q1, int R1, int R2, int TERMS, int NW>
+__global__ void __launch_bounds__(NW * 32)
 mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __restrict__ cnt,
                      float* __restrict__ d0parts, float* __restrict__ dcore1, size_t e0) {
+  // blockIdx.y = which 16 of the R1 values of k1 this CTA produces (ranks 32: two CTAs per i1
+  // read the same column of S and each keep half of d_core1[i1] / P[i1] in registers)
+  constexpr int kCoresThreads = NW * 32;
+  constexpr int kCoresWarps = NW;
   constexpr int A = Q0 * Q1;
   constexpr int C = Q1 * R2;
   constexpr int NTL = C / 8;              // n-tiles of d_core1 / k-steps of P
@@ -934,7 +937,8 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   constexpr int IPC = 16 / Q0;            // i0 per chunk
   constexpr int CS = cores_row_stride<C>();
   constexpr int CH4 = C / 4;              // 16-byte pieces per row
-  static_assert(R1 == 16 && 16 % Q0 == 0 && C % 8 == 0 && NTL * 128 <= 2 * 16 * CS, "tile shapes");
+  static_assert(R1 % 16 == 0 && 16 % Q0 == 0 && C % 8 == 0 && NTL * 128 <= 2 * 16 * CS, "tile shapes");
+  const int kh = blockIdx.y * 16;           // first k1 of this CTA
   extern __shared__ __align__(16) float smem[];
   float* b1f = smem;                                       // [NTL][2][32][4]: core1[i1] fragments
   float* stage_all = smem + NTL * 2 * 32 * 4;              // [warps][2][16][CS]
@@ -977,7 +981,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
     const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
     for (int x = threadIdx.x; x < NTL * 2 * 32; x += kCoresThreads) {
       const int ks = x / 64, nt = (x / 32) & 1, l = x & 31;
-      const int k1 = (l >> 2) + 8 * nt, c = (l & 3) + 8 * ks;
+      const int k1 = kh + (l >> 2) + 8 * nt, c = (l & 3) + 8 * ks;
       const float v0 = __ldg(b1p + k1 * C + c), v1 = __ldg(b1p + k1 * C + c + 4);
       const float h0 = tf32_hi(v0), h1 = tf32_hi(v1);
       *reinterpret_cast<float4*>(b1f + x * 4) = make_float4(h0, v0 - h0, h1, v1 - h1);
@@ -1002,10 +1006,10 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       const int r0 = ch * 16 + tid + 8 * ks, r1 = r0 + 4;
-      a0f[ks][0].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + gid) : 0.f);
-      a0f[ks][1].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + gid + 8) : 0.f);
-      a0f[ks][2].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + gid) : 0.f);
-      a0f[ks][3].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + gid + 8) : 0.f);
+      a0f[ks][0].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + kh + gid) : 0.f);
+      a0f[ks][1].set(r0 < K ? __ldg(a_base + (size_t)r0 * R1 + kh + gid + 8) : 0.f);
+      a0f[ks][2].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + kh + gid) : 0.f);
+      a0f[ks][3].set(r1 < K ? __ldg(a_base + (size_t)r1 * R1 + kh + gid + 8) : 0.f);
     }
     // ---- P[row][k1] = sum_c S[row][c] B1[k1][c]: M = rows, N = k1 (2 tiles), K = c
     float accp[2][4];
@@ -1032,7 +1036,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
     }
     {
       // c0/c1: (row gid, k1 = 2 tid, 2 tid + 1 (+ 8 nt)), c2/c3: row gid + 8
-      float* dp = d0parts + (size_t)i1 * e0 + (size_t)tix * K * R1;
+      float* dp = d0parts + (size_t)i1 * e0 + (size_t)tix * K * R1 + kh;
       const int r0 = ch * 16 + gid, r1 = r0 + 8;
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt) {
@@ -1077,7 +1081,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
     for (int w = 0; w < kCoresWarps; ++w) v += red[(size_t)w * (NTL * 128) + x];
     const int l = x & 31, e = (x >> 5) & 3, nt = x >> 7;
     const int row = (l >> 2) + 8 * (e >> 1), col = 8 * nt + 2 * (l & 3) + (e & 1);
-    dst[row * C + col] = v;
+    dst[(kh + row) * C + col] = v;
   }
 }
 
@@ -1256,8 +1260,6 @@ struct Shape {
                       const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
                       float* const* state, cudaStream_t stream) {
     const int npairs = tt.num_tables * tt.p[2] * Q2;
-    const int64_t e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
-    const int64_t e1 = (int64_t)tt.num_tables * tt.p[1] * tt.cols[1];
     const int64_t e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
     const int32_t groups = tt.num_tables * tt.p[0] * tt.p[1];
     TTG_CUDA(cudaMemsetAsync(dcore[2], 0, sizeof(float) * (size_t)e2, stream));
@@ -1282,21 +1284,38 @@ struct Shape {
       TTG_LAUNCH_CHECK();
     }
     {
-      constexpr int C = Q1 * R2;
-      const int nb1 = tt.num_tables * tt.p[1];
-      const size_t smem = sizeof(float) * ((C / 8) * 2 * 32 * 4 +
-                                           (size_t)kCoresWarps * 2 * 16 * cores_row_stride<C>());
-      auto kern = mma_bwd_cores_kernel<Q0, Q1, R1, R2, TERMS>;
-      static bool attr = false;
-      if (!attr) {
-        TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-      }
-      prof_begin(K_BWD_CORES, stream);
-      kern<<<nb1, kCoresThreads, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore[1], (size_t)e0);
-      prof_end(K_BWD_CORES, stream);
-      TTG_LAUNCH_CHECK();
+      int rc = cores<TERMS>(tt, pl, dcore[1], stream);
+      if (rc != TTG_OK) return rc;
     }
+    return finalize(tt, pl, dcore, optim, lr, eps, state, stream);
+  }
+
+  // d_core1 and the per-i1 partial products of d_core0 from S (any row kernel's S: same layout)
+  template <int TERMS>
+  static int cores(const TTDev& tt, const MmaPlan& pl, float* dcore1, cudaStream_t stream) {
+    constexpr int C = Q1 * R2;
+    constexpr int NW = cores_warps(C);
+    const int64_t e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
+    const int nb1 = tt.num_tables * tt.p[1];
+    const size_t smem = sizeof(float) * ((C / 8) * 2 * 32 * 4 + (size_t)NW * 2 * 16 * cores_row_stride<C>());
+    auto kern = mma_bwd_cores_kernel<Q0, Q1, R1, R2, TERMS, NW>;
+    static bool attr = false;
+    if (!attr) {
+      TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    prof_begin(K_BWD_CORES, stream);
+    kern<<<dim3(nb1, R1 / 16), NW * 32, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore1, (size_t)e0);
+    prof_end(K_BWD_CORES, stream);
+    TTG_LAUNCH_CHECK();
+    return TTG_OK;
+  }
+
+  static int finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, int32_t optim, float lr,
+                      float eps, float* const* state, cudaStream_t stream) {
+    const int64_t e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
+    const int64_t e1 = (int64_t)tt.num_tables * tt.p[1] * tt.cols[1];
+    const int64_t e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
     MmaFinalArgs a;
     memset(&a, 0, sizeof(a));
     a.e0 = e0;
@@ -1331,6 +1350,9 @@ struct MmaEntry {
   int (*fwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, float*, cudaStream_t);
   int (*bwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, const float*, float* const*,
                 int32_t, float, float, float* const*, cudaStream_t);
+  int (*cores[2])(const TTDev&, const MmaPlan&, float*, cudaStream_t);
+  int (*finalize)(const TTDev&, const MmaPlan&, float* const*, int32_t, float, float, float* const*,
+                  cudaStream_t);
   size_t (*fwd_smem)(int, int);
   size_t (*bwd_smem)(int);
 };
@@ -1341,6 +1363,8 @@ struct MmaEntry {
         {Shape<Q0, Q1, Q2, R1, R2>::table<3>, Shape<Q0, Q1, Q2, R1, R2>::table<1>},             \
         {Shape<Q0, Q1, Q2, R1, R2>::fwd<3>, Shape<Q0, Q1, Q2, R1, R2>::fwd<1>},                 \
         {Shape<Q0, Q1, Q2, R1, R2>::bwd<3>, Shape<Q0, Q1, Q2, R1, R2>::bwd<1>},                 \
+        {Shape<Q0, Q1, Q2, R1, R2>::cores<3>, Shape<Q0, Q1, Q2, R1, R2>::cores<1>},             \
+        Shape<Q0, Q1, Q2, R1, R2>::finalize,                                                    \
         Shape<Q0, Q1, Q2, R1, R2>::fwd_smem, Shape<Q0, Q1, Q2, R1, R2>::bwd_smem               \
   }
 
@@ -1381,6 +1405,15 @@ int mma_forward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan
   const MmaEntry* e = find_mma(tt);
   if (!e) return TTG_ENOTSUP;
   return e->fwd[tf32 ? 1 : 0](tt, nnz, total_rows, pl, output, stream);
+}
+
+int mma_cores_finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, int32_t optim, float lr,
+                       float eps, float* const* state, bool tf32, cudaStream_t stream) {
+  const MmaEntry* e = find_mma(tt);
+  if (!e) return TTG_ENOTSUP;
+  int rc = e->cores[tf32 ? 1 : 0](tt, pl, dcore[1], stream);
+  if (rc != TTG_OK) return rc;
+  return e->finalize(tt, pl, dcore, optim, lr, eps, state, stream);
 }
 
 int mma_backward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl,

@@ -1177,6 +1177,8 @@ struct BwdOpt {
   float lr, eps;
   float* const* state;   // host array of device pointers or nullptr
   bool table_valid;      // Ttab in the workspace matches the current cores
+  bool mma_cores;        // reductions over S + update on the tensor-core kernels (ranks 32)
+  bool tf32;
 };
 
 typedef int (*FwdLaunch)(const TTDev&, int64_t, uint32_t, const SortedWs&, float*, cudaStream_t);
@@ -1331,6 +1333,16 @@ int launch_bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
                                                                    d_output, dcore[2], stream);
   }
   if (rc != TTG_OK) return rc;
+  if (opt.mma_cores) {
+    // d_core2 went to global memory directly (no per-CTA partials); the dense reductions over S
+    // and the update run on the tensor-core kernels
+    MmaPlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.cnt = w.cnt;
+    pl.S = w.S;
+    pl.d0parts = w.d0parts;
+    return mma_cores_finalize(tt, pl, dcore, opt.optim, opt.lr, opt.eps, opt.state, opt.tf32, stream);
+  }
   const int nblocks = tt.num_tables * (tt.p[0] + tt.p[1]);
   prof_begin(K_BWD_CORES, stream);
   {
@@ -1640,6 +1652,9 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
   opt.eps = eps;
   opt.state = state;
   opt.table_valid = plan_valid;  // the forward that built the plan also built the table
+  // ranks 32: FFMA row kernel, then the tensor-core reductions over S
+  opt.mma_cores = !(flags & TTG_FLAG_FFMA) && !w.smem_acc && mma_fwd_supported(tt) && !mma_supported(tt);
+  opt.tf32 = (flags & TTG_FLAG_TF32) != 0;
   return e->bwd(tt, nnz, total_rows, w, d_output, dcore, opt, stream);
 }
 
