@@ -5,6 +5,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ttg {
@@ -182,6 +184,16 @@ extern "C" int ttg_profile_read(int32_t id, double* total_ms, int64_t* count) {
   *count = g_nrec[id];
   return TTG_OK;
 }
+
+namespace ttg {
+int pdl_level() {
+  static const int level = [] {
+    const char* v = getenv("TTG_PDL_LEVEL");
+    return v ? atoi(v) : 1;
+  }();
+  return level;
+}
+}  // namespace ttg
 
 extern "C" const char* ttg_profile_name(int32_t id) {
   return (id >= 0 && id < K_COUNT) ? kKernelNames[id] : nullptr;

@@ -247,6 +247,7 @@ mma_table_kernel(TTDev tt, float* __restrict__ Ttab, int mtiles_per_cta) {
   const int tix = blockIdx.x / p1, i1 = blockIdx.x % p1;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
+  pdl_trigger();
   {
     const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
 #pragma unroll   // a handful of iterations: all loads in flight before the first split
@@ -261,6 +262,10 @@ mma_table_kernel(TTDev tt, float* __restrict__ Ttab, int mtiles_per_cta) {
     }
   }
   __syncthreads();
+  // the table depends on nothing but the cores; the wait only keeps the chain of dependent
+  // launches transitive (the row kernel behind us must see the plan kernels in front of us) and
+  // the previous reader of Ttab out of the way
+  pdl_wait();
   const int M = p0 * Q0;
   const int mtiles = (M + 15) / 16;
   const int mt_lo = blockIdx.y * mtiles_per_cta;
@@ -364,7 +369,10 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
+  pdl_trigger();   // the next kernel's CTAs may take over SMs as ours leave
   if (C2S) {
+    // staged before pdl_wait(): nobody writes core2 between the update of the previous step and
+    // this kernel, so the copy overlaps the tail of the plan kernels
     stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
       const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
       const int k2 = rem / Q2, j2 = rem % Q2;
@@ -379,6 +387,7 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
     });
     __syncthreads();
   }
+  pdl_wait();      // plan and group table are complete
 
   const uint32_t p2 = tt.p[2];
   const uint32_t num_rows32 = (uint32_t)tt.num_rows;
@@ -602,6 +611,8 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
 
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int gid = lane >> 2, tid = lane & 3;
+  pdl_trigger();
+  // everything up to pdl_wait() touches shared memory and core2 only (see mma_fwd_kernel)
   stage_core2<kThreads>(tt.core[2], npairs_c2 * 16, [&](int e, float v) {
     const int i2row = e / (16 * Q2), rem = e % (16 * Q2);
     const int k2 = rem / Q2, j2 = rem % Q2;
@@ -619,6 +630,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_proxy_async();   // the zero-fill above is followed by bulk-copy writes to the ring
   __syncthreads();
+  pdl_wait();            // d_output, the plan, the table and the zeroed d_core2 are complete
 
   float* ring = ring_all + (size_t)wib * 2 * RB * D;
   uint64_t* bar = bars + wib * 2;
@@ -959,7 +971,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
       const int c2 = wib + kCoresWarps * (it + lane / IPC);
       const int i0m = c2 * IPC + lane % IPC;
       on_l = 0;
-      if (c2 < nchunks && i0m < p0) on_l = __ldg(cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
+      if (c2 < nchunks && i0m < p0) on_l = *((const volatile int32_t*)cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
     }
     if (ch < nchunks) {
       float* dst = stage + buf * 16 * CS;
@@ -974,9 +986,9 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
     }
     cp_async_commit();
   };
-  issue(0, 0);
-
+  pdl_trigger();
   // core1[i1] as the N-side operand of P: b0 = B1[k1 = gid + 8 nt][c = tid + 8 ks], b1: c + 4
+  // (before pdl_wait(): the cores are not written until the finalize kernel that follows)
   {
     const float* b1p = tt.core[1] + ((size_t)tix * p1 + i1) * (R1 * C);
     for (int x = threadIdx.x; x < NTL * 2 * 32; x += kCoresThreads) {
@@ -987,6 +999,8 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
       *reinterpret_cast<float4*>(b1f + x * 4) = make_float4(h0, v0 - h0, h1, v1 - h1);
     }
   }
+  pdl_wait();      // S and the group counts are complete
+  issue(0, 0);
   __syncthreads();
 
   float acc1[NTL][4];
@@ -1085,6 +1099,13 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
   }
 }
 
+__global__ void __launch_bounds__(256) mma_zero_kernel(float* __restrict__ p, int64_t n4) {
+  pdl_trigger();
+  pdl_wait();      // the previous reader of this buffer (last step's update) is done
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n4) reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // finalize: d_core0 = sum over i1 of the partial products (fixed order), then the optional
 // optimizer step on all three cores.  SGD: core -= lr g;  Adagrad: state += g g,
 // core -= lr g / (sqrt(state) + eps)  (FBTT/tt_embeddings_cuda.cu:381-419, applied to every row
@@ -1130,6 +1151,7 @@ constexpr int kFinPer = 12;      // partial copies one thread sums (all loads in
 
 __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
   __shared__ float4 sm[kFinSlices][kFinCols];
+  pdl_wait();
   if ((int)blockIdx.x < a.nb0) {
     // 16 float4 columns x 16 slices of the i1 axis; a slice is summed in order, then the slices
     const int col = threadIdx.x % kFinCols, sl = threadIdx.x / kFinCols;
@@ -1203,7 +1225,7 @@ struct Shape {
   }
 
   template <int TERMS>
-  static int table(const TTDev& tt, const MmaPlan& pl, cudaStream_t stream) {
+  static int table(const TTDev& tt, const MmaPlan& pl, bool chained, cudaStream_t stream) {
     const int nb = tt.num_tables * tt.p[1];
     const int mtiles = (tt.p[0] * Q0 + 15) / 16;
     int split = (int)ceil_div(2 * kNumSMs, nb);
@@ -1212,7 +1234,13 @@ struct Shape {
     if (per < kCoreWarps) per = kCoreWarps;
     split = (int)ceil_div(mtiles, per);
     prof_begin(K_TABLE, stream);
-    mma_table_kernel<Q0, Q1, R1, R2, TERMS><<<dim3(nb, split), kCoreThreads, 0, stream>>>(tt, pl.Ttab, per);
+    // chained: the plan kernels of this call precede us on the stream, so nothing that ran before
+    // them can still be writing the cores our prologue reads; otherwise serialise as usual
+    if (chained)
+      TTG_CUDA(launch_pdl<2>(mma_table_kernel<Q0, Q1, R1, R2, TERMS>, dim3(nb, split), dim3(kCoreThreads), 0,
+                          stream, tt, pl.Ttab, per));
+    else
+      mma_table_kernel<Q0, Q1, R1, R2, TERMS><<<dim3(nb, split), kCoreThreads, 0, stream>>>(tt, pl.Ttab, per);
     prof_end(K_TABLE, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
@@ -1235,9 +1263,9 @@ struct Shape {
     int64_t rpw = ceil_div(nnz, grid * kWarps);
     rpw = ceil_div(rpw, RB) * RB;
     prof_begin(K_FWD, stream);
-    kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, pl.skeys, pl.srow, pl.Ttab,
-                                                     output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
-                                                     pl.first_key);
+    TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, tt, nnz, total_rows,
+                        pl.skeys, pl.srow, pl.Ttab, output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
+                        pl.first_key));
     prof_end(K_FWD, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
@@ -1262,7 +1290,11 @@ struct Shape {
     const int npairs = tt.num_tables * tt.p[2] * Q2;
     const int64_t e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
     const int32_t groups = tt.num_tables * tt.p[0] * tt.p[1];
-    TTG_CUDA(cudaMemsetAsync(dcore[2], 0, sizeof(float) * (size_t)e2, stream));
+    // d_core2 = 0 as a kernel rather than a memset node, so that the row kernel's prologue can run
+    // beside whatever precedes it
+    TTG_CUDA(launch_pdl(mma_zero_kernel, dim3((unsigned)ceil_div(e2 / 4, 256)), dim3(256), 0, stream,
+                        dcore[2], e2 / 4));
+    count_launch();
     {
       const size_t smem = bwd_smem(npairs);
       auto kern = mma_bwd_rows_kernel<Q0, Q1, Q2, R2, TERMS>;
@@ -1276,10 +1308,9 @@ struct Shape {
       int64_t grid = ceil_div(ceil_div(nnz, chunk), kWarps);
       if (grid > kNumSMs) grid = kNumSMs;
       prof_begin(K_BWD_ROWS, stream);
-      kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, groups, pl.skeys, pl.srow,
-                                                       pl.cnt, pl.base, d_output, pl.Ttab, pl.S,
-                                                       dcore[2], npairs, (int)chunk,
-                                                       dbg_knob("TTG_DBG_BWD"));
+      TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, tt, nnz, total_rows,
+                          groups, pl.skeys, pl.srow, pl.cnt, pl.base, d_output, pl.Ttab, pl.S, dcore[2],
+                          npairs, (int)chunk, dbg_knob("TTG_DBG_BWD")));
       prof_end(K_BWD_ROWS, stream);
       TTG_LAUNCH_CHECK();
     }
@@ -1305,7 +1336,8 @@ struct Shape {
       attr = true;
     }
     prof_begin(K_BWD_CORES, stream);
-    kern<<<dim3(nb1, R1 / 16), NW * 32, smem, stream>>>(tt, pl.S, pl.cnt, pl.d0parts, dcore1, (size_t)e0);
+    TTG_CUDA(launch_pdl(kern, dim3(nb1, R1 / 16), dim3(NW * 32), smem, stream, tt, pl.S, pl.cnt, pl.d0parts,
+                        dcore1, (size_t)e0));
     prof_end(K_BWD_CORES, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
@@ -1335,7 +1367,7 @@ struct Shape {
     // dense mode only needs the d_core0 part
     const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(e1 + e2, 1024);
     prof_begin(K_REDUCE, stream);
-    mma_finalize_kernel<<<a.nb0 + nb12, 256, 0, stream>>>(a);
+    TTG_CUDA(launch_pdl(mma_finalize_kernel, dim3(a.nb0 + nb12), dim3(256), 0, stream, a));
     prof_end(K_REDUCE, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
@@ -1346,7 +1378,7 @@ struct MmaEntry {
   int q0, q1, q2, r1, r2;
   int a, d;
   bool has_bwd;
-  int (*table[2])(const TTDev&, const MmaPlan&, cudaStream_t);
+  int (*table[2])(const TTDev&, const MmaPlan&, bool, cudaStream_t);
   int (*fwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, float*, cudaStream_t);
   int (*bwd[2])(const TTDev&, int64_t, uint32_t, const MmaPlan&, const float*, float* const*,
                 int32_t, float, float, float* const*, cudaStream_t);
@@ -1394,10 +1426,10 @@ bool mma_supported(const TTDev& tt) {
   return e != nullptr && e->has_bwd;
 }
 
-int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, cudaStream_t stream) {
+int mma_table(const TTDev& tt, const MmaPlan& pl, bool tf32, bool chained, cudaStream_t stream) {
   const MmaEntry* e = find_mma(tt);
   if (!e) return TTG_ENOTSUP;
-  return e->table[tf32 ? 1 : 0](tt, pl, stream);
+  return e->table[tf32 ? 1 : 0](tt, pl, chained, stream);
 }
 
 int mma_forward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl, float* output,

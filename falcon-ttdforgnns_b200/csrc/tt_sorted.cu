@@ -151,6 +151,7 @@ plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32
             const int64_t* __restrict__ tableidx, uint32_t* __restrict__ keys,
             int32_t* __restrict__ vals, int32_t* __restrict__ ranks, int32_t* __restrict__ cnt,
             int32_t* __restrict__ rowcount, uint32_t p2, int32_t num_groups) {
+  pdl_trigger();
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
   int64_t idx[kPlanItems], t[kPlanItems], row[kPlanItems];
 #pragma unroll
@@ -181,6 +182,8 @@ __global__ void __launch_bounds__(1024)
 bucket_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ base) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t prefix_s;
+  pdl_trigger();
+  pdl_wait();      // the counters are complete
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int4* c4 = reinterpret_cast<const int4*>(cnt);
   int32_t acc = 0;
@@ -242,6 +245,8 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
                       const int32_t* __restrict__ rowcount, uint32_t* __restrict__ skeys,
                       int32_t* __restrict__ srow, float* __restrict__ output, int64_t out_rows,
                       int32_t D4) {
+  pdl_trigger();
+  pdl_wait();      // keys, ranks and the scanned bucket starts are complete
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
   if (ranks != nullptr) {
     uint32_t key[kPlanItems];
@@ -1447,7 +1452,8 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
   prof_end(K_PLAN, stream);
   TTG_LAUNCH_CHECK();
   prof_begin(K_SORT, stream);
-  bucket_scan_kernel<<<(unsigned)ceil_div(groups + 1, 4096), 1024, 0, stream>>>(w.cnt, w.base);
+  TTG_CUDA(launch_pdl<2>(bucket_scan_kernel, dim3((unsigned)ceil_div(groups + 1, 4096)), dim3(1024), 0, stream,
+                      w.cnt, w.base));
   TTG_LAUNCH_CHECK();
   if (deterministic) {
     int end_bit = 1;
@@ -1458,10 +1464,9 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                                              end_bit, stream));
     count_launch(3);
   }
-  bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(
-      nnz, total_rows, (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in,
-      deterministic ? nullptr : w.ranks, w.base, rowcount, w.skeys, w.srow, output, out_rows,
-      tt.D / 4);
+  TTG_CUDA(launch_pdl<2>(bucket_scatter_kernel, dim3(nblk), dim3(256), 0, stream, nnz, total_rows,
+                      (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in, deterministic ? nullptr : w.ranks,
+                      w.base, rowcount, w.skeys, w.srow, output, out_rows, tt.D / 4));
   TTG_LAUNCH_CHECK();
   prof_end(K_SORT, stream);
   return TTG_OK;
@@ -1488,16 +1493,19 @@ MmaPlan mma_plan(const SortedWs& w) {
   return pl;
 }
 
-// group table, then the plan, on the caller's stream.  (Running the table on a side stream beside
-// the plan -- the two are independent -- was measured: 1.6 us less device time per step against
-// four more driver calls per forward on a host-bound end-to-end path; not kept.)
+// the plan, then the group table, on the caller's stream: a chain of programmatic dependent
+// launches (plan -> scan -> scatter -> table -> row kernel) in which every kernel's operand staging
+// overlaps the tail of the one before; the table comes last so that the row kernel's CTAs stage
+// core2 while the (small) table CTAs still compute.  (Running the table on a side stream beside the
+// plan was measured earlier: 1.6 us less device time per step against four more driver calls per
+// forward on a host-bound end-to-end path; not kept.)
 int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                     const int64_t* rowidx, const int64_t* tableidx, const SortedWs& w,
                     int32_t flags, float* output, cudaStream_t stream) {
-  int rc = mma_table(tt, mma_plan(w), (flags & TTG_FLAG_TF32) != 0, stream);
+  int rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
+                      output, false, stream);
   if (rc != TTG_OK) return rc;
-  return build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
-                    output, false, stream);
+  return mma_table(tt, mma_plan(w), (flags & TTG_FLAG_TF32) != 0, true, stream);
 }
 
 int check_common(const TTDev& tt, int64_t B, int64_t nnz, const char* who) {
@@ -1586,7 +1594,7 @@ int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* ou
   }
   MmaPlan pl = mma_plan(w);
   const bool tf32 = (flags & TTG_FLAG_TF32) != 0;
-  int rc = mma_table(tt, pl, tf32, stream);
+  int rc = mma_table(tt, pl, tf32, false, stream);
   if (rc != TTG_OK) return rc;
   pl.skeys = nullptr;
   pl.srow = nullptr;

@@ -588,3 +588,41 @@ def test_full_size_papers_forward_properties(ttg_lib):
         te.EXTRA_FLAGS = 0
     for t in range(3):
         assert float((gs[t] - gg[t]).abs().max() / gg[t].abs().max()) < 5e-5, "core %d" % t
+
+
+def test_back_to_back_steps_with_a_deep_launch_queue(ttg_lib):
+    """The row / cores / finalize kernels start early (programmatic dependent launch) and stage
+    their operands before the kernel in front of them has finished.  Thirty forward + fused-SGD
+    steps are queued behind a busy GPU without any host synchronisation -- every kernel finds its
+    predecessor still running -- and must leave the cores the generic kernels leave."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["products"]
+    D, nnz, steps = 100, 30000, 30
+    g = torch.Generator(device="cpu").manual_seed(5)
+    batches = [torch.randint(0, n_emb, (nnz,), generator=g).to(DEV) for _ in range(4)]
+    dOs = [(torch.rand(1, nnz, D, generator=g) * 0.1).to(DEV) for _ in range(4)]
+    row = torch.arange(nnz, device=DEV)
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    start = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 14)]
+    results = {}
+    for name, fl in (("generic", _ttg.FLAG_FORCE_GENERIC), ("mma", 0), ("backward_only", 0)):
+        cores = [c.clone() for c in start]
+        te.EXTRA_FLAGS = fl
+        try:
+            torch.cuda.synchronize()
+            torch.cuda._sleep(40_000_000)        # about 20 ms: the queue fills behind it
+            for s in range(steps):
+                k = s % 4
+                if name != "backward_only":
+                    te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, batches[k], row, tb, cores)
+                te.tt_sgd_backward(1000, D, 2e-4, p, q, r, None, nnz, batches[k], row, tb, dOs[k], cores)
+            torch.cuda.synchronize()
+        finally:
+            te.EXTRA_FLAGS = 0
+        results[name] = cores
+    for name in ("mma", "backward_only"):
+        for t in range(3):
+            upd = (results["generic"][t] - start[t]).abs().max()
+            err = (results[name][t] - results["generic"][t]).abs().max()
+            assert float(err / upd) < 1e-4, "%s core %d: %.3g of the update" % (name, t, float(err / upd))

@@ -101,9 +101,19 @@ def test_fused_sgd_matches_reference_on_the_rows_it_updates(ttg_lib, ref):
     te.tt_sgd_backward(1000, 100, 0.1, p, q, r, L, nnz, idx, row, tb, dO, c_our)
     cols = [r[t] * q[t] * r[t + 1] for t in range(3)]
     lim = orc.reference_sgd_rows_updated(p, cols)
+    import _ttg
+    c_gen = [c.clone() for c in before]
+    te.EXTRA_FLAGS = _ttg.FLAG_FORCE_GENERIC
+    try:
+        te.tt_sgd_backward(1000, 100, 0.1, p, q, r, L, nnz, idx, row, tb, dO, c_gen)
+    finally:
+        te.EXTRA_FLAGS = 0
     for t in range(3):
         n = lim[t]
-        assert _rel(c_our[t][:, :n], c_ref[t][:, :n]) < TOL
+        assert _rel(c_our[t][:, :n], c_ref[t][:, :n]) < TOL, (
+            "core %d: ours vs reference %.3g, ours vs our generic kernels %.3g, reference vs generic %.3g"
+            % (t, _rel(c_our[t][:, :n], c_ref[t][:, :n]), _rel(c_our[t], c_gen[t]),
+               _rel(c_ref[t][:, :n], c_gen[t][:, :n])))
         if n < p[t]:      # the tail the reference skips: untouched there, updated here
             assert torch.equal(c_ref[t][:, n:], before[t][:, n:])
             assert not torch.equal(c_our[t][:, n:], before[t][:, n:])
