@@ -1324,6 +1324,17 @@ int launch_bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
       rc = launch_table<Q0, Q1, Q2, R1, R2>(tt, w, stream);
       if (rc != TTG_OK) return rc;
     }
+  } else if (opt.mma_cores && w.Ttab != nullptr) {
+    // ranks 32: the tensor-core table kernel writes the same [group][q0 q1][r2] layout; reading
+    // tr0 from it replaces 128 loads of core1 and 512 FFMAs per lane and group run
+    table = true;
+    if (!opt.table_valid) {
+      MmaPlan pl;
+      memset(&pl, 0, sizeof(pl));
+      pl.Ttab = w.Ttab;
+      rc = mma_table(tt, pl, opt.tf32, true, stream);
+      if (rc != TTG_OK) return rc;
+    }
   }
   if (w.smem_acc) {
     rc = table ? launch_bwd_rows<Q0, Q1, Q2, R1, R2, true, true>(tt, nnz, total_rows, w, d_output,
