@@ -81,6 +81,52 @@ class _SpMM(torch.autograd.Function):
         return None, None, dx, None, None, None
 
 
+class _SpMMWithSelf(torch.autograd.Function):
+    """(aggregate(block, x), x[:num_dst]) as ONE autograd node.  A SAGE layer reads its input
+    twice (gnn_model.py:211-214: h_dst = h[:num_dst] for fc_self, all of h for the neighbour mean);
+    as two nodes autograd materialises the slice's gradient as a zero-filled [num_src, F] tensor,
+    copies into it and adds it to the aggregation's gradient -- five passes over num_src * F floats
+    (0.5 ms per step at products shape).  Here the slice's gradient is added in place to the first
+    num_dst rows of the aggregation's gradient."""
+
+    @staticmethod
+    def forward(ctx, indptr, indices, x, num_dst, mean):
+        _ttg.require_cuda(indptr, "indptr", torch.int64)
+        _ttg.require_cuda(indices, "indices", torch.int32)
+        x = _ttg.require_cuda(x.contiguous(), "x", torch.float32)
+        dev = x.device
+        F = x.size(1)
+        with _ttg.on_device(dev):
+            out = torch.empty((num_dst, F), dtype=torch.float32, device=dev)
+            rc = _ttg.lib().ttg_spmm_csr_fwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices), None,
+                                             1 if mean else 0, _ttg.ptr(x), _ttg.ptr(out),
+                                             _ttg.stream_of(dev))
+            _ttg.check(rc, "spmm_csr_fwd")
+        ctx.save_for_backward(indptr, indices)
+        ctx.cfg = (x.size(0), num_dst, F, mean)
+        return out, x[:num_dst].clone()
+
+    @staticmethod
+    def backward(ctx, dout, dself):
+        indptr, indices = ctx.saved_tensors
+        num_src, num_dst, F, mean = ctx.cfg
+        dev = dout.device
+        with _ttg.on_device(dev):
+            dout = dout.to(torch.float32).contiguous()
+            dx = torch.zeros((num_src, F), dtype=torch.float32, device=dev)
+            rc = _ttg.lib().ttg_spmm_csr_bwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices), None,
+                                             1 if mean else 0, _ttg.ptr(dout), _ttg.ptr(dx),
+                                             _ttg.stream_of(dev))
+            _ttg.check(rc, "spmm_csr_bwd")
+            dx[:num_dst].add_(dself)
+        return None, None, dx, None, None
+
+
+def aggregate_with_self(block: Block, x: torch.Tensor, mean: bool) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(neighbour aggregate, the destination nodes' own rows): see _SpMMWithSelf."""
+    return _SpMMWithSelf.apply(block.indptr, block.indices, x, block.num_dst, mean)
+
+
 def aggregate(block: Block, x: torch.Tensor, mean: bool,
               edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[v] = (1/deg(v) if mean) * sum_{u in N_in(v)} w_uv * x[u]; rows without in-edges are 0."""
@@ -107,11 +153,22 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=gain)
 
     def forward(self, block: Block, feat: Tuple[torch.Tensor, torch.Tensor]) -> torch.Tensor:
-        h_src, h_dst = feat if isinstance(feat, tuple) else (feat, feat[:block.num_dst])
-        if self.in_feats > self.out_feats:
-            h_neigh = aggregate(block, self.fc_neigh(h_src), mean=True)
+        h_src, h_dst = feat if isinstance(feat, tuple) else (feat, None)
+        # h_dst is the first num_dst rows of h_src (how the reference calls its layers,
+        # gnn_model.py:211-214): both reads of h_src then go through one autograd node
+        head = h_dst is None or (h_dst.data_ptr() == h_src.data_ptr() and h_dst.dim() == 2
+                                 and h_dst.size(0) == block.num_dst and h_dst.size(1) == h_src.size(1)
+                                 and h_dst.stride() == h_src.stride())
+        if head and self.in_feats <= self.out_feats and h_src.requires_grad:
+            agg, h_dst = aggregate_with_self(block, h_src, mean=True)
+            h_neigh = self.fc_neigh(agg)
         else:
-            h_neigh = self.fc_neigh(aggregate(block, h_src, mean=True))
+            if h_dst is None:
+                h_dst = h_src[:block.num_dst]
+            if self.in_feats > self.out_feats:
+                h_neigh = aggregate(block, self.fc_neigh(h_src), mean=True)
+            else:
+                h_neigh = self.fc_neigh(aggregate(block, h_src, mean=True))
         out = self.fc_self(h_dst) + h_neigh
         if self.bias is not None:
             out = out + self.bias

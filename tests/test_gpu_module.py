@@ -149,11 +149,13 @@ def test_sageconv_and_graphconv_against_dense_torch(ttg_lib):
             A[v, indices[e]] += 1
     A = A.to(DEV)
     deg = A.sum(1).clamp(min=1)
-    for fin, fout in [(100, 256), (256, 47)]:          # aggregate-then-linear / linear-then-aggregate
+    # aggregate-then-linear / linear-then-aggregate; tuple input as the reference passes it (one
+    # fused autograd node for both reads when h_dst is the head of h), a separate h_dst, plain h
+    for fin, fout, how in [(100, 256, "head"), (256, 47, "head"), (100, 256, "plain"), (100, 256, "copy")]:
         torch.manual_seed(1)
         conv = gnn_ops.SAGEConv(fin, fout, "mean").to(DEV)
         h = torch.randn(num_src, fin, device=DEV, requires_grad=True)
-        out = conv(blk, (h, h[:num_dst]))
+        out = conv(blk, {"head": (h, h[:num_dst]), "plain": h, "copy": (h, h[:num_dst] * 1.0)}[how])
         h64 = h.detach().double().requires_grad_(True)
         neigh = (A @ h64) / deg[:, None]
         ref = (h64[:num_dst] @ conv.fc_self.weight.double().t()
