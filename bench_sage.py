@@ -97,9 +97,10 @@ def main():
             dist.barrier()
         e0.record()
         loss = None
-        for s in range(nsteps):
-            seeds = mine[(s * args.batch) % max(mine.numel(), 1):][:args.batch]
-            inp, outp, blocks = smp.sample_blocks(graph, seeds, seed=epoch * 100003 + s * world + rank)
+        batches = sampler.prefetched_minibatches(
+            graph, smp, lambda s: mine[(s * args.batch) % max(mine.numel(), 1):][:args.batch],
+            lambda s: epoch * 100003 + s * world + rank, nsteps)
+        for inp, outp, blocks in batches:      # sampled one step ahead on a side stream
             loss = trainer.step(blocks, inp, labels[outp])
             stats["input_nodes"] += inp.numel()
             stats["edges0"] += blocks[0].indices.numel()

@@ -83,3 +83,35 @@ class NeighborSampler:
             blocks.insert(0, blk)
             dst = src
         return dst, output_nodes, blocks
+
+
+def prefetched_minibatches(g: CSRGraph, sampler: NeighborSampler, seeds_of_step, seed_of_step,
+                           num_steps: int):
+    """Yields (input_nodes, output_nodes, blocks) for steps 0 .. num_steps - 1, each sampled on a
+    side stream while the consumer's previous step is still running on the current stream -- what
+    DGL's DataLoader does for GPU sampling (use_alternate_streams; sage_dgl_partition.py:141-154
+    takes the default).  The two size read-backs per layer then wait for the sampler's own kernels
+    only, not for the training step queued in front of them, so the host keeps the training stream
+    fed.  `seeds_of_step(s)` -> int64 seed nodes on the device, `seed_of_step(s)` -> draw seed."""
+    if num_steps <= 0:
+        return
+    main = torch.cuda.current_stream(g.indptr.device)
+    side = torch.cuda.Stream(g.indptr.device)
+    side.wait_stream(main)            # the graph and the seed tensors are ready
+
+    def produce(s):
+        with torch.cuda.stream(side):
+            batch = sampler.sample_blocks(g, seeds_of_step(s), seed=seed_of_step(s))
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return batch, ev
+
+    nxt = produce(0)
+    for s in range(num_steps):
+        (inp, outp, blocks), ev = nxt
+        main.wait_event(ev)
+        for t in [inp, outp] + [x for b in blocks for x in (b.indptr, b.indices)]:
+            t.record_stream(main)     # allocated under the side stream, consumed on this one
+        yield inp, outp, blocks       # the consumer enqueues its step ...
+        if s + 1 < num_steps:
+            nxt = produce(s + 1)      # ... and only then does the host wait for the next sample

@@ -92,3 +92,31 @@ def test_sampled_blocks_drive_sageconv(ttg_lib):
             want[v] = xc[ix[ip[v]:ip[v + 1]]].mean(0)
     got = gnn_ops.aggregate(b, x, mean=True).cpu().numpy()
     assert np.abs(got - want).max() < 1e-5
+
+
+def test_prefetched_minibatches_equal_direct_sampling(ttg_lib):
+    """Sampling one step ahead on a side stream yields exactly the batches of the plain loop, and
+    the tensors are safe to consume on the main stream while the next sample is being drawn."""
+    import sage
+    import sampler
+    g = sage.synthetic_graph(20000, 400000, torch.device(DEV), seed=3)
+    smp = sampler.NeighborSampler([3, 5])
+    seeds_all = torch.randperm(20000, generator=torch.Generator().manual_seed(1)).to(DEV)
+    seeds_of = lambda s: seeds_all[s * 256:(s + 1) * 256]
+    direct = [smp.sample_blocks(g, seeds_of(s), seed=100 + s) for s in range(6)]
+    sums = []
+    n = 0
+    for inp, outp, blocks in sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: 100 + s, 6):
+        torch.cuda._sleep(3_000_000)                  # a slow "training step" on the main stream
+        sums.append((inp.sum(), blocks[0].indices.long().sum()))
+        d_inp, d_outp, d_blocks = direct[n]
+        assert torch.equal(inp, d_inp) and torch.equal(outp, d_outp)
+        for b, d in zip(blocks, d_blocks):
+            assert torch.equal(b.indptr, d.indptr) and torch.equal(b.indices, d.indices)
+            assert (b.num_src, b.num_dst) == (d.num_src, d.num_dst)
+        n += 1
+    assert n == 6
+    torch.cuda.synchronize()
+    for (a, b), (d_inp, _, d_blocks) in zip(sums, direct):
+        assert int(a) == int(d_inp.sum()) and int(b) == int(d_blocks[0].indices.long().sum())
+    assert list(sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: s, 0)) == []
