@@ -119,6 +119,7 @@ def main():
         s, steps, l, st = run_epoch(e)
         secs.append(s)
         losses.append(l)
+    trainer.close()
     if rank == 0:
         best = min(secs)
         print(json.dumps({
@@ -135,7 +136,7 @@ def main():
                                    "TT p=125,140,140 q=4,5,5 ranks 16,16" %
                                    (args.hidden, args.classes, args.batch, args.train, args.nodes,
                                     args.edges),
-                       "parallelism": "dp%d, replicated model, one NCCL all-reduce per step" % world
+                       "parallelism": "dp%d, replicated model, one NCCL all-reduce of the dense layers' flat gradient buffer + the TT cores exchanged and updated by one kernel over NVLink peer memory per step" % world
                        if world > 1 else "dp1, fused TT SGD"}}), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -101,30 +101,56 @@ def synthetic_community_graph(num_nodes: int, num_edges: int, k: int, p_in: floa
 class Trainer:
     """One optimisation step of the reference's training loop (sage_dgl_partition.py:205-262):
     Adam on the SAGE layers, the TT cores by their fused SGD (single GPU, --sparse) or -- data
-    parallel -- by one all-reduce of every gradient followed by the same update on all ranks."""
+    parallel -- by the exchange step of dp.py: the dense layers' gradients live in ONE flat buffer
+    (the parameters' .grad are views of it) that is all-reduced in place, the TT cores go through
+    dp.PeerExchange (gradient exchange + update in one kernel over NVLink peer memory) when the
+    ranks share a node, else through the same all-reduce followed by ttg_apply_optimizer."""
 
-    def __init__(self, model: SAGE, lr: float = 0.003, world: int = 1):
+    def __init__(self, model: SAGE, lr: float = 0.003, world: int = 1, peer_exchange: bool = True):
         self.model, self.world = model, world
         self.opt = torch.optim.Adam(model.dense_parameters(), lr=lr)
+        self.flat = None
+        self.xchg = None
         if world > 1:
             model.embed_layer.sparse = False
+            params = model.dense_parameters()
+            self.flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32,
+                                    device=params[0].device)
+            off = 0
+            for p in params:      # autograd accumulates into an existing .grad in place
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            if peer_exchange:
+                try:
+                    self.xchg = dp.PeerExchange(model.embed_layer.tt_cores)
+                except RuntimeError:
+                    self.xchg = None          # not one node / no peer access: NCCL for the cores too
 
     def step(self, blocks, input_nodes, labels) -> torch.Tensor:
         m = self.model
         logits = m(blocks, input_nodes)
         loss = F.cross_entropy(logits, labels)
-        self.opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if self.world > 1:
+        if self.world == 1:
+            self.opt.zero_grad(set_to_none=True)
+            loss.backward()
+        else:
             emb = m.embed_layer
-            dense = [p.grad for p in m.dense_parameters()]
+            self.flat.zero_()
+            loss.backward()
             cores = [c.grad for c in emb.tt_cores]
-            reduced = dp.allreduce_mean(dense + cores)
-            for p, gr in zip(m.dense_parameters(), reduced[:len(dense)]):
-                p.grad = gr.contiguous()
-            dp.apply_optimizer(emb.tt_p_shapes, emb.tt_q_shapes, emb.tt_ranks, list(emb.tt_cores),
-                               [gr.contiguous() for gr in reduced[len(dense):]], emb.learning_rate)
+            if self.xchg is not None:
+                dp.allreduce_mean([self.flat])
+                self.xchg.step(cores, list(emb.tt_cores), "sgd", emb.learning_rate)
+            else:
+                reduced = dp.allreduce_mean([self.flat] + cores)
+                dp.apply_optimizer(emb.tt_p_shapes, emb.tt_q_shapes, emb.tt_ranks, list(emb.tt_cores),
+                                   [gr.contiguous() for gr in reduced[1:]], emb.learning_rate)
             for c in emb.tt_cores:
                 c.grad = None
         self.opt.step()
         return loss
+
+    def close(self) -> None:
+        if self.xchg is not None:
+            self.xchg.close()
+            self.xchg = None
