@@ -138,13 +138,13 @@ class Trainer:
             self.flat.zero_()
             loss.backward()
             cores = [c.grad for c in emb.tt_cores]
+            dp.allreduce_mean([self.flat])          # in place: the .grad views see the mean
             if self.xchg is not None:
-                dp.allreduce_mean([self.flat])
                 self.xchg.step(cores, list(emb.tt_cores), "sgd", emb.learning_rate)
             else:
-                reduced = dp.allreduce_mean([self.flat] + cores)
+                reduced = dp.allreduce_mean(cores)  # in place too (tt_dense_backward's flat buffer)
                 dp.apply_optimizer(emb.tt_p_shapes, emb.tt_q_shapes, emb.tt_ranks, list(emb.tt_cores),
-                                   [gr.contiguous() for gr in reduced[1:]], emb.learning_rate)
+                                   [gr.contiguous() for gr in reduced], emb.learning_rate)
             for c in emb.tt_cores:
                 c.grad = None
         self.opt.step()

@@ -95,6 +95,36 @@ def main():
         torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-5 * float(b.abs().max()))
     del gs
     xchg.close()
+    # the GraphSAGE trainer at N > 1: flat dense-gradient buffer + peer exchange for the cores;
+    # replicas stay bit-identical and equal the NCCL-only trainer
+    import sage
+    import sampler
+    graph = sage.synthetic_graph(5000, 60000, dev, seed=0)
+    labels = torch.randint(0, 7, (5000,), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    trainers = []
+    for peer in (True, False):
+        torch.manual_seed(0)
+        np.random.seed(0)
+        model = sage.SAGE(5000, 128, 32, 7, 2, 0.0, (16, 16), (14, 18, 20), (4, 4, 8), sparse=False,
+                          learning_rate=0.01).to(dev)
+        for prm in model.parameters():
+            dist.broadcast(prm.data, 0)
+        trainers.append(sage.Trainer(model, lr=0.01, world=world, peer_exchange=peer))
+    assert trainers[0].xchg is not None and trainers[1].xchg is None
+    smp = sampler.NeighborSampler([4, 4])
+    for step_i in range(4):
+        seeds = torch.randperm(5000, generator=torch.Generator().manual_seed(10 * step_i + rank))[:64].to(dev)
+        inp, outp, blocks = smp.sample_blocks(graph, seeds, seed=step_i * world + rank)
+        for tr in trainers:
+            tr.step(blocks, inp, labels[outp])
+    for pa, pb in zip(trainers[0].model.parameters(), trainers[1].model.parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-4, atol=1e-5 * float(pb.abs().max()) + 1e-7)
+        gathered = [torch.empty_like(pa.data) for _ in range(world)]
+        dist.all_gather(gathered, pa.data.contiguous())
+        for gth in gathered:
+            assert torch.equal(gth, pa.data), "SAGE replicas diverged"
+    for tr in trainers:
+        tr.close()
     dist.barrier()
     if rank == 0:
         print("PEER_EXCHANGE_OK", flush=True)
