@@ -115,6 +115,7 @@ def dist_env():
 # --------------------------------------------------------------------------------------------
 def cpu_step_rate(shape, sample_rows, steps, warmup, seed=0):
     from oracle import oracle as orc
+    orc.use_all_host_threads()      # torchrun exports OMP_NUM_THREADS=1
     p, q, ranks = shape["p"], shape["q"], [1] + shape["ranks"] + [1]
     D = int(np.prod(q))
     rng = np.random.default_rng(seed)

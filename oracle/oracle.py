@@ -65,6 +65,14 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_host_threads():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def tt_forward(p, q, ranks, cores, indices, rowidx, B, tableidx=None, num_tables=1):
     """Reference op tt_forward: zeros[num_tables, B, D] + bag-sum of reconstructed rows."""
     T = len(p)

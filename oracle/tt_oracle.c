@@ -67,6 +67,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline asks for every core */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* index split  FBTT/tt_embeddings_cuda.cu:798-802 */
 static void split_index(const shape_t* s, int64_t idx, int* it) {
   int64_t rem = idx;
