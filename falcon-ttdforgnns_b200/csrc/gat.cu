@@ -130,6 +130,141 @@ head_spmm_bwd_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __res
   }
 }
 
+
+// ---- 16-byte versions: F % 4 == 0 and H * F <= 4 * 32 * kMaxVec, so a lane owns up to kMaxVec
+// float4 columns of a source row and a float4 never straddles two heads.  Each source row is read
+// once per edge (the scalar kernels above re-read index and weight for every column).
+constexpr int kMaxVec = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_spmm_fwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __restrict__ indptr,
+                         const int32_t* __restrict__ indices, const float* __restrict__ a,
+                         const float* __restrict__ ft, float* __restrict__ out) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= num_dst) return;
+  const int64_t e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  const int HF = H * F, n4 = HF / 4;
+  int hj[NV];
+  float4 acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = lane + 32 * j;
+    hj[j] = (c < n4) ? (4 * c) / F : 0;
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  int64_t e = e0;
+  for (; e + 2 <= e1; e += 2) {       // two source rows in flight per lane
+    const float* r0 = ft + (int64_t)__ldg(indices + e) * HF;
+    const float* r1 = ft + (int64_t)__ldg(indices + e + 1) * HF;
+    const float* w0 = a + e * H;
+    const float* w1 = w0 + H;
+    float4 x0[NV], x1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        x0[j] = ldg4(r0 + 4 * c);
+        x1[j] = ldg4(r1 + 4 * c);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        const float a0 = __ldg(w0 + hj[j]), a1 = __ldg(w1 + hj[j]);
+        acc[j].x = fmaf(a0, x0[j].x, acc[j].x);
+        acc[j].y = fmaf(a0, x0[j].y, acc[j].y);
+        acc[j].z = fmaf(a0, x0[j].z, acc[j].z);
+        acc[j].w = fmaf(a0, x0[j].w, acc[j].w);
+        acc[j].x = fmaf(a1, x1[j].x, acc[j].x);
+        acc[j].y = fmaf(a1, x1[j].y, acc[j].y);
+        acc[j].z = fmaf(a1, x1[j].z, acc[j].z);
+        acc[j].w = fmaf(a1, x1[j].w, acc[j].w);
+      }
+    }
+  }
+  if (e < e1) {
+    const float* r0 = ft + (int64_t)__ldg(indices + e) * HF;
+    const float* w0 = a + e * H;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        const float4 x = ldg4(r0 + 4 * c);
+        const float a0 = __ldg(w0 + hj[j]);
+        acc[j].x = fmaf(a0, x.x, acc[j].x);
+        acc[j].y = fmaf(a0, x.y, acc[j].y);
+        acc[j].z = fmaf(a0, x.z, acc[j].z);
+        acc[j].w = fmaf(a0, x.w, acc[j].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = lane + 32 * j;
+    if (c < n4) *reinterpret_cast<float4*>(out + v * HF + 4 * c) = acc[j];
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_spmm_bwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __restrict__ indptr,
+                         const int32_t* __restrict__ indices, const float* __restrict__ a,
+                         const float* __restrict__ ft, const float* __restrict__ dout,
+                         float* __restrict__ dft, float* __restrict__ da) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= num_dst) return;
+  const int64_t e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  if (e1 <= e0) return;
+  const int HF = H * F, n4 = HF / 4;
+  int hj[NV];
+  float4 g[NV];                    // this destination row's gradient, held for all its edges
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = lane + 32 * j;
+    hj[j] = (c < n4) ? (4 * c) / F : 0;
+    g[j] = (c < n4) ? ldg4(dout + v * HF + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t e = e0; e < e1; ++e) {
+    const int64_t u = __ldg(indices + e);
+    const float* r = ft + u * HF;
+    float* dr = dft + u * HF;
+    const float* w = a + e * H;
+    float part[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) part[h] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        const float4 x = ldg4(r + 4 * c);
+        const float ah = __ldg(w + hj[j]);
+        red_add_v4(dr + 4 * c, make_float4(ah * g[j].x, ah * g[j].y, ah * g[j].z, ah * g[j].w));
+        const float dot = g[j].x * x.x + g[j].y * x.y + g[j].z * x.z + g[j].w * x.w;
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h == hj[j]) part[h] += dot;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      if (h < H) {
+        const float sum = warp_sum(part[h]);
+        if (lane == 0) da[e * H + h] = sum;
+      }
+    }
+  }
+}
+
+template <typename K, typename... Args>
+void launch_vec(int nv, K k1, K k2, K k4, K k8, unsigned grid, cudaStream_t s, Args... args) {
+  K k = nv <= 1 ? k1 : nv <= 2 ? k2 : nv <= 4 ? k4 : k8;
+  k<<<grid, 256, 0, s>>>(args...);
+}
+
 }  // namespace
 }  // namespace ttg
 
@@ -164,8 +299,14 @@ extern "C" int ttg_head_spmm_csr_fwd(int64_t num_dst, int32_t H, int32_t F, cons
   TTG_CHECK_ARG(H > 0 && H <= kMaxHeads && F > 0, "head_spmm: heads=%d, F=%d out of range", H, F);
   if (num_dst == 0) return TTG_OK;
   TTG_CHECK_ARG(indptr && out, "head_spmm_fwd: null pointer");
-  head_spmm_fwd_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      num_dst, H, F, indptr, indices, a, ft, out);
+  const unsigned grid = (unsigned)ceil_div(num_dst * 32, 256);
+  const int nv = (int)ceil_div((int64_t)H * F / 4, 32);
+  if (F % 4 == 0 && nv <= kMaxVec && ((uintptr_t)ft & 15) == 0 && ((uintptr_t)out & 15) == 0)
+    launch_vec(nv, head_spmm_fwd_vec_kernel<1>, head_spmm_fwd_vec_kernel<2>, head_spmm_fwd_vec_kernel<4>,
+               head_spmm_fwd_vec_kernel<8>, grid, (cudaStream_t)stream, num_dst, H, F, indptr, indices, a,
+               ft, out);
+  else
+    head_spmm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft, out);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
 }
@@ -177,8 +318,16 @@ extern "C" int ttg_head_spmm_csr_bwd(int64_t num_dst, int32_t H, int32_t F, cons
   TTG_CHECK_ARG(H > 0 && H <= kMaxHeads && F > 0, "head_spmm: heads=%d, F=%d out of range", H, F);
   if (num_dst == 0) return TTG_OK;
   TTG_CHECK_ARG(indptr && dout && dft && da, "head_spmm_bwd: null pointer");
-  head_spmm_bwd_kernel<<<(unsigned)ceil_div(num_dst * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      num_dst, H, F, indptr, indices, a, ft, dout, dft, da);
+  const unsigned grid = (unsigned)ceil_div(num_dst * 32, 256);
+  const int nv = (int)ceil_div((int64_t)H * F / 4, 32);
+  if (F % 4 == 0 && nv <= kMaxVec && ((uintptr_t)ft & 15) == 0 && ((uintptr_t)dout & 15) == 0 &&
+      ((uintptr_t)dft & 15) == 0)
+    launch_vec(nv, head_spmm_bwd_vec_kernel<1>, head_spmm_bwd_vec_kernel<2>, head_spmm_bwd_vec_kernel<4>,
+               head_spmm_bwd_vec_kernel<8>, grid, (cudaStream_t)stream, num_dst, H, F, indptr, indices, a,
+               ft, dout, dft, da);
+  else
+    head_spmm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft,
+                                                                 dout, dft, da);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
 }
