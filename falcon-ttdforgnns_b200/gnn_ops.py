@@ -395,3 +395,36 @@ class GAT(nn.Module):
             if i < self.n_layers - 1:
                 h = self.dropout(self.activation(self.bns[i](h.flatten(1))))
         return self.bias_last(h.mean(1))
+
+
+class GCN(nn.Module):
+    """The reference's GCN model (gnn_model.py:269-314): GraphConv(norm='both') layers (bias only
+    on the last), an optional parallel Linear per layer, BatchNorm / activation / dropout between
+    layers.  `graph` is a Block with num_src == num_dst (the full graph, CSR by destination)."""
+
+    def __init__(self, in_feats, n_hidden, n_classes, n_layers, activation, dropout, use_linear):
+        super().__init__()
+        self.n_layers, self.n_hidden, self.n_classes, self.use_linear = n_layers, n_hidden, n_classes, use_linear
+        self.convs, self.bns = nn.ModuleList(), nn.ModuleList()
+        if use_linear:
+            self.linear = nn.ModuleList()
+        for i in range(n_layers):
+            in_hidden = n_hidden if i > 0 else in_feats
+            out_hidden = n_hidden if i < n_layers - 1 else n_classes
+            self.convs.append(GraphConv(in_hidden, out_hidden, "both", bias=(i == n_layers - 1)))
+            if use_linear:
+                self.linear.append(nn.Linear(in_hidden, out_hidden, bias=False))
+            if i < n_layers - 1:
+                self.bns.append(nn.BatchNorm1d(out_hidden))
+        self.dropout0 = nn.Dropout(min(0.1, dropout))
+        self.dropout = nn.Dropout(dropout)
+        self.activation = activation
+
+    def forward(self, graph: Block, feat):
+        h = self.dropout0(feat)
+        for i in range(self.n_layers):
+            conv = self.convs[i](graph, h)
+            h = conv + self.linear[i](h) if self.use_linear else conv
+            if i < self.n_layers - 1:
+                h = self.dropout(self.activation(self.bns[i](h)))
+        return h

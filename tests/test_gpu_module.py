@@ -262,3 +262,29 @@ def test_graphed_step_equals_eager_steps(ttg_lib):
     for a, b in zip(m_graph.tt_cores, m_eager.tt_cores):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-5 * float(b.abs().max()))
     assert not torch.equal(m_eager.tt_cores[2], _make(n_emb, D, ranks, p, q, **kw).tt_cores[2])
+
+
+def test_gcn_stack_wiring(ttg_lib):
+    """gnn_ops.GCN composes GraphConv / Linear / BatchNorm as the reference's GCN does
+    (gnn_model.py:297-314): checked against the same layers applied by hand, in eval mode."""
+    import gnn_ops
+    from helpers import random_block
+    rng = np.random.default_rng(8)
+    n = 400
+    indptr, indices = random_block(rng, n, n, 6)
+    blk = gnn_ops.Block(torch.from_numpy(indptr).to(DEV), torch.from_numpy(indices).to(DEV), n, n)
+    torch.manual_seed(2)
+    for use_linear in (False, True):
+        m = gnn_ops.GCN(32, 24, 5, 3, torch.nn.functional.relu, 0.5, use_linear).to(DEV).eval()
+        x = torch.randn(n, 32, device=DEV, requires_grad=True)
+        out = m(blk, x)
+        h = x
+        for i in range(3):
+            c = m.convs[i](blk, h)
+            h = c + m.linear[i](h) if use_linear else c
+            if i < 2:
+                h = torch.relu(m.bns[i](h))
+        torch.testing.assert_close(out, h)
+        assert out.shape == (n, 5) and m.convs[2].bias is not None and m.convs[0].bias is None
+        out.sum().backward()
+        assert x.grad is not None and float(x.grad.abs().sum()) > 0
