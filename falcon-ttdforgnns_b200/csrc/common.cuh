@@ -103,13 +103,40 @@ __device__ __forceinline__ void st_cs_v4(float* p, float4 v) {
 // visible.  Both instructions are no-ops in a launch without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// After pdl_wait(), data that a preceding kernel of the chain produced must NOT be read with
+// __ldg / through const __restrict__ pointers: those become ld.global.nc, which both the compiler
+// and ptxas treat as invariant and hoist above griddepcontrol.wait when the address is known early
+// (ptxas did: the backward row kernel read the plan's row count before the scan kernel of the same
+// call had written it -- wrong gradients whenever the previous call had a different count).  The
+// ld_dep_* loads below are ordinary ld.global in volatile asm: ordered after the wait, and every
+// load whose address depends on their result is ordered behind them by that dependence.
+__device__ __forceinline__ uint32_t ld_dep_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int32_t ld_dep_s32(const void* p) { return (int32_t)ld_dep_u32(p); }
+__device__ __forceinline__ int4 ld_dep_int4(const void* p) {
+  int4 v;
+  asm volatile("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_dep_float4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
 
 int pdl_level();   // api.cu: environment TTG_PDL_LEVEL, default 1
                    // 0: ordinary launches; 1: row / cores / finalize kernels; 2: also the plan chain
-                   // (scan, scatter, table).  Level 2 is NOT the default: with a deep launch queue one
-                   // backward-only case computes a wrong d_core0 (tests/test_gpu_vs_reference_ext.py::
-                   // test_fused_sgd_matches_reference_on_the_rows_it_updates in the full suite); cause
-                   // not found yet, see DESIGN.md section 4
+                   // (scan, scatter, table).  Level 2 is correct (full suite) but gains nothing
+                   // measurable over level 1, so it stays opt-in.
 
 template <int LEVEL = 1, typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,

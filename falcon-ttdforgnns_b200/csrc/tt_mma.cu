@@ -424,8 +424,8 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
   uint32_t nkey = total_rows;
   int32_t nsr = 0;
   if (lane < 2 * RB && s_begin + lane < s_end) {
-    nkey = skeys ? __ldg(skeys + s_begin + lane) : first_key + (uint32_t)(s_begin + lane);
-    nsr = skeys ? __ldg(srow + s_begin + lane) : (int32_t)(s_begin + lane);
+    nkey = skeys ? ld_dep_u32(skeys + s_begin + lane) : first_key + (uint32_t)(s_begin + lane);
+    nsr = skeys ? ld_dep_s32(srow + s_begin + lane) : (int32_t)(s_begin + lane);
   }
   for (int64_t w0 = s_begin; w0 < s_end; w0 += 2 * RB) {
     const uint32_t key = nkey;
@@ -433,8 +433,8 @@ mma_fwd_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, const uint32_t* __res
     nkey = total_rows;
     nsr = 0;
     if (lane < 2 * RB && w0 + 2 * RB + lane < s_end) {
-      nkey = skeys ? __ldg(skeys + w0 + 2 * RB + lane) : first_key + (uint32_t)(w0 + 2 * RB + lane);
-      nsr = skeys ? __ldg(srow + w0 + 2 * RB + lane) : (int32_t)(w0 + 2 * RB + lane);
+      nkey = skeys ? ld_dep_u32(skeys + w0 + 2 * RB + lane) : first_key + (uint32_t)(w0 + 2 * RB + lane);
+      nsr = skeys ? ld_dep_s32(srow + w0 + 2 * RB + lane) : (int32_t)(w0 + 2 * RB + lane);
     }
     const int nwin = (int)((s_end - w0 < 2 * RB) ? (s_end - w0) : 2 * RB);
     const bool kvalid = key < total_rows;
@@ -637,7 +637,7 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
   uint32_t phase0 = 0, phase1 = 0;
   const uint32_t p2 = tt.p[2];
   const uint32_t num_rows32 = (uint32_t)tt.num_rows;
-  const int64_t nvalid = __ldg(base + num_groups);     // invalid keys form the last bucket
+  const int64_t nvalid = ld_dep_s32(base + num_groups);  // invalid keys form the last bucket
   const int64_t nchunks = (nvalid + chunk_rows - 1) / chunk_rows;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + wib;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
@@ -656,12 +656,12 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
     const int64_t nom_end = (nom_begin + chunk_rows < nvalid) ? nom_begin + chunk_rows : nvalid;
     int64_t s = nom_begin, e_run = nom_end;
     if (chunk > 0) {
-      const uint32_t gp = __ldg(skeys + nom_begin - 1) / p2;
-      s = (int64_t)__ldg(base + gp) + __ldg(cnt + gp);   // first row after that group
+      const uint32_t gp = ld_dep_u32(skeys + nom_begin - 1) / p2;
+      s = (int64_t)ld_dep_s32(base + gp) + ld_dep_s32(cnt + gp);   // first row after that group
     }
     {
-      const uint32_t gl = __ldg(skeys + nom_end - 1) / p2;
-      e_run = (int64_t)__ldg(base + gl) + __ldg(cnt + gl);
+      const uint32_t gl = ld_dep_u32(skeys + nom_end - 1) / p2;
+      e_run = (int64_t)ld_dep_s32(base + gl) + ld_dep_s32(cnt + gl);
     }
     if (s >= e_run) continue;
 
@@ -685,8 +685,8 @@ mma_bwd_rows_kernel(TTDev tt, int64_t nnz, uint32_t total_rows, int32_t num_grou
       k = total_rows;
       r = 0;
       if (lane < 2 * RB && row0 + lane < e_run) {
-        k = __ldg(skeys + row0 + lane);
-        r = __ldg(srow + row0 + lane);
+        k = ld_dep_u32(skeys + row0 + lane);
+        r = ld_dep_s32(srow + row0 + lane);
       }
     };
     uint32_t nkey;
@@ -971,7 +971,7 @@ mma_bwd_cores_kernel(TTDev tt, const float* __restrict__ Sbuf, const int32_t* __
       const int c2 = wib + kCoresWarps * (it + lane / IPC);
       const int i0m = c2 * IPC + lane % IPC;
       on_l = 0;
-      if (c2 < nchunks && i0m < p0) on_l = *((const volatile int32_t*)cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
+      if (c2 < nchunks && i0m < p0) on_l = ld_dep_s32(cnt + ((size_t)tix * p0 + i0m) * p1 + i1) > 0;
     }
     if (ch < nchunks) {
       float* dst = stage + buf * 16 * CS;
@@ -1164,7 +1164,7 @@ __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
         float4 v[kFinPer];
 #pragma unroll
         for (int u = 0; u < kFinPer; ++u)
-          v[u] = (p + u < hi) ? ldg4(a.d0parts + (size_t)(p + u) * a.e0 + o)
+          v[u] = (p + u < hi) ? ld_dep_float4(a.d0parts + (size_t)(p + u) * a.e0 + o)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < kFinPer; ++u) {

@@ -188,10 +188,10 @@ bucket_scan_kernel(const int32_t* __restrict__ cnt, int32_t* __restrict__ base) 
   const int4* c4 = reinterpret_cast<const int4*>(cnt);
   int32_t acc = 0;
   for (int i = threadIdx.x; i < (int)blockIdx.x * 1024; i += 1024) {
-    const int4 v = __ldg(c4 + i);
+    const int4 v = ld_dep_int4(c4 + i);
     acc += v.x + v.y + v.z + v.w;
   }
-  const int4 mine = __ldg(c4 + (size_t)blockIdx.x * 1024 + threadIdx.x);
+  const int4 mine = ld_dep_int4(c4 + (size_t)blockIdx.x * 1024 + threadIdx.x);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) warp_tot[wib] = acc;
@@ -254,15 +254,15 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
 #pragma unroll
     for (int k = 0; k < kPlanItems; ++k) {
       const int64_t n = n0 + k * 256;
-      key[k] = (n < nnz) ? __ldg(keys + n) : total_rows;
-      val[k] = (n < nnz) ? __ldg(vals + n) : 0;
-      pos[k] = (n < nnz) ? __ldg(ranks + n) : 0;
+      key[k] = (n < nnz) ? ld_dep_u32(keys + n) : total_rows;
+      val[k] = (n < nnz) ? ld_dep_s32(vals + n) : 0;
+      pos[k] = (n < nnz) ? ld_dep_s32(ranks + n) : 0;
     }
 #pragma unroll
     for (int k = 0; k < kPlanItems; ++k) {
       const int32_t g = key[k] < total_rows ? (int32_t)(key[k] / p2) : num_groups;
-      pos[k] += __ldg(base + g);
-      rc[k] = rowcount ? __ldg(rowcount + val[k]) : 1;
+      pos[k] += ld_dep_s32(base + g);
+      rc[k] = rowcount ? ld_dep_s32(rowcount + val[k]) : 1;
     }
 #pragma unroll
     for (int k = 0; k < kPlanItems; ++k) {
@@ -277,7 +277,7 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
       const int64_t n = n0 + k * 256;
       if (n < nnz) {
         const int32_t v = srow[n];
-        if (__ldg(rowcount + v) != 1) srow[n] = (int32_t)((uint32_t)v | kMultiBit);
+        if (ld_dep_s32(rowcount + v) != 1) srow[n] = (int32_t)((uint32_t)v | kMultiBit);
       }
     }
   }
@@ -288,7 +288,7 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
     const int64_t nwarps = ((int64_t)gridDim.x * 256) >> 5;
     for (int64_t r0 = warp * 32; r0 < out_rows; r0 += nwarps * 32) {
       const int64_t r = r0 + lane;
-      uint32_t pending = __ballot_sync(0xffffffffu, r < out_rows && __ldg(rowcount + r) != 1);
+      uint32_t pending = __ballot_sync(0xffffffffu, r < out_rows && ld_dep_s32(rowcount + r) != 1);
       while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;

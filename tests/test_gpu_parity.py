@@ -626,3 +626,38 @@ def test_back_to_back_steps_with_a_deep_launch_queue(ttg_lib):
             upd = (results["generic"][t] - start[t]).abs().max()
             err = (results[name][t] - results["generic"][t]).abs().max()
             assert float(err / upd) < 1e-4, "%s core %d: %.3g of the update" % (name, t, float(err / upd))
+
+
+def test_backward_only_after_a_call_with_another_row_count(ttg_lib):
+    """Regression: the backward row kernel once read the plan's row count with an invariant
+    (ld.global.nc) load that ptxas hoisted above griddepcontrol.wait, i.e. before the scan kernel
+    of the same call had written it -- the count of the PREVIOUS call was used.  Backward-only
+    calls with alternating row counts, queued behind a busy GPU."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["products"]
+    D = 100
+    g = torch.Generator(device="cpu").manual_seed(6)
+    sizes = [30000, 18000, 41000, 20000]
+    idx = [torch.randint(0, n_emb, (n,), generator=g).to(DEV) for n in sizes]
+    dOs = [(torch.rand(1, n, D, generator=g) * 0.1).to(DEV) for n in sizes]
+    cores = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 15)]
+    outs = {}
+    for name, fl in (("generic", _ttg.FLAG_FORCE_GENERIC), ("mma", 0)):
+        te.EXTRA_FLAGS = fl
+        try:
+            torch.cuda.synchronize()
+            torch.cuda._sleep(40_000_000)
+            res = []
+            for k, n in enumerate(sizes):
+                row = torch.arange(n, device=DEV)
+                res.append(te.tt_dense_backward(1000, D, p, q, r, None, n, idx[k], row,
+                                                torch.zeros_like(row), dOs[k], cores))
+            torch.cuda.synchronize()
+        finally:
+            te.EXTRA_FLAGS = 0
+        outs[name] = res
+    for k in range(len(sizes)):
+        for t in range(3):
+            a, b = outs["mma"][k][t], outs["generic"][k][t]
+            assert float((a - b).abs().max() / b.abs().max()) < 5e-5, "call %d core %d" % (k, t)
