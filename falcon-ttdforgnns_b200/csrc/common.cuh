@@ -50,6 +50,21 @@ void count_launch(int n = 1);
     }                                                                               \
   } while (0)
 
+// opt-in to more than 48 KB of dynamic shared memory, once per kernel AND device (the attribute
+// belongs to the device's context; a process may drive several GPUs)
+#define TTG_ENSURE_SMEM(kern, bytes)                                                          \
+  do {                                                                                        \
+    static size_t _ttg_set[32] = {};                                                          \
+    int _ttg_dev = 0;                                                                         \
+    TTG_CUDA(cudaGetDevice(&_ttg_dev));                                                       \
+    const bool _ttg_in = _ttg_dev >= 0 && _ttg_dev < 32;                                      \
+    if (!_ttg_in || _ttg_set[_ttg_dev] < (size_t)(bytes)) {                                   \
+      TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                    (int)(bytes)));                                           \
+      if (_ttg_in) _ttg_set[_ttg_dev] = (size_t)(bytes);                                      \
+    }                                                                                         \
+  } while (0)
+
 // ---- optional per-kernel timing (CUDA events on the launching stream), api.cu ------------
 enum KernelId {
   K_PLAN = 0, K_SORT, K_ZERO_ROWS, K_FWD, K_BWD_ROWS, K_BWD_CORES, K_REDUCE, K_OPTIM,

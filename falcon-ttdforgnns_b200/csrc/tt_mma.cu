@@ -1252,11 +1252,7 @@ struct Shape {
     const int npairs = tt.num_tables * tt.p[2] * Q2;
     const size_t smem = fwd_smem(npairs, TERMS);
     auto kern = mma_fwd_kernel<Q0, Q1, Q2, R2, TERMS, kC2S>;
-    static size_t set_smem = 0;
-    if (set_smem < smem) {
-      TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      set_smem = smem;
-    }
+    TTG_ENSURE_SMEM(kern, smem);
     constexpr int RB = fwd_rb(Q2);
     int64_t grid = kNumSMs;
     if (grid * kWarps * RB > nnz) grid = ceil_div(nnz, kWarps * RB);
@@ -1298,11 +1294,7 @@ struct Shape {
     {
       const size_t smem = bwd_smem(npairs);
       auto kern = mma_bwd_rows_kernel<Q0, Q1, Q2, R2, TERMS>;
-      static size_t set_smem = 0;
-      if (set_smem < smem) {
-        TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_smem = smem;
-      }
+      TTG_ENSURE_SMEM(kern, smem);
       int64_t chunk = ceil_div(nnz, (int64_t)kNumSMs * kWarps);
       if (chunk < 32) chunk = 32;
       int64_t grid = ceil_div(ceil_div(nnz, chunk), kWarps);
@@ -1330,11 +1322,7 @@ struct Shape {
     const int nb1 = tt.num_tables * tt.p[1];
     const size_t smem = sizeof(float) * ((C / 8) * 2 * 32 * 4 + (size_t)NW * 2 * 16 * cores_row_stride<C>());
     auto kern = mma_bwd_cores_kernel<Q0, Q1, R1, R2, TERMS, NW>;
-    static bool attr = false;
-    if (!attr) {
-      TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
+    TTG_ENSURE_SMEM(kern, smem);
     prof_begin(K_BWD_CORES, stream);
     TTG_CUDA(launch_pdl(kern, dim3(nb1, R1 / 16), dim3(NW * 32), smem, stream, tt, pl.S, pl.cnt, pl.d0parts,
                         dcore1, (size_t)e0));

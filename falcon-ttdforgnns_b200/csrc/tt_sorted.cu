@@ -1202,12 +1202,7 @@ int launch_table(const TTDev& tt, const SortedWs& w, cudaStream_t stream) {
   split = (int)ceil_div(tt.p[0], per);
   const size_t smem = sizeof(float) * (size_t)per * Q0 * R1;
   auto kern = group_table_kernel<Q0, Q1, R1, R2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(sizeof(float) * 128 * Q0 * R1)));
-    attr_set = true;
-  }
+  TTG_ENSURE_SMEM(kern, sizeof(float) * 128 * Q0 * R1);
   prof_begin(K_TABLE, stream);
   kern<<<dim3(nb, split), Q0 * Q1 * R2, smem, stream>>>(tt, w.Ttab, per);
   prof_end(K_TABLE, stream);
@@ -1221,8 +1216,8 @@ int fwd_grid(Kern kern, size_t smem, int slot, int64_t nnz, int64_t* grid, int64
   static size_t cached_smem[4] = {~(size_t)0, ~(size_t)0, ~(size_t)0, ~(size_t)0};
   static int cached_per_sm[4] = {0, 0, 0, 0};
   constexpr int wpb = kFwdThreads / 32;
+  TTG_ENSURE_SMEM(kern, smem);      // per device
   if (cached_smem[slot] != smem) {  // first call for this (kernel, smem): query once
-    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int q = 0;
     TTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kFwdThreads, smem));
     cached_per_sm[slot] = q < 1 ? 1 : q;
@@ -1288,11 +1283,7 @@ int launch_bwd_rows(const TTDev& tt, int64_t nnz, uint32_t total_rows, const Sor
   const size_t ring_bytes = sizeof(float) * (kBwdThreads / 32) * kBwdStages * RPW * D;
   const size_t smem = ring_bytes + (SMEM_ACC ? sizeof(float) * (size_t)core2_elems : 0);
   auto kern = sorted_bwd_rows_kernel<Q0, Q1, Q2, R1, R2, SMEM_ACC, TTAB>;
-  static size_t set_smem = ~(size_t)0;
-  if (set_smem != smem) {
-    TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set_smem = smem;
-  }
+  TTG_ENSURE_SMEM(kern, smem);
   // one contiguous, equally long run of sorted rows per warp (groups belong to the run they
   // start in), so every warp finishes at the same time
   int64_t chunk_rows = ceil_div(nnz, (int64_t)kBwdGrid * (kBwdThreads / 32));
@@ -1367,11 +1358,7 @@ int launch_bwd(const TTDev& tt, int64_t nnz, uint32_t total_rows, const SortedWs
         sizeof(float) * ((size_t)Q0 * KH * NT > (size_t)4 * R1 * C ? (size_t)Q0 * KH * NT
                                                                    : (size_t)4 * R1 * C);
     auto ckern = sorted_bwd_cores_kernel<Q0, Q1, Q2, R1, R2>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      TTG_CUDA(cudaFuncSetAttribute(ckern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-      attr_set = true;
-    }
+    TTG_ENSURE_SMEM(ckern, csmem);
     ckern<<<dim3(nblocks, kCoreSplit), NT, csmem, stream>>>(tt, w.S, w.touched, w.cparts,
                                                             w.cparts + e0, (size_t)(e0 + e1));
   }
