@@ -1259,9 +1259,17 @@ struct Shape {
     int64_t rpw = ceil_div(nnz, grid * kWarps);
     rpw = ceil_div(rpw, RB) * RB;
     prof_begin(K_FWD, stream);
-    TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, tt, nnz, total_rows,
-                        pl.skeys, pl.srow, pl.Ttab, output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
-                        pl.first_key));
+    // Implicit keys (range reconstruction): the group-table loads do not depend on any ordered
+    // load, so nothing would keep the compiler from hoisting them above griddepcontrol.wait --
+    // that launch is an ordinary one (the wait is then a no-op).
+    if (pl.skeys != nullptr)
+      TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, tt, nnz, total_rows,
+                          pl.skeys, pl.srow, pl.Ttab, output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
+                          pl.first_key));
+    else
+      kern<<<(unsigned)grid, kThreads, smem, stream>>>(tt, nnz, total_rows, pl.skeys, pl.srow, pl.Ttab,
+                                                       output, (int)rpw, npairs, dbg_knob("TTG_DBG_FWD"),
+                                                       pl.first_key);
     prof_end(K_FWD, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
