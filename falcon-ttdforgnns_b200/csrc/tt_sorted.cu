@@ -1216,7 +1216,9 @@ int fwd_grid(Kern kern, size_t smem, int slot, int64_t nnz, int64_t* grid, int64
   static size_t cached_smem[4] = {~(size_t)0, ~(size_t)0, ~(size_t)0, ~(size_t)0};
   static int cached_per_sm[4] = {0, 0, 0, 0};
   constexpr int wpb = kFwdThreads / 32;
-  TTG_ENSURE_SMEM(kern, smem);      // per device
+  // Kern is a function-pointer TYPE shared by several kernels, so nothing can be cached per kernel
+  // in here: set the attribute on every call (a host-side table write; FFMA path only)
+  TTG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (cached_smem[slot] != smem) {  // first call for this (kernel, smem): query once
     int q = 0;
     TTG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kFwdThreads, smem));
