@@ -184,7 +184,7 @@ def reference_gpu_rate(args, shape, steps=5):
             return None
         dev = torch.device("cuda", 0)
         p, q, rr, N = shape["p"], shape["q"], [1] + shape["ranks"] + [1], shape["n"]
-        D, nnz = int(np.prod(q)), args.nnz
+        D, nnz = int(np.prod(q)), min(args.nnz, N)
         g = torch.Generator().manual_seed(1000)
         cores = [(torch.randn(1, p[t], rr[t] * q[t] * rr[t + 1], generator=g) / np.sqrt(N)).to(dev)
                  for t in range(3)]
@@ -218,7 +218,7 @@ def reference_gpu_rate(args, shape, steps=5):
 def workload_name(args):
     s = SHAPES[args.shape]
     return ("%s shape: N=%d, p=%s q=%s ranks=%s, %d distinct uniform ids per step, one index per "
-            "bag, fwd+bwd+SGD" % (args.shape, s["n"], s["p"], s["q"], s["ranks"], args.nnz))
+            "bag, fwd+bwd+SGD" % (args.shape, s["n"], s["p"], s["q"], s["ranks"], min(args.nnz, s["n"])))
 
 
 # --------------------------------------------------------------------------------------------
@@ -251,7 +251,7 @@ def run_ours(args, shape):
     p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
     rr = [1] + ranks + [1]
     D = int(np.prod(q))
-    nnz = args.nnz
+    nnz = min(args.nnz, N)     # distinct ids per step: a table smaller than the batch caps it
     torch.manual_seed(1234)
     module = TTEmbeddingBag(N, D, ranks, p, q, optimizer=OptimType.SGD, learning_rate=LR,
                             sparse=True, use_cache=False, weight_dist="normal")
