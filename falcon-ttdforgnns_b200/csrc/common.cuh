@@ -222,4 +222,26 @@ int mma_backward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPla
 int mma_cores_finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, int32_t optim, float lr,
                        float eps, float* const* state, bool tf32, cudaStream_t stream);
 
+// right-grouped kernels on the sm_100a tensor path (tcgen05 + TMEM), tt_tc5.cu.  The plan is the one of
+// tt_sorted.cu built on TRANSPOSED keys  table * prod(p) + (idx % (p1 p2)) * p0 + idx / (p1 p2):
+// group = key / p0 = (table, i1, i2), i0 = key % p0.
+struct RPlan {
+  const uint32_t* skeys;
+  const int32_t* srow;
+  const int32_t* cnt;      // [groups + 1] rows per group
+  const int32_t* base;     // [groups + 1] exclusive scan
+  float* tab;              // [groups][2][r1 * q1 q2]  tr1 operand images, hi plane then lo plane
+  float* S1;               // [groups][r1][q1 q2]      d(tr1), written by the backward row kernel
+  float* d0parts;          // [kNumSMs][core0 elements] per-CTA copies of d_core0
+};
+bool r_supported(const TTDev& tt);
+size_t r_table_floats(const TTDev& tt);
+int r_table(const TTDev& tt, const RPlan& pl, cudaStream_t stream);
+int r_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream);
+int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
+               int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream);
+// d_core0 = sum of `nparts` partial copies (fixed order) + optimizer step on all three cores, tt_mma.cu
+int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float* const* dcore, int32_t optim,
+                       float lr, float eps, float* const* state, cudaStream_t stream);
+
 }  // namespace ttg

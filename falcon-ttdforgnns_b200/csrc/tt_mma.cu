@@ -1444,6 +1444,32 @@ int mma_cores_finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, 
   return e->finalize(tt, pl, dcore, optim, lr, eps, state, stream);
 }
 
+int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float* const* dcore, int32_t optim,
+                       float lr, float eps, float* const* state, cudaStream_t stream) {
+  MmaFinalArgs a;
+  memset(&a, 0, sizeof(a));
+  a.e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
+  a.e1 = (int64_t)tt.num_tables * tt.p[1] * tt.cols[1];
+  a.e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
+  a.nparts = nparts;
+  a.d0parts = d0parts;
+  for (int t = 0; t < 3; ++t) {
+    a.dcore[t] = dcore[t];
+    a.core[t] = tt.core[t];
+    a.state[t] = state ? state[t] : nullptr;
+  }
+  a.optim = optim;
+  a.lr = lr;
+  a.eps = eps;
+  a.nb0 = (int)ceil_div(a.e0, 4 * kFinCols);
+  const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(a.e1 + a.e2, 1024);
+  prof_begin(K_REDUCE, stream);
+  TTG_CUDA(launch_pdl(mma_finalize_kernel, dim3(a.nb0 + nb12), dim3(256), 0, stream, a));
+  prof_end(K_REDUCE, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
 int mma_backward(const TTDev& tt, int64_t nnz, uint32_t total_rows, const MmaPlan& pl,
                  const float* d_output, float* const* dcore, int32_t optim, float lr, float eps,
                  float* const* state, bool tf32, cudaStream_t stream) {

@@ -58,6 +58,14 @@ inline bool use_group_table(const TTDev& tt, int64_t nnz) {
   return 2.0 * groups * cost_group <= (double)nnz * cost_row;
 }
 
+// Right-grouped strategy (tt_tc5.cu, tcgen05 kernels): groups are (i1, i2), tr1 = core1 core2 of every
+// group comes from a dense table kernel -- worth it when a group has a row on average
+inline bool use_right_groups(const TTDev& tt, int64_t nnz) {
+  if (!r_supported(tt)) return false;
+  if ((uint64_t)tt.num_tables * tt.p[1] * tt.p[2] >= 0x7ffffff0ull) return false;
+  return (double)tt.num_tables * tt.p[1] * tt.p[2] <= (double)nnz;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -84,6 +92,9 @@ struct SortedWs {
   float* partials;     // [kBwdGrid][tables * p2 * cols2] or nullptr (FFMA kernels)
   float* cparts;       // [kCoreSplit][core0 + core1 elements]    (FFMA kernels)
   float* d0parts;      // [p1][core0 elements]                    (tensor-core kernels)
+  float* tabR;         // [tables * p1 * p2][2][r1 q1 q2]  tr1 operand images (tcgen05 kernels)
+  float* S1R;          // [tables * p1 * p2][r1][q1 q2]    d(tr1)          (tcgen05 kernels)
+  float* d0partsR;     // [kNumSMs][core0 elements]                (tcgen05 kernels)
   int32_t* cnt;        // [cnt_elems] rows per group (+1: invalid keys), padded to scan tiles
   int32_t* rowcount;   // [tables * B] valid indices per output row; directly behind cnt
   size_t cnt_bytes;    // cnt alone (backward-only plan)
@@ -105,6 +116,7 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
   };
   const size_t n = (size_t)(nnz > 0 ? nnz : 1);
   const size_t groups = (size_t)tt.num_tables * tt.p[0] * tt.p[1];
+  const size_t groups_r = (size_t)tt.num_tables * tt.p[1] * tt.p[2];
   const size_t core2 = (size_t)tt.num_tables * tt.p[2] * tt.cols[2];
   const size_t e0 = (size_t)tt.num_tables * tt.p[0] * tt.cols[0];
   const size_t e1 = (size_t)tt.num_tables * tt.p[1] * tt.cols[1];
@@ -121,8 +133,12 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
                : nullptr;
   w.cparts = (float*)take(sizeof(float) * kCoreSplit * (e0 + e1));
   w.d0parts = (float*)take(sizeof(float) * (size_t)tt.p[1] * e0);
+  const bool rpath = use_right_groups(tt, nnz);
+  w.tabR = rpath ? (float*)take(sizeof(float) * r_table_floats(tt)) : nullptr;
+  w.S1R = rpath ? (float*)take(sizeof(float) * r_table_floats(tt) / 2) : nullptr;
+  w.d0partsR = rpath ? (float*)take(sizeof(float) * (size_t)kNumSMs * e0) : nullptr;
   // counters (padded to whole 4096-counter scan tiles) and the per-row counts share one memset
-  const size_t cnt_elems = align_up(groups + 1, 4096);
+  const size_t cnt_elems = align_up((rpath && groups_r > groups ? groups_r : groups) + 1, 4096);
   w.cnt_bytes = sizeof(int32_t) * cnt_elems;
   w.clear_bytes = sizeof(int32_t) * (cnt_elems + out_rows);
   w.cnt = (int32_t*)take(w.clear_bytes);
@@ -150,7 +166,9 @@ plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32
             const int64_t* __restrict__ indices, const int64_t* __restrict__ rowidx,
             const int64_t* __restrict__ tableidx, uint32_t* __restrict__ keys,
             int32_t* __restrict__ vals, int32_t* __restrict__ ranks, int32_t* __restrict__ cnt,
-            int32_t* __restrict__ rowcount, uint32_t p2, int32_t num_groups) {
+            int32_t* __restrict__ rowcount, uint32_t p2, int32_t num_groups, uint32_t hp, uint32_t tp0) {
+  // hp != 0: transposed keys (idx % hp) * tp0 + idx / hp  (hp = p1 p2, tp0 = p0; p2 is then p0 too): rows
+  // that share (i1, i2) become a group
   pdl_trigger();
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
   int64_t idx[kPlanItems], t[kPlanItems], row[kPlanItems];
@@ -167,7 +185,8 @@ plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32
     if (n >= nnz) continue;
     const bool ok = idx[k] >= 0 && idx[k] < num_rows && t[k] >= 0 && t[k] < num_tables &&
                     row[k] >= 0 && row[k] < B;
-    const uint32_t key = ok ? (uint32_t)(t[k] * num_rows + idx[k]) : total_rows;  // invalid -> end
+    const int64_t local = hp ? (idx[k] % hp) * tp0 + idx[k] / hp : idx[k];
+    const uint32_t key = ok ? (uint32_t)(t[k] * num_rows + local) : total_rows;  // invalid -> end
     const int32_t gr = ok ? (int32_t)(t[k] * B + row[k]) : 0;
     keys[n] = key;
     vals[n] = gr;
@@ -1429,15 +1448,18 @@ const Entry* find_entry(const TTDev& tt) {
 // workspace is still valid, only the zero-fill is repeated.
 int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                const int64_t* rowidx, const int64_t* tableidx, const SortedWs& w,
-               bool deterministic, float* output, bool zero_only, cudaStream_t stream) {
+               bool deterministic, float* output, bool zero_only, cudaStream_t stream,
+               bool right = false) {
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
-  const int32_t groups = tt.num_tables * tt.p[0] * tt.p[1];
+  const int32_t groups = right ? tt.num_tables * tt.p[1] * tt.p[2] : tt.num_tables * tt.p[0] * tt.p[1];
+  const uint32_t gdiv = (uint32_t)(right ? tt.p[0] : tt.p[2]);   // group = key / gdiv
+  const uint32_t hp = right ? (uint32_t)(tt.p[1] * tt.p[2]) : 0u;
   const int64_t out_rows = (int64_t)tt.num_tables * B;
   const unsigned nblk = (unsigned)ceil_div(nnz, 256 * kPlanItems);
   int32_t* rowcount = output ? w.rowcount : nullptr;
   if (zero_only) {
     prof_begin(K_SORT, stream);
-    bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(0, total_rows, (uint32_t)tt.p[2], groups,
+    bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(0, total_rows, gdiv, groups,
                                                     nullptr, nullptr, nullptr, nullptr, w.rowcount,
                                                     nullptr, nullptr, output, out_rows, tt.D / 4);
     prof_end(K_SORT, stream);
@@ -1448,7 +1470,7 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
   prof_begin(K_PLAN, stream);
   plan_kernel<<<nblk, 256, 0, stream>>>(nnz, B, tt.num_rows, tt.num_tables, total_rows, indices,
                                         rowidx, tableidx, w.keys_in, w.vals_in, w.ranks, w.cnt,
-                                        rowcount, (uint32_t)tt.p[2], groups);
+                                        rowcount, gdiv, groups, hp, (uint32_t)tt.p[0]);
   prof_end(K_PLAN, stream);
   TTG_LAUNCH_CHECK();
   prof_begin(K_SORT, stream);
@@ -1465,7 +1487,7 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
     count_launch(3);
   }
   TTG_CUDA(launch_pdl<2>(bucket_scatter_kernel, dim3(nblk), dim3(256), 0, stream, nnz, total_rows,
-                      (uint32_t)tt.p[2], groups, w.keys_in, w.vals_in, deterministic ? nullptr : w.ranks,
+                      gdiv, groups, w.keys_in, w.vals_in, deterministic ? nullptr : w.ranks,
                       w.base, rowcount, w.skeys, w.srow, output, out_rows, tt.D / 4));
   TTG_LAUNCH_CHECK();
   prof_end(K_SORT, stream);
@@ -1506,6 +1528,23 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
                       output, false, stream);
   if (rc != TTG_OK) return rc;
   return mma_table(tt, mma_plan(w), (flags & TTG_FLAG_TF32) != 0, true, stream);
+}
+
+// tcgen05 kernels (right-grouped): default whenever the shape has them and the batch is dense in groups
+bool use_r(const TTDev& tt, const SortedWs& w, int32_t flags) {
+  return w.tabR != nullptr && !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
+}
+
+RPlan r_plan(const SortedWs& w) {
+  RPlan pl;
+  pl.skeys = w.skeys;
+  pl.srow = w.srow;
+  pl.cnt = w.cnt;
+  pl.base = w.base;
+  pl.tab = w.tabR;
+  pl.S1 = w.S1R;
+  pl.d0parts = w.d0partsR;
+  return pl;
 }
 
 int check_common(const TTDev& tt, int64_t B, int64_t nnz, const char* who) {
@@ -1554,6 +1593,16 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
   const bool zero_only = (flags & TTG_FLAG_PLAN_VALID) != 0;
+  if (use_r(tt, w, flags)) {
+    rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, output,
+                    zero_only, stream, true);
+    if (rc != TTG_OK) return rc;
+    if (!zero_only) {   // otherwise the table of this batch is still in the workspace
+      rc = r_table(tt, r_plan(w), stream);
+      if (rc != TTG_OK) return rc;
+    }
+    return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
+  }
   if (use_mma_fwd(tt, w, flags)) {
     if (zero_only)  // plan and table of this batch are still in the workspace
       rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, false, output, true, stream);
@@ -1639,8 +1688,19 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
     set_error("sorted_backward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
   }
-  const bool plan_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
+  bool plan_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
+  if (use_r(tt, w, flags)) {
+    if (!plan_valid) {   // otherwise the forward that built the plan also built the table
+      rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, nullptr,
+                      false, stream, true);
+      if (rc != TTG_OK) return rc;
+      rc = r_table(tt, r_plan(w), stream);
+      if (rc != TTG_OK) return rc;
+    }
+    return r_backward(tt, nnz, r_plan(w), d_output, dcore, optim, lr, eps, state, (flags & TTG_FLAG_TF32) != 0,
+                      stream);
+  }
   if (use_mma(tt, w, flags)) {
     if (!plan_valid) {  // otherwise the forward that built the plan also built the table
       rc = table_then_plan(tt, B, nnz, indices, rowidx, tableidx, w, flags, nullptr, stream);

@@ -57,7 +57,10 @@ enum {
   TTG_FLAG_TF32 = 8,          /* tensor-core kernels use plain TF32 operands (about 1e-3
                                  relative) instead of the default 3xTF32 split, which keeps
                                  fp32 accuracy (about 3e-7 relative)                    */
-  TTG_FLAG_FFMA = 16          /* fp32 FFMA kernels instead of the tensor-core kernels     */
+  TTG_FLAG_FFMA = 16,         /* fp32 FFMA kernels instead of the tensor-core kernels     */
+  TTG_FLAG_MMA_SYNC = 32      /* the mma.sync (warp-level) tensor-core kernels instead of the
+                                 tcgen05 / tensor-memory kernels (kept as a second
+                                 implementation for the parity tests)                   */
 };
 
 /* TT table description: tt_p_shapes / tt_q_shapes / tt_ranks of the reference. */

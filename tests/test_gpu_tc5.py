@@ -1,0 +1,148 @@
+"""GPU parity tests of the tcgen05 / tensor-memory kernels (csrc/tt_tc5.cu) against the fp64 oracle
+(oracle/tt_oracle.c restates FBTT/tt_embeddings_cuda.cu:967-1081, :421-654) at 1e-5, on the shapes
+the kernels are instantiated for, including BASELINE.json's full batch and index range, and against
+the other two implementations of the library (FFMA kernels, mma.sync kernels).
+
+Tolerance: 1e-5 of the tensor's largest magnitude against the fp64 oracle (north star).
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+DEV = "cuda:0"
+
+SHAPES = {
+    "products": ([125, 140, 140], [4, 5, 5], [16, 16], 2449029),
+    "arxiv": ([55, 55, 56], [4, 4, 8], [16, 16], 169343),
+    "cora": ([14, 14, 14], [4, 4, 8], [16, 16], 2708),
+}
+
+
+def _cores(p, q, r, n_emb, seed, num_tables=1):
+    g = torch.Generator().manual_seed(seed)
+    rr = [1] + list(r) + [1]
+    return [torch.randn(num_tables, p[t], rr[t] * q[t] * rr[t + 1], generator=g) / (n_emb ** 0.25)
+            for t in range(3)]
+
+
+@pytest.fixture
+def te(ttg_lib):
+    import tt_embeddings
+    tt_embeddings.EXTRA_FLAGS = 0
+    yield tt_embeddings
+    tt_embeddings.EXTRA_FLAGS = 0
+
+
+def _fwd(te, shape, cores, idx, row, B, tb=None, num_tables=1, flags=0):
+    p, q, r, _ = shape
+    te.EXTRA_FLAGS = flags
+    try:
+        idx_t = torch.from_numpy(idx).to(DEV)
+        row_t = torch.from_numpy(row).to(DEV)
+        tb_t = torch.zeros_like(idx_t) if tb is None else torch.from_numpy(tb).to(DEV)
+        return te.tt_forward(1000, num_tables, B, int(np.prod(q)), p, q, r, None, idx.size, idx_t, row_t,
+                             tb_t, [c.to(DEV) for c in cores])
+    finally:
+        te.EXTRA_FLAGS = 0
+
+
+@pytest.mark.parametrize("name,nnz", [("cora", 2708), ("cora", 300), ("arxiv", 20000), ("products", 60000)])
+def test_forward_against_oracle(te, name, nnz):
+    shape = SHAPES[name]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 3)
+    rng = np.random.default_rng(1)
+    # dense in groups: ids from a window that holds about nnz / 3 groups
+    hi = min(n_emb, max(nnz, p[1] * p[2] * max(1, nnz // (3 * p[1] * p[2]) + 1)))
+    idx = rng.integers(0, hi, size=nnz).astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    out = _fwd(te, shape, cores, idx, row, nnz)
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+
+
+def test_forward_full_size_products_against_oracle_and_other_kernels(te):
+    """BASELINE config 2: 262,144 distinct ids over the whole index range."""
+    shape = SHAPES["products"]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 5)
+    g = torch.Generator().manual_seed(0)
+    nnz = 262144
+    idx = torch.randperm(n_emb, generator=g)[:nnz].numpy().astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    out = _fwd(te, shape, cores, idx, row, nnz)
+    orc.use_all_host_threads()
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    out_ffma = _fwd(te, shape, cores, idx, row, nnz, flags=16)
+    out_sync = _fwd(te, shape, cores, idx, row, nnz, flags=32)
+    assert float((out - out_ffma).abs().max() / out_ffma.abs().max()) < TOL
+    assert float((out - out_sync).abs().max() / out_sync.abs().max()) < TOL
+    # permutation equivariance and sorted input
+    perm = torch.randperm(nnz, generator=g).numpy()
+    out_p = _fwd(te, shape, cores, np.ascontiguousarray(idx[perm]), row, nnz)
+    assert torch.equal(out_p[0], out[0][torch.from_numpy(perm).to(DEV)])
+
+
+def test_forward_bags_tables_and_invalid_indices(te):
+    """several indices per bag (accumulation), empty bags (zero rows), two tables, out-of-range ids
+    (skipped, as the sorted kernels do), rows in arbitrary order"""
+    shape = SHAPES["cora"]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 9, num_tables=2)
+    rng = np.random.default_rng(4)
+    B, nnz = 700, 4000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = rng.integers(0, B - 50, size=nnz).astype(np.int64)      # the last 50 bags stay empty
+    tb = rng.integers(0, 2, size=nnz).astype(np.int64)
+    out = _fwd(te, shape, cores, idx, row, B, tb=tb, num_tables=2)
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, B, tableidx=tb, num_tables=2)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    assert float(out[:, B - 50:].abs().max()) == 0.0
+    # invalid ids contribute nothing
+    idx_bad = idx.copy()
+    idx_bad[::7] = 14 ** 3 + 5
+    keep = np.ones(nnz, dtype=bool)
+    keep[::7] = False
+    out_bad = _fwd(te, shape, cores, idx_bad, row, B, tb=tb, num_tables=2)
+    want_bad = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx[keep], row[keep], B,
+                              tableidx=tb[keep], num_tables=2)
+    assert rel_err(out_bad.cpu().numpy(), want_bad) < TOL
+
+
+def test_forward_one_giant_group_and_many_tiles(te):
+    """one group with 40,000 rows (more than one round of the kernel's tile list: 512 tiles of 32
+    rows) next to ordinary groups, duplicates included"""
+    shape = SHAPES["cora"]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 11)
+    rng = np.random.default_rng(6)
+    hp = p[1] * p[2]
+    giant = (rng.integers(0, p[0], size=40000) * hp + 77).astype(np.int64)   # all in group h = 77
+    rest = rng.integers(0, n_emb, size=5000).astype(np.int64)
+    idx = np.concatenate([giant, rest])
+    rng.shuffle(idx)
+    nnz = idx.size
+    row = np.arange(nnz, dtype=np.int64)
+    out = _fwd(te, shape, cores, idx, row, nnz)
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+
+
+def test_forward_tf32_mode_stated_bound(te):
+    shape = SHAPES["arxiv"]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 13)
+    rng = np.random.default_rng(8)
+    nnz = 30000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    out = _fwd(te, shape, cores, idx, row, nnz, flags=8)
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
+    assert rel_err(out.cpu().numpy(), want) < 3e-3
