@@ -146,3 +146,123 @@ def test_forward_tf32_mode_stated_bound(te):
     out = _fwd(te, shape, cores, idx, row, nnz, flags=8)
     want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
     assert rel_err(out.cpu().numpy(), want) < 3e-3
+
+
+def _bwd(te, shape, cores, idx, row, dO, tb=None, flags=0, mode="dense", lr=0.1, state=None):
+    p, q, r, _ = shape
+    D = int(np.prod(q))
+    te.EXTRA_FLAGS = flags
+    try:
+        idx_t = torch.from_numpy(idx).to(DEV)
+        row_t = torch.from_numpy(row).to(DEV)
+        tb_t = torch.zeros_like(idx_t) if tb is None else torch.from_numpy(tb).to(DEV)
+        dO_t = torch.from_numpy(dO).to(DEV)
+        if mode == "dense":
+            return te.tt_dense_backward(1000, D, p, q, r, None, idx.size, idx_t, row_t, tb_t, dO_t, cores)
+        if mode == "sgd":
+            return te.tt_sgd_backward(1000, D, lr, p, q, r, None, idx.size, idx_t, row_t, tb_t, dO_t, cores)
+        return te.tt_adagrad_backward(1000, D, lr, 1e-10, p, q, r, None, idx.size, idx_t, row_t, tb_t, dO_t,
+                                      state, cores)
+    finally:
+        te.EXTRA_FLAGS = 0
+
+
+@pytest.mark.parametrize("name,nnz", [("cora", 2708), ("cora", 300), ("arxiv", 20000), ("products", 60000)])
+def test_dense_backward_against_oracle(te, name, nnz):
+    shape = SHAPES[name]
+    p, q, r, n_emb = shape
+    D = int(np.prod(q))
+    cores = _cores(p, q, r, n_emb, 3)
+    rng = np.random.default_rng(2)
+    hi = min(n_emb, max(nnz, p[1] * p[2] * max(1, nnz // (3 * p[1] * p[2]) + 1)))
+    idx = rng.integers(0, hi, size=nnz).astype(np.int64)
+    row = rng.permutation(nnz).astype(np.int64)
+    dO = ((rng.random(size=(1, nnz, D)) - 0.5) * 0.2).astype(np.float32)
+    got = _bwd(te, shape, [c.to(DEV) for c in cores], idx, row, dO)
+    want = orc.tt_backward_dense(p, q, r, [c.numpy() for c in cores], idx, row, dO)
+    for t in range(3):
+        assert rel_err(got[t].cpu().numpy(), want[t]) < TOL, "core %d" % t
+
+
+def test_backward_full_size_products_against_oracle(te):
+    """BASELINE config 2: 262,144 distinct ids over the whole index range; forward first, so the backward
+    runs on the forward's plan and table (TTG_FLAG_PLAN_VALID), then once more on its own."""
+    shape = SHAPES["products"]
+    p, q, r, n_emb = shape
+    D = 100
+    cores = _cores(p, q, r, n_emb, 5)
+    dcores = [c.to(DEV) for c in cores]
+    g = torch.Generator().manual_seed(0)
+    nnz = 262144
+    idx = torch.randperm(n_emb, generator=g)[:nnz].numpy().astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    dO = ((torch.rand(1, nnz, D, generator=g) - 0.5) * 0.2).numpy()
+    idx_t, row_t = torch.from_numpy(idx).to(DEV), torch.from_numpy(row).to(DEV)
+    tb_t, dO_t = torch.zeros_like(idx_t), torch.from_numpy(dO).to(DEV)
+    te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, idx_t, row_t, tb_t, dcores)
+    got = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx_t, row_t, tb_t, dO_t, dcores)
+    orc.use_all_host_threads()
+    want = orc.tt_backward_dense(p, q, r, [c.numpy() for c in cores], idx, row, dO)
+    for t in range(3):
+        assert rel_err(got[t].cpu().numpy(), want[t]) < TOL, "core %d" % t
+    got2 = _bwd(te, shape, dcores, idx, row, dO)
+    for t in range(3):
+        assert rel_err(got2[t].cpu().numpy(), want[t]) < TOL, "core %d (own plan)" % t
+    # the two other implementations of the library agree
+    for fl in (16, 32):
+        other = _bwd(te, shape, dcores, idx, row, dO, flags=fl)
+        for t in range(3):
+            assert rel_err(got[t].cpu().numpy(), other[t].cpu().numpy()) < TOL
+
+
+def test_backward_bags_tables_duplicates_and_giant_group(te):
+    shape = SHAPES["cora"]
+    p, q, r, n_emb = shape
+    D = 128
+    cores = _cores(p, q, r, n_emb, 9, num_tables=2)
+    rng = np.random.default_rng(4)
+    hp = p[1] * p[2]
+    giant = (rng.integers(0, p[0], size=30000) * hp + 77).astype(np.int64)   # one group, heavy duplicates
+    rest = rng.integers(0, n_emb, size=6000).astype(np.int64)
+    idx = np.concatenate([giant, rest])
+    rng.shuffle(idx)
+    nnz, B = idx.size, 5000
+    row = rng.integers(0, B, size=nnz).astype(np.int64)
+    tb = rng.integers(0, 2, size=nnz).astype(np.int64)
+    dO = ((rng.random(size=(2, B, D)) - 0.5) * 0.2).astype(np.float32)
+    got = _bwd(te, shape, [c.to(DEV) for c in cores], idx, row, dO, tb=tb)
+    want = orc.tt_backward_dense(p, q, r, [c.numpy() for c in cores], idx, row, dO, tableidx=tb, num_tables=2)
+    for t in range(3):
+        assert rel_err(got[t].cpu().numpy(), want[t]) < TOL, "core %d" % t
+
+
+def test_fused_sgd_and_adagrad_updates(te):
+    shape = SHAPES["arxiv"]
+    p, q, r, n_emb = shape
+    D = 128
+    rr = [1] + list(r) + [1]
+    cols = [rr[t] * q[t] * rr[t + 1] for t in range(3)]
+    cores = _cores(p, q, r, n_emb, 17)
+    rng = np.random.default_rng(5)
+    nnz = 12000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    dO = ((rng.random(size=(1, nnz, D)) - 0.5) * 0.2).astype(np.float32)
+    grads = orc.tt_backward_dense(p, q, r, [c.numpy() for c in cores], idx, row, dO)
+    dev = [c.to(DEV) for c in cores]
+    _bwd(te, shape, dev, idx, row, dO, mode="sgd", lr=0.1)
+    want = [c.numpy().copy() for c in cores]
+    orc.apply_optimizer(p, cols, "sgd", 0.1, 0.0, want, None, grads)
+    for t in range(3):
+        assert rel_err(dev[t].cpu().numpy(), want[t]) < TOL
+    dev = [c.to(DEV) for c in cores]
+    state = [torch.zeros_like(c) for c in dev]
+    want = [c.numpy().copy() for c in cores]
+    wstate = [np.zeros_like(c) for c in want]
+    for _ in range(2):
+        _bwd(te, shape, dev, idx, row, dO, mode="adagrad", lr=0.05, state=state)
+        g = orc.tt_backward_dense(p, q, r, want, idx, row, dO)
+        orc.apply_optimizer(p, cols, "adagrad", 0.05, 1e-10, want, wstate, g)
+    for t in range(3):
+        assert rel_err(state[t].cpu().numpy(), wstate[t]) < TOL
+        assert rel_err(dev[t].cpu().numpy(), want[t]) < TOL
