@@ -18,6 +18,7 @@ TTG_MAX_PEERS = 8
 PEER_HANDLE_BYTES = 64
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
 FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC, FLAG_TF32, FLAG_FFMA = 1, 2, 4, 8, 16
+FLAG_MMA_SYNC, FLAG_TCGEN05 = 32, 64
 
 
 class Shape(C.Structure):

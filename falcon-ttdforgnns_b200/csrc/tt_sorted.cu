@@ -1530,9 +1530,10 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
   return mma_table(tt, mma_plan(w), (flags & TTG_FLAG_TF32) != 0, true, stream);
 }
 
-// tcgen05 kernels (right-grouped): default whenever the shape has them and the batch is dense in groups
+// tcgen05 kernels (right-grouped): opt-in (TTG_FLAG_TCGEN05), when the shape has them and the batch is dense
+// in groups
 bool use_r(const TTDev& tt, const SortedWs& w, int32_t flags) {
-  return w.tabR != nullptr && !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
+  return w.tabR != nullptr && (flags & TTG_FLAG_TCGEN05) && !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
 }
 
 RPlan r_plan(const SortedWs& w) {

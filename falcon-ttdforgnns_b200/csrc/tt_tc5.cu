@@ -20,6 +20,8 @@
 // magnitude, the same as an fp32 FFMA chain.  TTG_FLAG_TF32 issues hi*hi only.  The accumulator adds
 // with truncation (error grows linearly with the chain), so no accumulation chain here is longer than a
 // few dozen instructions.
+#include <stdlib.h>
+
 #include "tc5.cuh"
 
 namespace ttg {
@@ -30,9 +32,11 @@ using namespace tc5;
 
 constexpr int kWorkWarps = 4;                 // one per TMEM lane quadrant
 constexpr int kThreadsR = (kWorkWarps + 2) * 32;   // + MMA issuer + loader
+constexpr int kThreadsRB = (2 * kWorkWarps + 2) * 32;   // backward: two teams of workers
 constexpr int kTileRows = 32;                 // 128 lanes = 32 rows x 4 pairs
 constexpr int kNB = 4;                        // ring of group operands in shared memory
-constexpr int kMaxTiles = 512;                // tile list per round
+constexpr int kMaxTiles = 512;                // tile list per round (backward)
+constexpr int kFwdTiles = 256;                // tile list per round (forward: several CTAs per SM)
 constexpr uint32_t kFull = 0xffffffffu;
 
 template <int Q1, int Q2>
@@ -93,9 +97,10 @@ __device__ int warp_lower_bound(const int32_t* base, int n, int target, int lane
 
 // Tile list of the next groups of [g, g_hi): groups are cut into tiles of up to 32 rows; a round ends
 // when the list is full.  One warp; state (g, off) = next group and rows of it already listed.
-__device__ int build_tiles(const int32_t* base, int& g, int& off, int g_hi, Tile* tiles, int lane) {
+__device__ int build_tiles(const int32_t* base, int& g, int& off, int g_hi, Tile* tiles, int lane,
+                           int kCap = kMaxTiles) {
   int T = 0;
-  while (g < g_hi && T < kMaxTiles) {
+  while (g < g_hi && T < kCap) {
     const int gg = g + lane;
     int b0 = 0, b1 = 0;
     if (gg < g_hi) {
@@ -111,13 +116,13 @@ __device__ int build_tiles(const int32_t* base, int& g, int& off, int g_hi, Tile
       const int y = __shfl_up_sync(kFull, incl, o);
       if (lane >= o) incl += y;
     }
-    const uint32_t fits = __ballot_sync(kFull, T + incl <= kMaxTiles);
+    const uint32_t fits = __ballot_sync(kFull, T + incl <= kCap);
     const int k = (fits == kFull) ? 32 : (__ffs(~fits) - 1);   // incl is monotone: a prefix of the lanes fits
     if (k == 0) {
       if (T != 0) break;                       // give the group a fresh list
-      // even a fresh list is too short for it: list kMaxTiles full tiles, the rest next round
+      // even a fresh list is too short for it: list kCap full tiles, the rest next round
       const int b0l = __shfl_sync(kFull, b0, 0);
-      for (int i = lane; i < kMaxTiles; i += 32) {
+      for (int i = lane; i < kCap; i += 32) {
         Tile t;
         t.row0 = b0l + i * kTileRows;
         t.n = kTileRows;
@@ -125,8 +130,8 @@ __device__ int build_tiles(const int32_t* base, int& g, int& off, int g_hi, Tile
         t.flags = (i == 0 && off == 0) ? 1 : 0;
         tiles[i] = t;
       }
-      off += kMaxTiles * kTileRows;
-      T = kMaxTiles;
+      off += kCap * kTileRows;
+      T = kCap;
       break;
     }
     if (lane < k && gg < g_hi) {
@@ -220,16 +225,15 @@ struct RSmem {
 };
 
 template <int Q1, int Q2, int TERMS>
-__global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
+__global__ void __launch_bounds__(kThreadsR, 4) r_fwd_kernel(RFwdArgs a) {
   using S = RShape<Q1, Q2>;
-  constexpr int C = S::C, D = S::D, CS = S::kC0Stride;
+  constexpr int C = S::C, D = S::D;
   extern __shared__ __align__(1024) unsigned char smem[];
   // carve
   unsigned char* bring = smem;                                                   // kNB slots
   Tile* tiles = reinterpret_cast<Tile*>(bring + kNB * S::kSlotBytes);
-  float* rowbuf = reinterpret_cast<float*>(tiles + kMaxTiles);                   // [4 warps][8][D]
-  float* core0s = rowbuf + kWorkWarps * 8 * D;                                   // [c0_rows * 4][CS]
-  RSmem* sm = reinterpret_cast<RSmem*>(core0s + (size_t)a.c0_rows * 4 * CS);
+  float* rowbuf = reinterpret_cast<float*>(tiles + kFwdTiles);                   // [4 warps][8][D]
+  RSmem* sm = reinterpret_cast<RSmem*>(rowbuf + kWorkWarps * 8 * D);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_trigger();
@@ -248,12 +252,6 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
   for (int i = tid; i < kNB * S::kSlotBytes / 4; i += kThreadsR) reinterpret_cast<float*>(bring)[i] = 0.f;
   fence_proxy_async();
   if (warp == 0) tmem_alloc(&sm->tmem_base, 128);
-  // core0 is not written by any kernel of this call's chain (see DESIGN: programmatic launches)
-  for (int i = tid; i < a.c0_rows * 16; i += kThreadsR) {   // one float4 per thread and trip
-    const int row = i >> 2, q = i & 3;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.core0) + i);
-    *reinterpret_cast<float4*>(core0s + row * CS + 4 * q) = v;
-  }
   pdl_wait();
   // partition of the groups over the CTAs
   if (warp < 2) {
@@ -276,7 +274,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
 
   while (true) {
     if (warp == 5) {
-      const int T = build_tiles(a.base, g_next, g_off, g_hi, tiles, lane);
+      const int T = build_tiles(a.base, g_next, g_off, g_hi, tiles, lane, kFwdTiles);
       if (lane == 0) {
         sm->ntiles = T;
         sm->more = (g_next < g_hi) ? 1 : 0;
@@ -312,10 +310,11 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
             // key = (table * p1 p2 + h) * p0 + i0
             const uint32_t i0 = key % (uint32_t)a.p0;
             const uint32_t tbl = (a.c0_rows == a.p0) ? 0u : (key / (uint32_t)a.p0) / (uint32_t)a.hp;
-            const float* src = core0s + ((tbl * a.p0 + i0) * 4 + j0) * CS;
+            // core0 (32 KB at products) stays in L1 / L2; no kernel of this call's chain writes it
+            const float4* src = reinterpret_cast<const float4*>(a.core0) + ((size_t)(tbl * a.p0 + i0) * 4 + j0) * 4;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 v = *reinterpret_cast<const float4*>(src + 4 * q);
+              const float4 v = __ldg(src + q);
               hi[4 * q + 0] = __float_as_uint(v.x);
               hi[4 * q + 1] = __float_as_uint(v.y);
               hi[4 * q + 2] = __float_as_uint(v.z);
@@ -362,9 +361,10 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
           }
           __syncwarp();
           const int nrows = min(8, tl.n - warp * 8);
-          for (int rr = 0; rr < nrows; ++rr) {
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
             const int32_t orow = __shfl_sync(kFull, sr, 4 * rr);
-            if (lane < D / 4) {
+            if (rr < nrows && lane < D / 4) {
               float4 val;
               if constexpr (C % 4 == 0) {
                 const int jj = lane / (C / 4), i = lane % (C / 4);
@@ -485,6 +485,19 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_fwd_kernel(RFwdArgs a) {
 // warp 4     issues the tcgen05.mma (12 + 3 per 8 rows, in 3-term mode)
 // warp 5     tile list; streams tr1[h] (bulk copy) and turns it into the c-major operand of G0
 // ---------------------------------------------------------------------------------------------
+#ifdef TTG_R_TIMING
+__device__ long long g_rtime[16];
+#define RT_DECL long long rt_t0 = clock64(), rt_t1;
+#define RT_ADD(i)                \
+  do {                           \
+    rt_t1 = clock64();           \
+    rt_acc[i] += rt_t1 - rt_t0;  \
+    rt_t0 = rt_t1;               \
+  } while (0)
+#else
+#define RT_DECL
+#define RT_ADD(i)
+#endif
 constexpr int kNBG = 4;           // ring of G0 operands
 constexpr int kSubTiles = 2;      // tiles per S1 accumulation chain
 
@@ -510,6 +523,7 @@ struct RBSmem {
   int32_t ntiles;
   int32_t more;
   int32_t i0s[2][kTileRows];
+  int32_t dup[2];
 };
 
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
@@ -520,7 +534,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
-__device__ __forceinline__ void bar_workers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // teams X + T
+__device__ __forceinline__ void bar_x() { asm volatile("bar.sync 2, 128;" ::: "memory"); }      // team X
+__device__ __forceinline__ void bar_t() { asm volatile("bar.sync 3, 128;" ::: "memory"); }      // team T
+// physical word of element (j0, c) of row slot `sl` in a row buffer: D = 128 rows are stored with their 16-byte
+// chunks permuted so that both fills read them without bank conflicts; D = 100 rows linear
+template <int C>
+__device__ __forceinline__ int row_word(int sl, int jj, int c) {
+  if constexpr (C % 4 == 0)
+    return sl * (4 * C) + 4 * (jj * (C / 4) + ((c >> 2) ^ (((sl & 1) << 2) | jj))) + (c & 3);
+  else
+    return sl * (4 * C) + jj * C + c;
+}
 
 // tile flags (backward): 1 first tile of the group, 2 last tile of the group, 4 first tile of an S1 chain,
 // 8 last tile of an S1 chain, 16 the chain adds to an S1 an earlier chain of the group wrote
@@ -533,9 +558,9 @@ __device__ __forceinline__ int bwd_flags(int fwd_flags, int tile_in_group) {
 }
 
 template <int Q1, int Q2, int TERMS>
-__global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
+__global__ void __launch_bounds__(kThreadsRB, 1) r_bwd_kernel(RBwdArgs a) {
   using S = RShape<Q1, Q2>;
-  constexpr int C = S::C, D = S::D, CS = S::kC0Stride;
+  constexpr int C = S::C, D = S::D;
   constexpr int kBsPlane = kTileRows * 256;                     // 32 rows x 64 floats
   constexpr int kBgPlane = 8 * 16 * 16;                         // [c / 4][k1][c % 4]
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -546,15 +571,19 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
   float* tbuf = rowbuf + 2 * kTileRows * D;                     // [32][64]  G0 of the tile, chunk-swizzled
   float* sx = tbuf + kTileRows * 64;                            // [2][4][16][32]
   Tile* tiles = reinterpret_cast<Tile*>(sx + 2 * 4 * 16 * 32);
-  float* core0s = reinterpret_cast<float*>(tiles + kMaxTiles);  // [c0_rows * 4][CS]
-  float* d0s = core0s + (size_t)a.c0_rows * 4 * CS;             // [c0_rows][64]
-  RBSmem* sm = reinterpret_cast<RBSmem*>(d0s + (size_t)a.c0_rows * 64);
+  float* d0s = reinterpret_cast<float*>(tiles + kMaxTiles);     // [c0_rows][64]
+  int32_t* stamp = reinterpret_cast<int32_t*>(d0s + (size_t)a.c0_rows * 64);   // [c0_rows]
+  RBSmem* sm = reinterpret_cast<RBSmem*>(stamp + ((a.c0_rows + 3) & ~3));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef TTG_R_TIMING
+  long long rt_acc[16];
+  for (int i = 0; i < 16; ++i) rt_acc[i] = 0;
+#endif
   pdl_trigger();
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm->a_full[i], kWorkWarps);
+      mbar_init(&sm->a_full[i], 2 * kWorkWarps);
       mbar_init(&sm->d_full[i], 1);
       mbar_init(&sm->s_full[i], 1);
       mbar_init(&sm->s_empty[i], kWorkWarps);
@@ -567,16 +596,11 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
     mbar_init_fence();
   }
   // operands the tensor core may read beyond what a tile writes must be finite: clear them once
-  for (int i = tid; i < (2 * 2 * kBsPlane + kNBG * 2 * kBgPlane) / 16; i += kThreadsR)
+  for (int i = tid; i < (2 * 2 * kBsPlane + kNBG * 2 * kBgPlane) / 16; i += kThreadsRB)
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < a.c0_rows * 16; i += kThreadsR) reinterpret_cast<float4*>(d0s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < a.c0_rows * 16; i += kThreadsRB) reinterpret_cast<float4*>(d0s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   fence_proxy_async();
   if (warp == 0) tmem_alloc(&sm->tmem_base, 512);
-  for (int i = tid; i < a.c0_rows * 16; i += kThreadsR) {
-    const int row = i >> 2, q = i & 3;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(a.core0) + i);
-    *reinterpret_cast<float4*>(core0s + row * CS + 4 * q) = v;
-  }
   pdl_wait();
   if (warp < 2) {
     const int total = ld_dep_s32(a.base + a.num_groups);
@@ -600,7 +624,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
   constexpr uint32_t kColX = 0, kColT = 128, kColG = 256, kColW = 320;
 
   while (true) {
-    if (warp == 5) {
+    if (warp == 2 * kWorkWarps + 1) {
       const int off_before = g_off;
       const int g_before = g_next;
       const int T = build_tiles(a.base, g_next, g_off, g_hi, tiles, lane);
@@ -623,17 +647,9 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
     const int T = sm->ntiles;
     const int more = sm->more;
     if (warp < kWorkWarps) {
-      // ---------------- workers ----------------
+      // ---------------- team X: rows, dO pairs, core0 operand, G0 -> d_core0 ----------------
       const int r = lane >> 2, j0 = lane & 3, slot = warp * 8 + r;
       const uint32_t lane_base = tbase + ((uint32_t)(warp * 32) << 16);
-      // physical word of element (j0, c) of row slot `sl` in a row buffer: D = 128 rows are stored with their
-      // 16-byte chunks permuted so that both fills read them without bank conflicts; D = 100 rows linear
-      auto row_word = [&](int sl, int jj, int c) -> int {
-        if constexpr (C % 4 == 0)
-          return sl * D + 4 * (jj * (C / 4) + ((c >> 2) ^ (((sl & 1) << 2) | jj))) + (c & 3);
-        else
-          return sl * D + jj * C + c;
-      };
       auto load_meta = [&](int t, uint32_t& key, int32_t& orow) {   // key of `slot`, output row of slot 8w + lane % 8
         key = 0;
         orow = 0;
@@ -650,13 +666,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
           const Tile tl = tiles[t];
           float* dst = rowbuf + (size_t)((gt + (uint32_t)t) & 1u) * kTileRows * D;
           const int nrows = min(8, tl.n - warp * 8);
-          for (int rr = 0; rr < nrows; ++rr) {
+          const int cj = (C % 4 == 0) ? lane / (C / 4) : 0, cc = (C % 4 == 0) ? 4 * (lane % (C / 4)) : 4 * lane;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
             const int32_t src_row = __shfl_sync(kFull, orow, rr);
-            if (lane < D / 4) {
-              const int sl = warp * 8 + rr;
-              cp_async16(dst + row_word(sl, lane / (C % 4 == 0 ? C / 4 : D), 4 * (lane % (C % 4 == 0 ? C / 4 : D))),
-                         a.d_output + (size_t)src_row * D + 4 * lane);
-            }
+            if (rr < nrows && lane < D / 4)
+              cp_async16(dst + row_word<C>(warp * 8 + rr, cj, cc), a.d_output + (size_t)src_row * D + 4 * lane);
           }
         }
         cp_async_commit();
@@ -665,25 +680,33 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
         const Tile tl = tiles[t];
         const uint32_t s = (gt + (uint32_t)t) & 1u;
         const float* rows = rowbuf + (size_t)s * kTileRows * D;
+        RT_DECL
         cp_async_wait<0>();
-        // i0 of this warp's slots (also needed by the other warps' G0 pass)
+        RT_ADD(0);
+        // i0 of this warp's slots; a slot whose stamp is overwritten shares its i0 with another slot of the tile
         uint32_t i0 = 0;
         if (slot < tl.n) {
           const uint32_t tbl = (a.c0_rows == a.p0) ? 0u : (key / (uint32_t)a.p0) / (uint32_t)a.hp;
           i0 = tbl * a.p0 + key % (uint32_t)a.p0;
-          if (j0 == 0) sm->i0s[s][slot] = (int32_t)i0;
+          if (j0 == 0) {
+            sm->i0s[s][slot] = (int32_t)i0;
+            stamp[i0] = slot;
+          }
         }
-        bar_workers();                       // every warp's rows of tile t have landed; rowbuf[s ^ 1] is free
+        if (tid == 0) sm->dup[s] = 0;
+        bar_rows();                          // rows of tile t have landed (both teams); rowbuf[s ^ 1] is free
+        RT_ADD(1);
+        if (slot < tl.n && j0 == 0 && stamp[i0] != slot) sm->dup[s] = 1;
         prefetch_rows(t + 1, orow_next);
-        const int nslots = (tl.n + 7) & ~7;
-        // (1) dO pairs: lane (r, j0) <- dO[row][j0 * C .. + C)
+        RT_ADD(2);
         if (warp * 8 < tl.n) {
+          // dO pairs: lane (r, j0) <- dO[row][j0 * C .. + C)
           uint32_t hi[32], lo[32];
           if (slot < tl.n) {
             if constexpr (C % 4 == 0) {
 #pragma unroll
               for (int i = 0; i < C / 4; ++i) {
-                const float4 v = *reinterpret_cast<const float4*>(rows + row_word(slot, j0, 4 * i));
+                const float4 v = *reinterpret_cast<const float4*>(rows + row_word<C>(slot, j0, 4 * i));
                 hi[4 * i + 0] = __float_as_uint(v.x);
                 hi[4 * i + 1] = __float_as_uint(v.y);
                 hi[4 * i + 2] = __float_as_uint(v.z);
@@ -691,7 +714,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
               }
             } else {
 #pragma unroll
-              for (int c = 0; c < 32; ++c) hi[c] = (c < C) ? __float_as_uint(rows[row_word(slot, j0, c)]) : 0u;
+              for (int c = 0; c < 32; ++c) hi[c] = (c < C) ? __float_as_uint(rows[row_word<C>(slot, j0, c)]) : 0u;
             }
           } else {
 #pragma unroll
@@ -703,37 +726,17 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
             for (int c = 0; c < 32; ++c) lo[c] = __float_as_uint(tf32_lo(__uint_as_float(hi[c])));
             st32(lane_base + kColX + s * 64 + 32, lo);
           }
-        }
-        // (2) dO transposed: warp = j0, lane = c, column = row slot
-        {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half * 16 < nslots) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int sl = half * 16 + i;
-                hi[i] = (sl < tl.n && lane < C) ? __float_as_uint(rows[row_word(sl, warp, lane)]) : 0u;
-              }
-              st16(lane_base + kColT + s * 64 + half * 16, hi);
-              if (TERMS == 3) {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
-                st16(lane_base + kColT + s * 64 + 32 + half * 16, lo);
-              }
-            }
-          }
-        }
-        // (3) core0 rows of this warp's slots -> MN-major operand: row k at (k / 4) * 1024 + (n / 32) * 512 +
-        //     (k % 4) * 128 + (((n % 32) / 8) ^ (k % 4)) * 32 + (n % 8) * 4  bytes, n = j0' * 16 + k1
-        if (warp * 8 < tl.n) {
+          RT_ADD(3);
+          // core0 rows of this warp's slots -> MN-major operand: row k at (k / 4) * 1024 + (n / 32) * 512 +
+          // (k % 4) * 128 + (((n % 32) / 8) ^ (k % 4)) * 32 + (n % 8) * 4  bytes, n = j0' * 16 + k1
           unsigned char* plane = bs + (size_t)s * 2 * kBsPlane;
           if (slot < tl.n) {
             const int k = slot;
+            const float4* src = reinterpret_cast<const float4*>(a.core0) + (size_t)i0 * 16 + j0 * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const int ch = j0 * 4 + i;                 // 16-byte chunk of the 64-float row: j0' = ch / 4
-              const float4 v = *reinterpret_cast<const float4*>(core0s + (i0 * 4 + (ch >> 2)) * CS + 4 * (ch & 3));
+              const int ch = j0 * 4 + i;                 // 16-byte chunk of the 64-float row
+              const float4 v = __ldg(src + i);
               const int off = (k >> 2) * 1024 + (ch >> 3) * 512 + (k & 3) * 128 +
                               ((((ch & 7) >> 1) ^ (k & 3)) << 5) + ((ch & 1) << 4);
               *reinterpret_cast<float4*>(plane + off) = v;
@@ -743,17 +746,21 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
             }
           }
           fence_proxy_async();
+          wait_st();
         }
-        wait_st();
+        RT_ADD(5);
         fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm->a_full[s]);
+        RT_ADD(6);
       };
-      auto epilogue = [&](int t, uint32_t chain) {
+      auto epilogue = [&](int t) {
         const Tile tl = tiles[t];
         const uint32_t u = gt + (uint32_t)t, s = u & 1u;
+        RT_DECL
         mbar_wait(&sm->d_full[s], (u >> 1) & 1u);
         fence_after();
+        RT_ADD(7);
         // G0 -> tbuf[slot][j0 * 16 + k1], 16-byte chunks swizzled (ch ^ 2 (j0 >> 1) ^ (slot & 1))
         if (warp * 8 < tl.n) {
           uint32_t v[16];
@@ -767,72 +774,56 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           }
         }
-        bar_workers();
-        // warp w owns j0 = w of this CTA's d_core0 copy: lane = (slot % 8, 4 k1)
+        RT_ADD(8);
+        bar_x();
+        RT_ADD(9);
+        // warp w owns j0 = w of this CTA's d_core0 copy: lane = (slot % 8, 4 k1); slots of a tile have distinct
+        // i0 unless the batch repeats an index (sm->dup): those tiles go one slot at a time
         {
           const int sl = lane >> 2, m = lane & 3;
-          for (int s0 = 0; s0 < tl.n; s0 += 8) {
-            const int sl2 = s0 + sl;
-            const bool on = sl2 < tl.n;
-            const int i0 = on ? sm->i0s[s][sl2] : -1 - sl;
-            // equal i0 in one pass (duplicate indices) would race: take those slots one at a time
-            const uint32_t same = __match_any_sync(kFull, i0);
-            const bool dup = __any_sync(kFull, on && (__popc(same) > 4));
+          const bool dup = sm->dup[s] != 0;
+          float4 g[4];
+          int i0v[4];
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int sl2 = it * 8 + sl;
+            i0v[it] = (sl2 < tl.n) ? sm->i0s[s][sl2] : -1;
             const int ch = (warp * 4 + m) ^ ((warp >> 1) << 1) ^ (sl2 & 1);
-            for (int pass = 0; pass < (dup ? 8 : 1); ++pass) {
-              if (on && (!dup || sl == pass)) {
-                const float4 g = *reinterpret_cast<const float4*>(tbuf + sl2 * 64 + 4 * ch);
-                float4* dst = reinterpret_cast<float4*>(d0s + (size_t)i0 * 64 + warp * 16 + 4 * m);
-                float4 o = *dst;
-                o.x += g.x;
-                o.y += g.y;
-                o.z += g.z;
-                o.w += g.w;
-                *dst = o;
+            if (sl2 < tl.n) g[it] = *reinterpret_cast<const float4*>(tbuf + sl2 * 64 + 4 * ch);
+          }
+          if (!dup) {
+            float4 o[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              if (i0v[it] >= 0) o[it] = *reinterpret_cast<const float4*>(d0s + (size_t)i0v[it] * 64 + warp * 16 + 4 * m);
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+              if (i0v[it] >= 0) {
+                o[it].x += g[it].x;
+                o[it].y += g[it].y;
+                o[it].z += g[it].z;
+                o[it].w += g[it].w;
+                *reinterpret_cast<float4*>(d0s + (size_t)i0v[it] * 64 + warp * 16 + 4 * m) = o[it];
               }
-              if (dup) __syncwarp();
-            }
-            __syncwarp();
+          } else {
+            for (int it = 0; it < 4; ++it)
+              for (int pass = 0; pass < 8; ++pass) {
+                if (i0v[it] >= 0 && sl == pass) {
+                  float4* dst = reinterpret_cast<float4*>(d0s + (size_t)i0v[it] * 64 + warp * 16 + 4 * m);
+                  float4 o = *dst;
+                  o.x += g[it].x;
+                  o.y += g[it].y;
+                  o.z += g[it].z;
+                  o.w += g[it].w;
+                  *dst = o;
+                }
+                __syncwarp();
+              }
           }
         }
-        // end of an S1 chain: diagonal blocks of W -> sx -> S1[h]
-        if (tl.flags & 8) {
-          const uint32_t ss = chain & 1u;
-          mbar_wait(&sm->s_full[ss], (chain >> 1) & 1u);
-          fence_after();
-          uint32_t v[16];
-          ld16(lane_base + kColW + ss * 64 + warp * 16, v);
-          wait_ld();
-          fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm->s_empty[ss]);
-          float* sxs = sx + (size_t)ss * 4 * 16 * 32 + warp * 16 * 32;
-#pragma unroll
-          for (int k1 = 0; k1 < 16; ++k1) sxs[k1 * 32 + lane] = __uint_as_float(v[k1]);
-          bar_workers();
-          // S1[h][k1][c]: 16 C floats, one float4 per thread
-          const int f = warp * 32 + lane;
-          if (f < 16 * C / 4) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int idx = 4 * f + e, k1 = idx / C, c = idx % C;
-              const float* px = sx + (size_t)ss * 4 * 16 * 32 + k1 * 32 + c;
-              o[e] = (px[0] + px[16 * 32]) + (px[2 * 16 * 32] + px[3 * 16 * 32]);
-            }
-            float4* dst = reinterpret_cast<float4*>(a.S1 + (size_t)tl.group * (16 * C)) + f;
-            float4 val = make_float4(o[0], o[1], o[2], o[3]);
-            if (tl.flags & 16) {
-              const float4 old = ld_dep_float4(dst);
-              val.x += old.x;
-              val.y += old.y;
-              val.z += old.z;
-              val.w += old.w;
-            }
-            *dst = val;
-          }
-        }
-        bar_workers();      // tbuf (and i0s[s]) may be rewritten
+        RT_ADD(10);
+        bar_x();      // tbuf (and i0s[s]) may be rewritten
+        RT_ADD(13);
       };
       // keys and output rows are loaded one tile ahead of their use (a dependent global load per tile otherwise)
       uint32_t key_c, key_n, key_nn;
@@ -840,7 +831,6 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
       load_meta(0, key_c, or_c);
       load_meta(1, key_n, or_n);
       prefetch_rows(0, or_c);
-      uint32_t chain = gs;
       if (T > 0) fill(0, key_c, or_n);          // prefetches the rows of tile 1
       load_meta(2, key_nn, or_nn);
       for (int t = 0; t < T; ++t) {
@@ -849,14 +839,102 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
         int32_t or_3;
         load_meta(t + 3, key_3, or_3);
         if (t + 1 < T) fill(t + 1, key_n, or_nn);   // prefetches the rows of tile t + 2
-        epilogue(t, chain);
-        if (tiles[t].flags & 8) ++chain;
+        epilogue(t);
         key_n = key_nn;
         key_nn = key_3;
         or_nn = or_3;
       }
       cp_async_wait<0>();
-    } else if (warp == kWorkWarps) {
+    } else if (warp < 2 * kWorkWarps) {
+      // ---------------- team T: dO transposed, S1 ----------------
+      const int qd = warp - kWorkWarps;              // TMEM lane quadrant = j0
+      const uint32_t lane_base = tbase + ((uint32_t)(qd * 32) << 16);
+      // element offsets of this thread's float4 of S1[h] ([k1][c], 16 C floats) inside sx
+      const int f = qd * 32 + lane;
+      int sxo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = 4 * f + e;
+        sxo[e] = (idx / C) * 32 + idx % C;
+      }
+      auto fill = [&](int t) {
+        const Tile tl = tiles[t];
+        const uint32_t s = (gt + (uint32_t)t) & 1u;
+        const float* rows = rowbuf + (size_t)s * kTileRows * D;
+        RT_DECL
+        bar_rows();
+        RT_ADD(1);
+        const int nslots = (tl.n + 7) & ~7;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half * 16 < nslots) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int sl = half * 16 + i;
+              hi[i] = (sl < tl.n && lane < C) ? __float_as_uint(rows[row_word<C>(sl, qd, lane)]) : 0u;
+            }
+            st16(lane_base + kColT + s * 64 + half * 16, hi);
+            if (TERMS == 3) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) lo[i] = __float_as_uint(tf32_lo(__uint_as_float(hi[i])));
+              st16(lane_base + kColT + s * 64 + 32 + half * 16, lo);
+            }
+          }
+        }
+        RT_ADD(4);
+        wait_st();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->a_full[s]);
+        RT_ADD(6);
+      };
+      auto epilogue = [&](int t, uint32_t chain) {
+        const Tile tl = tiles[t];
+        if (!(tl.flags & 8)) return;
+        // end of an S1 chain: diagonal blocks of W -> sx -> S1[h]
+        const uint32_t ss = chain & 1u;
+        RT_DECL
+        mbar_wait(&sm->s_full[ss], (chain >> 1) & 1u);
+        fence_after();
+        RT_ADD(11);
+        uint32_t v[16];
+        ld16(lane_base + kColW + ss * 64 + qd * 16, v);
+        wait_ld();
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm->s_empty[ss]);
+        float* sxs = sx + (size_t)ss * 4 * 16 * 32 + qd * 16 * 32;
+#pragma unroll
+        for (int k1 = 0; k1 < 16; ++k1) sxs[k1 * 32 + lane] = __uint_as_float(v[k1]);
+        bar_t();
+        if (f < 16 * C / 4) {
+          const float* px = sx + (size_t)ss * 4 * 16 * 32;
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = (px[sxo[e]] + px[sxo[e] + 16 * 32]) + (px[sxo[e] + 2 * 16 * 32] + px[sxo[e] + 3 * 16 * 32]);
+          float4* dst = reinterpret_cast<float4*>(a.S1 + (size_t)tl.group * (16 * C)) + f;
+          float4 val = make_float4(o[0], o[1], o[2], o[3]);
+          if (tl.flags & 16) {
+            const float4 old = ld_dep_float4(dst);
+            val.x += old.x;
+            val.y += old.y;
+            val.z += old.z;
+            val.w += old.w;
+          }
+          *dst = val;
+        }
+        RT_ADD(12);
+      };
+      uint32_t chain = gs;
+      if (T > 0) fill(0);
+      for (int t = 0; t < T; ++t) {
+        if (t + 1 < T) fill(t + 1);
+        epilogue(t, chain);
+        if (tiles[t].flags & 8) ++chain;
+      }
+    } else if (warp == 2 * kWorkWarps) {
       // ---------------- MMA issuer ----------------
       const uint32_t lead = elect_one();
       const uint32_t tb = __shfl_sync(kFull, tbase, 0);
@@ -872,10 +950,12 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
         const int n = __shfl_sync(kFull, tiles[t].n, 0);
         const uint32_t u = gt0 + (uint32_t)t, s = u & 1u;
         const uint32_t gslot = q % kNBG, ss = chain & 1u;
+        RT_DECL
         if (flags & 1) mbar_wait(&sm->bg_full[gslot], (q / kNBG) & 1u);
         if ((flags & 4) && chain >= 2) mbar_wait(&sm->s_empty[ss], ((chain >> 1) - 1) & 1u);
         mbar_wait(&sm->a_full[s], (u >> 1) & 1u);
         fence_after();
+        RT_ADD(14);
         const uint32_t xhi = tb + kColX + s * 64, xlo = xhi + 32;
         const uint32_t thi = tb + kColT + s * 64, tlo = thi + 32;
         const uint32_t dg = tb + kColG + s * 16, dw = tb + kColW + ss * 64;
@@ -915,6 +995,7 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
           if (flags & 2) commit(&sm->bg_empty[gslot]);
         }
         __syncwarp();
+        RT_ADD(15);
         if (flags & 8) ++chain;
         if (flags & 2) ++q;
       }
@@ -986,10 +1067,14 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
     __syncthreads();
     if (!more) break;
   }
+#ifdef TTG_R_TIMING
+  if (blockIdx.x == 3 && lane == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(&g_rtime[i]), (unsigned long long)rt_acc[i]);
+#endif
   // this CTA's share of d_core0
   {
     float4* dst = reinterpret_cast<float4*>(a.d0parts + (size_t)blockIdx.x * a.c0_rows * 64);
-    for (int i = tid; i < a.c0_rows * 16; i += kThreadsR) dst[i] = reinterpret_cast<const float4*>(d0s)[i];
+    for (int i = tid; i < a.c0_rows * 16; i += kThreadsRB) dst[i] = reinterpret_cast<const float4*>(d0s)[i];
   }
   fence_before();
   __syncthreads();
@@ -1000,115 +1085,189 @@ __global__ void __launch_bounds__(kThreadsR, 1) r_bwd_kernel(RBwdArgs a) {
 // cores: the two dense reductions over S1 (groups no row touched count as zero and are not read)
 //   role A, CTA = (table, i1):  d_core1[i1][k1, j1, k2] = sum_i2 sum_j2 S1[(i1, i2)][k1, (j1, j2)] core2[i2][k2, j2]
 //   role B, CTA = (table, i2):  d_core2[i2][k2, j2]     = sum_i1 sum_(k1, j1) core1[i1][k1, j1, k2] S1[(i1, i2)][k1, (j1, j2)]
-// fp32 FFMA, fixed summation order, no atomics.  (250 MFLOP in all; the time is the 2 x 31 MB of S1 from L2.)
+// fp32 FFMA with register tiles (A: 16 k2 per thread, B: 4 k2 per thread), the S1 tiles double-buffered through
+// shared memory by cp.async, fixed summation order, no atomics.  250 MFLOP in all.
 // ---------------------------------------------------------------------------------------------
 template <int Q1, int Q2, int R2>
 __global__ void __launch_bounds__(256) r_cores_kernel(TTDev tt, const float* S1, const int32_t* cnt,
                                                       float* __restrict__ dcore1, float* __restrict__ dcore2) {
-  constexpr int C = Q1 * Q2, R1 = 16, IMG = R1 * C;
-  constexpr int U = 4;                                    // groups staged per trip
-  __shared__ __align__(16) float s1s[U][IMG];
-  __shared__ __align__(16) float os[U][R1 * Q1 * R2 > R2 * Q2 * 8 ? R1 * Q1 * R2 : R2 * Q2 * 8];
-  __shared__ int32_t cs[U];
+  constexpr int C = Q1 * Q2, R1 = 16, IMG = R1 * C, NKJ = R1 * Q1;
+  constexpr int NGA = 3;                     // role A: i2 handled side by side (3 x 80 threads)
+  constexpr int NGB = 240 / (R2 / 4 * Q2);   // role B: i1 handled side by side (12 x 20 / 7 x 32 threads)
+  static_assert(NGA * NKJ <= 256 && NGB * (R2 / 4 * Q2) <= 256 && NGA * R2 * Q2 <= 512, "thread layout");
+  constexpr int kBufA = 2 * NGA * IMG, kBufB = 2 * NGB * IMG;
+  constexpr int kRedA = NGA * NKJ * R2, kRedB = NGB * R2 * Q2;
+  constexpr int kFloats = (kBufA + 2 * NGA * R2 * Q2 + kRedA) > (kBufB + kRedB) ? (kBufA + 2 * NGA * R2 * Q2 + kRedA)
+                                                                                : (kBufB + kRedB);
+  __shared__ __align__(16) float sh[kFloats];
+  __shared__ int32_t cnts[512];
   pdl_trigger();
   pdl_wait();
   const int tid = threadIdx.x;
   const int nb1 = tt.num_tables * tt.p[1];
   if ((int)blockIdx.x < nb1) {
-    // ---- role A: thread = (k1, j1, 4 k2) of d_core1[i1]; 320 float4 outputs, 256 threads: two passes ----
+    // ---- role A ----
     const int ti1 = blockIdx.x, table = ti1 / tt.p[1];
     const float* core2 = tt.core[2] + (size_t)table * tt.p[2] * (R2 * Q2);
     const size_t h0 = (size_t)ti1 * tt.p[2];
-    constexpr int NO = R1 * Q1 * R2 / 4;                  // float4 outputs
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int i2 = 0; i2 < tt.p[2]; i2 += U) {
-      __syncthreads();
-      if (tid < U) cs[tid] = (i2 + tid < tt.p[2]) ? ld_dep_s32(cnt + h0 + i2 + tid) : 0;
-      __syncthreads();
-      for (int i = tid; i < U * IMG / 4; i += 256) {
-        const int u = i / (IMG / 4), e = i % (IMG / 4);
-        if (cs[u] > 0)
-          reinterpret_cast<float4*>(s1s[u])[e] = ld_dep_float4(S1 + (h0 + i2 + u) * IMG + 4 * e);
+    float* s1s = sh;                              // [2][NGA][IMG]
+    float* c2t = sh + kBufA;                      // [2][NGA][Q2][R2]
+    float* red = c2t + 2 * NGA * R2 * Q2;         // [NGA][NKJ][R2]
+    for (int i = tid; i < tt.p[2]; i += 256) cnts[i] = cnt[h0 + i];
+    __syncthreads();
+    const int grp = tid / NKJ, kj = tid % NKJ;    // kj = k1 * Q1 + j1
+    const bool worker = tid < NGA * NKJ;
+    const int ntrips = (tt.p[2] + NGA - 1) / NGA;
+    auto stage = [&](int trip, int buf) {
+      for (int i = tid; i < NGA * (IMG / 4); i += 256) {
+        const int u = i / (IMG / 4), e = i % (IMG / 4), i2 = trip * NGA + u;
+        float* dst = s1s + ((size_t)buf * NGA + u) * IMG + 4 * e;
+        if (i2 < tt.p[2] && cnts[i2] > 0)
+          cp_async16(dst, S1 + (h0 + i2) * IMG + 4 * e);
+        else
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // core2[i2 .. i2 + U) rows: [k2][j2]
-      for (int i = tid; i < U * R2 * Q2; i += 256) {
-        const int u = i / (R2 * Q2), e = i % (R2 * Q2);
-        os[u][e] = (i2 + u < tt.p[2]) ? __ldg(core2 + (size_t)(i2 + u) * (R2 * Q2) + e) : 0.f;
+      cp_async_commit();
+    };
+    // the trip's core2 rows, up to two elements per thread (NGA * R2 * Q2 <= 512), kept in registers while the
+    // previous trip is computed and then stored transposed: [j2][k2]
+    auto load_c2 = [&](int trip) -> float2 {
+      float v[2] = {0.f, 0.f};
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int x = tid + w * 256;
+        if (x < NGA * R2 * Q2) {
+          const int u = x / (R2 * Q2), e = x % (R2 * Q2), i2 = trip * NGA + u;
+          if (i2 < tt.p[2]) v[w] = __ldg(core2 + (size_t)i2 * (R2 * Q2) + e);
+        }
+      }
+      return make_float2(v[0], v[1]);
+    };
+    auto store_c2 = [&](int buf, float2 v) {
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int x = tid + w * 256;
+        if (x < NGA * R2 * Q2) {
+          const int u = x / (R2 * Q2), e = x % (R2 * Q2);
+          c2t[((size_t)buf * NGA + u) * (R2 * Q2) + (e % Q2) * R2 + e / Q2] = w ? v.y : v.x;
+        }
+      }
+    };
+    float acc[R2];
+#pragma unroll
+    for (int i = 0; i < R2; ++i) acc[i] = 0.f;
+    stage(0, 0);
+    store_c2(0, load_c2(0));
+    for (int trip = 0; trip < ntrips; ++trip) {
+      const int buf = trip & 1;
+      float2 c2n = make_float2(0.f, 0.f);
+      if (trip + 1 < ntrips) {
+        stage(trip + 1, buf ^ 1);
+        c2n = load_c2(trip + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
+      if (worker) {
+        const float* st = s1s + ((size_t)buf * NGA + grp) * IMG + (kj / Q1) * C + (kj % Q1) * Q2;
+        const float* ct = c2t + ((size_t)buf * NGA + grp) * (R2 * Q2);
 #pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int o = tid + pass * 256;
-        if (o < NO) {
-          const int k2q = o % (R2 / 4), kj = o / (R2 / 4);          // kj = k1 * Q1 + j1
-          const int k1 = kj / Q1, j1 = kj % Q1;
+        for (int j2 = 0; j2 < Q2; ++j2) {
+          const float sv = st[j2];
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (cs[u] > 0) {
-#pragma unroll
-              for (int j2 = 0; j2 < Q2; ++j2) {
-                const float sv = s1s[u][k1 * C + j1 * Q2 + j2];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[pass][e] = fmaf(sv, os[u][(4 * k2q + e) * Q2 + j2], acc[pass][e]);
-              }
-            }
+          for (int k4 = 0; k4 < R2 / 4; ++k4) {
+            const float4 cv = *reinterpret_cast<const float4*>(ct + j2 * R2 + 4 * k4);
+            acc[4 * k4 + 0] = fmaf(sv, cv.x, acc[4 * k4 + 0]);
+            acc[4 * k4 + 1] = fmaf(sv, cv.y, acc[4 * k4 + 1]);
+            acc[4 * k4 + 2] = fmaf(sv, cv.z, acc[4 * k4 + 2]);
+            acc[4 * k4 + 3] = fmaf(sv, cv.w, acc[4 * k4 + 3]);
           }
         }
       }
+      __syncthreads();
+      if (trip + 1 < ntrips) store_c2(buf ^ 1, c2n);
     }
+    if (worker) {
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-      const int o = tid + pass * 256;
-      if (o < NO)
-        reinterpret_cast<float4*>(dcore1 + (size_t)ti1 * (R1 * Q1 * R2))[o] =
-            make_float4(acc[pass][0], acc[pass][1], acc[pass][2], acc[pass][3]);
+      for (int k4 = 0; k4 < R2 / 4; ++k4)
+        *reinterpret_cast<float4*>(red + ((size_t)grp * NKJ + kj) * R2 + 4 * k4) =
+            make_float4(acc[4 * k4], acc[4 * k4 + 1], acc[4 * k4 + 2], acc[4 * k4 + 3]);
+    }
+    __syncthreads();
+    for (int o = tid; o < NKJ * R2 / 4; o += 256) {
+      float4 v = reinterpret_cast<const float4*>(red)[o];
+#pragma unroll
+      for (int g = 1; g < NGA; ++g) {
+        const float4 w = reinterpret_cast<const float4*>(red + (size_t)g * NKJ * R2)[o];
+        v.x += w.x;
+        v.y += w.y;
+        v.z += w.z;
+        v.w += w.w;
+      }
+      reinterpret_cast<float4*>(dcore1 + (size_t)ti1 * (NKJ * R2))[o] = v;
     }
   } else {
-    // ---- role B: thread = (k2, j2, slice of k1 (8 slices of 2)); partial sums reduced through shared memory ----
+    // ---- role B ----
+    constexpr int TPG = R2 / 4 * Q2;              // threads per group: (4 k2, j2)
     const int ti2 = blockIdx.x - nb1, table = ti2 / tt.p[2], i2 = ti2 % tt.p[2];
-    const float* core1 = tt.core[1] + (size_t)table * tt.p[1] * (R1 * Q1 * R2);
-    constexpr int NO = R2 * Q2;                           // 80 / 128 outputs
-    const int o = tid % 128, sl = tid / 128;              // two k1 halves when NO <= 128
-    const int k2 = o / Q2, j2 = o % Q2;
-    float acc = 0.f;
-    for (int i1 = 0; i1 < tt.p[1]; i1 += U) {
-      __syncthreads();
-      if (tid < U)
-        cs[tid] = (i1 + tid < tt.p[1]) ? ld_dep_s32(cnt + ((size_t)table * tt.p[1] + i1 + tid) * tt.p[2] + i2) : 0;
-      __syncthreads();
-      for (int i = tid; i < U * IMG / 4; i += 256) {
-        const int u = i / (IMG / 4), e = i % (IMG / 4);
-        if (cs[u] > 0)
-          reinterpret_cast<float4*>(s1s[u])[e] =
-              ld_dep_float4(S1 + (((size_t)table * tt.p[1] + i1 + u) * tt.p[2] + i2) * IMG + 4 * e);
+    const float* core1 = tt.core[1] + (size_t)table * tt.p[1] * (NKJ * R2);
+    float* s1s = sh;                              // [2][NGB][IMG]
+    float* red = sh + kBufB;                      // [NGB][R2 * Q2]
+    for (int i = tid; i < tt.p[1]; i += 256) cnts[i] = cnt[((size_t)table * tt.p[1] + i) * tt.p[2] + i2];
+    __syncthreads();
+    const int grp = tid / TPG, k2q = (tid % TPG) / Q2, j2 = tid % Q2;
+    const bool worker = tid < NGB * TPG;
+    const int ntrips = (tt.p[1] + NGB - 1) / NGB;
+    auto stage = [&](int trip, int buf) {
+      for (int i = tid; i < NGB * (IMG / 4); i += 256) {
+        const int u = i / (IMG / 4), e = i % (IMG / 4), i1 = trip * NGB + u;
+        float* dst = s1s + ((size_t)buf * NGB + u) * IMG + 4 * e;
+        if (i1 < tt.p[1] && cnts[i1] > 0)
+          cp_async16(dst, S1 + (((size_t)table * tt.p[1] + i1) * tt.p[2] + i2) * IMG + 4 * e);
+        else
+          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int i = tid; i < U * (R1 * Q1 * R2 / 4); i += 256) {
-        const int u = i / (R1 * Q1 * R2 / 4), e = i % (R1 * Q1 * R2 / 4);
-        if (cs[u] > 0)
-          reinterpret_cast<float4*>(os[u])[e] = ld_dep_float4(core1 + (size_t)(i1 + u) * (R1 * Q1 * R2) + 4 * e);
+      cp_async_commit();
+    };
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    stage(0, 0);
+    for (int trip = 0; trip < ntrips; ++trip) {
+      const int buf = trip & 1;
+      if (trip + 1 < ntrips) {
+        stage(trip + 1, buf ^ 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
-      if (o < NO) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (cs[u] > 0) {
-            const float* c1 = os[u] + k2;
-#pragma unroll
-            for (int kk = 0; kk < R1 / 2; ++kk) {
-              const int k1 = sl * (R1 / 2) + kk;
-#pragma unroll
-              for (int j1 = 0; j1 < Q1; ++j1)
-                acc = fmaf(c1[(k1 * Q1 + j1) * R2], s1s[u][k1 * C + j1 * Q2 + j2], acc);
-            }
-          }
+      const int i1 = trip * NGB + grp;
+      if (worker && i1 < tt.p[1] && cnts[i1] > 0) {
+        const float* st = s1s + ((size_t)buf * NGB + grp) * IMG + j2;
+        const float4* c1 = reinterpret_cast<const float4*>(core1 + (size_t)i1 * (NKJ * R2)) + k2q;
+#pragma unroll 8
+        for (int t = 0; t < NKJ; ++t) {           // t = k1 * Q1 + j1
+          const float4 cv = __ldg(c1 + t * (R2 / 4));
+          const float sv = st[(t / Q1) * C + (t % Q1) * Q2];
+          acc[0] = fmaf(cv.x, sv, acc[0]);
+          acc[1] = fmaf(cv.y, sv, acc[1]);
+          acc[2] = fmaf(cv.z, sv, acc[2]);
+          acc[3] = fmaf(cv.w, sv, acc[3]);
         }
       }
+      __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) red[grp * (R2 * Q2) + (4 * k2q + e) * Q2 + j2] = acc[e];
     }
     __syncthreads();
-    float* red = &os[0][0];
-    if (o < NO) red[sl * 128 + o] = acc;
-    __syncthreads();
-    if (tid < NO) dcore2[(size_t)ti2 * NO + tid] = red[tid] + red[128 + tid];
+    if (tid < R2 * Q2) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < NGB; ++g) v += red[g * (R2 * Q2) + tid];
+      dcore2[(size_t)ti2 * (R2 * Q2) + tid] = v;
+    }
   }
 }
 
@@ -1122,8 +1281,9 @@ namespace {
 template <int Q1, int Q2>
 size_t r_fwd_smem(int c0_rows) {
   using S = RShape<Q1, Q2>;
-  return (size_t)kNB * S::kSlotBytes + sizeof(Tile) * kMaxTiles + sizeof(float) * kWorkWarps * 8 * S::D +
-         sizeof(float) * (size_t)c0_rows * 4 * S::kC0Stride + sizeof(RSmem) + 64;
+  (void)c0_rows;
+  return (size_t)kNB * S::kSlotBytes + sizeof(Tile) * kFwdTiles + sizeof(float) * kWorkWarps * 8 * S::D +
+         sizeof(RSmem) + 64;
 }
 
 template <int Q1, int Q2>
@@ -1162,7 +1322,8 @@ int r_fwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, c
   const size_t smem = r_fwd_smem<Q1, Q2>(a.c0_rows);
   auto kern = r_fwd_kernel<Q1, Q2, TERMS>;
   TTG_ENSURE_SMEM(kern, smem);
-  int64_t grid = kNumSMs;
+  static const int cps = [] { const char* v = getenv("TTG_R_CPS"); return v ? atoi(v) : 4; }();
+  int64_t grid = (int64_t)kNumSMs * cps;
   if (grid * 64 > nnz) grid = ceil_div(nnz, 64);
   prof_begin(K_FWD, stream);
   TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreadsR), smem, stream, a));
@@ -1176,7 +1337,7 @@ size_t r_bwd_smem(int c0_rows) {
   using S = RShape<Q1, Q2>;
   return (size_t)2 * 2 * kTileRows * 256 + (size_t)kNBG * 2 * 2048 + (size_t)kNB * S::kSlotBytes +
          sizeof(float) * (2 * kTileRows * S::D + kTileRows * 64 + 2 * 4 * 16 * 32) + sizeof(Tile) * kMaxTiles +
-         sizeof(float) * (size_t)c0_rows * (4 * S::kC0Stride + 64) + sizeof(RBSmem) + 64;
+         sizeof(float) * (size_t)c0_rows * 64 + sizeof(int32_t) * ((c0_rows + 3) & ~3) + sizeof(RBSmem) + 64;
 }
 
 template <int Q1, int Q2, int TERMS>
@@ -1203,7 +1364,7 @@ int r_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_o
   if (grid * 64 > nnz) grid = ceil_div(nnz, 64);
   *nparts = (int)grid;
   prof_begin(K_BWD_ROWS, stream);
-  TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreadsR), smem, stream, a));
+  TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreadsRB), smem, stream, a));
   prof_end(K_BWD_ROWS, stream);
   TTG_LAUNCH_CHECK();
   const int nb = tt.num_tables * (tt.p[1] + tt.p[2]);
@@ -1237,6 +1398,7 @@ const REntry kREntries[] = {
 
 const REntry* find_r(const TTDev& tt) {
   if (tt.T != 3 || tt.q[0] != 4 || tt.r[1] != 16 || tt.r[2] != 16) return nullptr;
+  if (tt.p[1] > 512 || tt.p[2] > 512) return nullptr;   // cores kernel: per-CTA row counters in shared memory
   for (const REntry& e : kREntries)
     if (e.q1 == tt.q[1] && e.q2 == tt.q[2]) {
       if (e.fwd_smem(tt.num_tables * tt.p[0]) > 220 * 1024 || e.bwd_smem(tt.num_tables * tt.p[0]) > 220 * 1024)
@@ -1247,6 +1409,17 @@ const REntry* find_r(const TTDev& tt) {
 }
 
 }  // namespace
+
+#ifdef TTG_R_TIMING
+extern "C" void ttg_r_timing(long long* out, int reset) {
+  if (reset) {
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_rtime, z, sizeof(z));
+  } else {
+    cudaMemcpyFromSymbol(out, g_rtime, sizeof(long long) * 16);
+  }
+}
+#endif
 
 bool r_supported(const TTDev& tt) { return find_r(tt) != nullptr; }
 

@@ -58,9 +58,12 @@ enum {
                                  relative) instead of the default 3xTF32 split, which keeps
                                  fp32 accuracy (about 3e-7 relative)                    */
   TTG_FLAG_FFMA = 16,         /* fp32 FFMA kernels instead of the tensor-core kernels     */
-  TTG_FLAG_MMA_SYNC = 32      /* the mma.sync (warp-level) tensor-core kernels instead of the
-                                 tcgen05 / tensor-memory kernels (kept as a second
-                                 implementation for the parity tests)                   */
+  TTG_FLAG_MMA_SYNC = 32,     /* force the mma.sync (warp-level) tensor-core kernels: the default,
+                                 the flag exists so that a caller can name it           */
+  TTG_FLAG_TCGEN05 = 64       /* the tcgen05 / tensor-memory kernels (csrc/tt_tc5.cu; q0 = 4, ranks
+                                 16,16, batch dense in (i1, i2) groups): same results, measured
+                                 slower than the mma.sync kernels on B200 at the BASELINE batch
+                                 (DESIGN.md section 4b), hence opt-in                    */
 };
 
 /* TT table description: tt_p_shapes / tt_q_shapes / tt_ranks of the reference. */
