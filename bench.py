@@ -16,7 +16,12 @@ cores.  Prints ONE JSON line (rank 0).
              indices / offsets copied from pinned host memory and the scalar loss read back every
              step
   roofline   dominant kernel, algorithmic bytes / CUDA-event duration vs the measured HBM peak
-  cpu_baseline / --impl reference : the oracle's C port of the same step on the host cores
+  cpu_baseline / --impl reference : the oracle's C port of the same step on the host cores, same rows per step
+  sage / config3 / papers : sub-records of the same line -- the GraphSAGE epoch of BASELINE configs 2 and 3
+             (bench_sage.sage_epoch_record: strong scaling over the N ranks, its own clock sample) and the
+             TT step at the papers100M shape (config 5); `sage_epoch_s` repeats the config-2 epoch time at
+             the top level.  --no-extra skips them.
+  replicas_bit_identical (N > 1): checksums of the cores of all ranks after the timed steps
 
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 L2: four batches are rotated; one step touches 212 MB (> 126 MB L2), the rotation 850 MB.
@@ -153,7 +158,7 @@ def run_reference(args, shape):
     world, rank, _ = dist_env()
     if rank != 0:
         return
-    rows = args.cpu_rows
+    rows = args.cpu_rows or min(args.nnz, shape["n"])      # same config as the GPU arm
     rate, sec, threads = cpu_step_rate(shape, rows, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "rows/s", "n_gpus": args.gpus,
@@ -163,7 +168,8 @@ def run_reference(args, shape):
         "config": {"workload": workload_name(args), "rows_per_step": rows,
                    "note": "the reference has no CPU implementation of this path (CUDA only); "
                            "this is the oracle's C port of FBTT tt_forward + tt_sgd_backward on "
-                           "all host threads, on a bounded sample of the workload"},
+                           "all host threads, the same rows per step as the GPU arm; under torchrun "
+                           "rank 0 alone runs it (one CPU job whatever N is)"},
         "cpu_baseline": {"value": rate, "unit": "rows/s", "cores": threads, "kind": "port",
                          "sample": "%d rows per step" % rows},
         "e2e": {"value": rate, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -224,6 +230,108 @@ def workload_name(args):
 # --------------------------------------------------------------------------------------------
 # ours
 # --------------------------------------------------------------------------------------------
+class _DotLoss(torch.autograd.Function):
+    """loss = <out, target>, the cheapest loss whose gradient (d_output = target) is arbitrary: one pass over
+    `out` forward, and the backward hands `target` itself to the embedding (no multiply by the incoming 1.0:
+    round 1 spent 98 us of a 331 us step in the benchmark's own loss arithmetic)."""
+
+    @staticmethod
+    def forward(ctx, out, target):
+        ctx.target = target
+        ctx.shape = out.shape
+        return torch.dot(out.reshape(-1), target)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return ctx.target.view(ctx.shape), None
+
+
+def tt_subrecord(shape_name, nnz, steps, warmup, world, rank, dev, exchange):
+    """The same fwd + bwd + SGD step at another BASELINE shape (config 5: papers100M shape), raw C-ABI ops,
+    eager launches, CUDA events, max over ranks; a sub-record of the JSON line."""
+    import torch.distributed as dist
+    import dp
+    import tt_embeddings as te
+    shape = SHAPES[shape_name]
+    p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
+    rr = [1] + ranks + [1]
+    D = int(np.prod(q))
+    nnz = min(nnz, N)
+    g = torch.Generator().manual_seed(77)
+    cores = [(torch.randn(1, p[t], rr[t] * q[t] * rr[t + 1], generator=g) / np.sqrt(N)).to(dev) for t in range(3)]
+    g = torch.Generator().manual_seed(2000 + rank)
+    # distinct ids over the whole range (ids beyond 2^24 and 2^31 / 4 at papers shape)
+    idx = []
+    for _ in range(2):
+        u = torch.randint(0, N, (nnz + nnz // 8,), generator=g).unique()
+        idx.append(u[torch.randperm(u.numel(), generator=g)][:nnz])       # distinct, unsorted
+    nn = min(int(i.numel()) for i in idx)
+    idx = [i[:nn].contiguous().to(dev) for i in idx]
+    rowidx = torch.arange(nn, device=dev)
+    tableidx = torch.zeros(nn, dtype=torch.int64, device=dev)
+    d_out = [((torch.rand(1, nn, D, generator=g) - 0.5) * 0.2).to(dev) for _ in range(2)]
+    xchg = None
+    if world > 1 and exchange == "peer":
+        try:
+            xchg = dp.PeerExchange(cores)
+        except Exception:
+            xchg = None
+
+    def step(k):
+        te.tt_forward(1000, 1, nn, D, p, q, rr, None, nn, idx[k], rowidx, tableidx, cores)
+        if world == 1:
+            te.tt_sgd_backward(1000, D, LR, p, q, rr, None, nn, idx[k], rowidx, tableidx, d_out[k], cores)
+        else:
+            dc = te.tt_dense_backward(1000, D, p, q, rr, None, nn, idx[k], rowidx, tableidx, d_out[k], cores)
+            if xchg is not None:
+                xchg.step(dc, cores, "sgd", LR)
+            else:
+                dp.apply_optimizer(p, q, rr, cores, dp.allreduce_mean(dc), LR)
+
+    for i in range(max(warmup, 3)):
+        step(i % 2)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i % 2)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    failed = 0
+    if xchg is not None:
+        failed = xchg.failed_epoch()
+        xchg.close()
+    hbm_peak, _, _ = measured_peaks()
+    step_bytes = nn * (16 + 8 * D) + 2 * sum(c.numel() * 4 for c in cores)
+    return {"metric": METRIC, "value": world * nn / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms,
+            "n_gpus": world, "steps": steps, "scaling": "weak", "launch": "eager",
+            "workload": "%s shape: N=%d, p=%s q=%s ranks=%s, %d distinct ids per step and rank over the whole "
+                        "index range" % (shape_name, N, p, q, ranks, nn),
+            "step_frac_of_hbm_bound": (step_bytes / (hbm_peak * 1e9)) / (ms * 1e-3),
+            "exchange_failed": failed}
+
+
+def replicas_identical(tensors, dev):
+    """All ranks hold bit-identical copies of `tensors`? (two checksums of the bit patterns, all-gathered)"""
+    import torch.distributed as dist
+    flat = torch.cat([t.detach().reshape(-1).view(torch.int32).to(torch.int64) for t in tensors])
+    chk = torch.stack([flat.sum(), (flat * torch.arange(1, flat.numel() + 1, device=dev)).sum()])
+    allc = [torch.empty_like(chk) for _ in range(dist.get_world_size())]
+    dist.all_gather(allc, chk)
+    return all(bool(torch.equal(allc[0], c)) for c in allc)
+
+
 def run_ours(args, shape):
     import torch.distributed as dist
     world, rank, local = dist_env()
@@ -398,7 +506,7 @@ def run_ours(args, shape):
 
     def module_step(indices, offsets, k):
         out = module(indices, offsets)
-        loss = torch.dot(out.view(-1), target[k])
+        loss = _DotLoss.apply(out, target[k])
         loss.backward()
         if world > 1:  # data parallel: explicit exchange step instead of the fused update
             dp.dp_backward_step(module, [c.grad for c in module.tt_cores], exchange=xchg)
@@ -469,9 +577,32 @@ def run_ours(args, shape):
     e2e_sync_ms = timed(e2e_sync_step, args.steps) / args.steps
 
     exchange_failed, peer_exchange = 0, xchg is not None
+    identical = None
+    if world > 1:                 # every rank applied the same updates to the same cores?
+        identical = replicas_identical(cores, dev)
     if xchg is not None:          # collective: before the ranks part ways
         exchange_failed = xchg.failed_epoch()
         xchg.close()
+    # ---- the other BASELINE configs as sub-records (collective at N > 1: every rank runs them)
+    extra = {}
+    if not args.no_extra:
+        import bench_sage
+        mk = (lambda: ClockSampler(local)) if rank == 0 else None
+        try:
+            extra["papers"] = tt_subrecord("papers", args.nnz, min(args.steps, 20), 3, world, rank, dev,
+                                           args.exchange)
+        except Exception as ex:
+            extra["papers"] = {"error": str(ex)[:300]}
+            if world > 1:
+                raise
+        for name, cfg in (("sage", 2), ("config3", 3)):
+            try:
+                extra[name] = bench_sage.sage_epoch_record(world, rank, dev, config=cfg, epochs=args.sage_epochs,
+                                                           flags=args.flags, clock_sampler=mk)
+            except Exception as ex:   # a sub-record must not take the headline line down
+                extra[name] = {"error": str(ex)[:300]}
+                if world > 1:
+                    raise
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -568,7 +699,7 @@ def run_ours(args, shape):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rows/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
-                "api": "TTEmbeddingBag.forward(indices, offsets), loss = dot(out, target), loss.backward(); indices and "
+                "api": "TTEmbeddingBag.forward(indices, offsets), loss = dot(out, target) (backward hands target over as d_output), loss.backward(); indices and "
                        "offsets staged from pinned host memory one step ahead on a copy stream "
                        "(pipeline.HostBatchPipeline), the loss read back every step, one step "
                        "late (pipeline.DeferredScalars)" + (
@@ -587,6 +718,12 @@ def run_ours(args, shape):
         "cpu_baseline": cpu,
         "reference_gpu": ref_gpu,
         "alt_modes": alt_modes,
+        "replicas_bit_identical": identical,
+        "exchange_failed": exchange_failed,
+        "sage_epoch_s": (extra.get("sage") or {}).get("value"),
+        "sage": extra.get("sage"),
+        "config3": extra.get("config3"),
+        "papers": extra.get("papers"),
     }
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
@@ -601,8 +738,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="products", choices=sorted(SHAPES))
     ap.add_argument("--nnz", type=int, default=262144)
-    ap.add_argument("--cpu-rows", type=int, default=16384,
-                    help="rows per step of the --impl reference (CPU) arm")
+    ap.add_argument("--cpu-rows", type=int, default=0,
+                    help="rows per step of the --impl reference (CPU) arm; 0 = the same rows per step as "
+                         "the GPU arm (--nnz)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: how the core gradients are exchanged")
@@ -610,6 +748,9 @@ def main():
                     help="TTG_FLAG_* bits OR-ed into every tt_forward / tt_backward call "
                          "(8 = plain TF32 tensor-core mode, 16 = fp32 FFMA kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the sub-records (GraphSAGE epoch of configs 2 and 3, papers-shape step)")
+    ap.add_argument("--sage-epochs", type=int, default=2, help="timed GraphSAGE epochs per sub-record")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -99,6 +99,11 @@ def lib():
     return _lib
 
 
+def last_error():
+    msg = lib().ttg_last_error()
+    return msg.decode() if msg else "?"
+
+
 def check(rc, what):
     if rc != 0:
         msg = lib().ttg_last_error()
@@ -230,8 +235,17 @@ workspace = _Workspace()
 
 
 def plan_key_of(tag, indices, rowidx, nnz, B, shape_tuple, cores=()):
-    """Identity of an index plan + group table: the index tensors (address and version counter),
-    the sizes, the table shape and the cores the group table was computed from."""
-    return (tag, indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version,
+    """Identity of an index plan + group table: the stream it was built on, the index tensors (address and
+    version counter), the sizes, the table shape and the cores the group table was computed from.  Pass the
+    cores as the caller holds them (nn.Parameter or its .detach()): `.data` makes a tensor with its own
+    version counter that never moves.  Updates through raw pointers (ttg_apply_optimizer, the peer exchange)
+    do not bump any counter: dp.apply_optimizer / PeerExchange.step clear the plan themselves."""
+    dev = indices.device
+    try:
+        stream = int(torch._C._cuda_getCurrentRawStream(dev.index if dev.index is not None
+                                                        else torch.cuda.current_device()))
+    except AttributeError:
+        stream = int(torch.cuda.current_stream(dev).cuda_stream)
+    return (tag, stream, indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version,
             int(nnz), int(B), shape_tuple,
             tuple((c.data_ptr(), c._version) for c in cores))

@@ -93,6 +93,11 @@ mark_popular_kernel(int32_t size, int32_t cache_size, int64_t* __restrict__ sort
     } else {
       keys[s] = kEmpty;
       freq[s] = 0;
+      // the reference leaves cache_state[s] as it was (FBTT/tt_embeddings_cuda.cu:1139-1142): harmless there
+      // because cache_populate runs once (state is -1 everywhere).  After a SECOND populate an evicted slot
+      // would keep its old cache row and hand it to whatever key is inserted there next; clearing it is
+      // identical to the reference on the first call and correct on later ones.
+      cache_state[s] = -1;
     }
   } else if (n < cache_size) {
     sorted_keys[n] = 0;  // filler row so the prefetch reconstructs a valid index

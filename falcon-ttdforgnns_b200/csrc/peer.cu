@@ -116,8 +116,14 @@ __global__ void __launch_bounds__(kPeerThreads) dp_exchange_update_kernel(PeerAr
     }
   }
   __syncthreads();
+  // A peer that never arrived leaves stale or half-written data in its slot: the step is then skipped by
+  // every CTA that sees the error word (no update, no mean_out), and the host raises on its next look at
+  // ttg_peer_status.  (CTAs time out within microseconds of each other after a 10 s budget; one that saw
+  // the flags at the last moment may still have applied its share, which is why the host treats the step as
+  // failed for good rather than retrying.)
+  const bool failed = (ld_volatile_u32(words + kWFailed) == epoch);
   // 3. + 4.
-  for (int64_t i4 = first; i4 < n4; i4 += stride) {
+  for (int64_t i4 = first; i4 < n4 && !failed; i4 += stride) {
     const int64_t i = i4 * 4;
     float4 v[TTG_MAX_PEERS];
 #pragma unroll

@@ -95,6 +95,7 @@ def apply_optimizer(tt_p_shapes, tt_q_shapes, tt_ranks, tt_cores: Sequence[torch
         rc = _ttg.lib().ttg_apply_optimizer(C.byref(shape), optim, float(learning_rate), float(eps),
                                             cp, sp, dp, _ttg.stream_of(dev))
         _ttg.check(rc, "apply_optimizer")
+        _ttg.workspace.set_plan(dev, None)   # cores changed through raw pointers: the group table is stale
 
 
 class PeerExchange:
@@ -131,32 +132,60 @@ class PeerExchange:
         self.seg = (C.c_int64 * len(self.sizes))(*self.sizes)
         lib = _ttg.lib()
         self.nbytes = lib.ttg_peer_buffer_bytes(self.total)
-        own = C.c_void_p()
+        self.own, self.opened = None, []
+        self.ptrs = (C.c_void_p * _ttg.TTG_MAX_PEERS)()
+        # Construction is collective; a failure on ONE rank must become a failure on ALL of them (a rank that
+        # fell back to NCCL alone would leave the others spinning in the exchange kernel).  Every phase ends in
+        # an agreement: all_gather_object carries this rank's error next to its handle, the open phase is
+        # followed by an all-reduce(MIN) of an ok flag; on disagreement every rank frees what it holds and raises.
+        import socket
+        err, handle = None, None
         with torch.cuda.device(self.device):
-            _ttg.check(lib.ttg_peer_alloc(self.nbytes, C.byref(own)), "peer_alloc")
-            self.own = own.value
-            handle = (C.c_ubyte * _ttg.PEER_HANDLE_BYTES)()
-            _ttg.check(lib.ttg_peer_export(own, handle), "peer_export")
-            import socket
-            mine = (socket.gethostname(), bytes(handle))
+            own = C.c_void_p()
+            if lib.ttg_peer_alloc(self.nbytes, C.byref(own)) != 0:
+                err = "peer_alloc: " + _ttg.last_error()
+            else:
+                self.own = own.value
+                h = (C.c_ubyte * _ttg.PEER_HANDLE_BYTES)()
+                if lib.ttg_peer_export(own, h) != 0:
+                    err = "peer_export: " + _ttg.last_error()
+                else:
+                    handle = bytes(h)
+            mine = (socket.gethostname(), handle, err)
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
-            if any(h[0] != mine[0] for h in everyone):
-                lib.ttg_peer_free(own)
-                self.own = None
-                raise RuntimeError("PeerExchange: the ranks are not on one node")
-            self.ptrs = (C.c_void_p * _ttg.TTG_MAX_PEERS)()
-            self.opened = []
-            for r, (_, h) in enumerate(everyone):
+            errs = [e[2] for e in everyone if e[2]]
+            if not errs and any(e[0] != mine[0] for e in everyone):
+                errs = ["the ranks are not on one node"]
+            if errs:
+                self._release()
+                raise RuntimeError("PeerExchange: " + errs[0])
+            ok = 1
+            for r, (_, h, _) in enumerate(everyone):
                 if r == self.rank:
                     self.ptrs[r] = self.own
                     continue
                 p = C.c_void_p()
                 buf = (C.c_ubyte * _ttg.PEER_HANDLE_BYTES).from_buffer_copy(h)
-                _ttg.check(lib.ttg_peer_open(buf, C.byref(p)), "peer_open(rank %d)" % r)
+                if lib.ttg_peer_open(buf, C.byref(p)) != 0:
+                    ok, err = 0, "peer_open(rank %d): %s" % (r, _ttg.last_error())
+                    break
                 self.ptrs[r] = p.value
                 self.opened.append(p.value)
-        dist.barrier(group=group)      # every buffer is mapped everywhere before the first signal
+            flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # also: every buffer is mapped everywhere
+            if int(flag.item()) == 0:
+                self._release()
+                raise RuntimeError("PeerExchange: " + (err or "a peer could not map the exchange buffers"))
+
+    def _release(self) -> None:
+        lib = _ttg.lib()
+        for p in self.opened:
+            lib.ttg_peer_close(C.c_void_p(p))
+        self.opened = []
+        if self.own is not None:
+            lib.ttg_peer_free(C.c_void_p(self.own))
+            self.own = None
 
     def step(self, d_cores: Sequence[torch.Tensor], tt_cores: Sequence[torch.Tensor],
              optimizer: str = "sgd", learning_rate: float = 0.0, eps: float = 1e-10,
@@ -181,6 +210,8 @@ class PeerExchange:
                 _ttg.ptr_array(cores), sp, optim, float(learning_rate), float(eps),
                 _ttg.ptr(mean_out), _ttg.stream_of(self.device))
             _ttg.check(rc, "dp_exchange_update")
+            if optim != _ttg.OPTIM_DENSE:
+                _ttg.workspace.set_plan(self.device, None)   # cores changed: the group table is stale
         return mean_out
 
     def failed_epoch(self) -> int:
@@ -196,12 +227,7 @@ class PeerExchange:
             return
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)               # nobody still reads what is about to go away
-        lib = _ttg.lib()
-        for p in self.opened:
-            lib.ttg_peer_close(C.c_void_p(p))
-        self.opened = []
-        lib.ttg_peer_free(C.c_void_p(self.own))
-        self.own = None
+        self._release()
 
 
 def dp_backward_step(module, d_cores: Sequence[torch.Tensor], group=None,

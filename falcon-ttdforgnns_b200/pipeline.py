@@ -64,13 +64,14 @@ class HostBatchPipeline:
         bufs = self._buffers(slot, host)
         if self.freed[slot] is not None:
             self.copy_stream.wait_event(self.freed[slot])
+        prev = torch.cuda.current_stream(self.device)    # whatever the caller had current, not necessarily ours
         torch.cuda.set_stream(self.copy_stream)          # copy_ takes the current stream
         try:
             for b, h in zip(bufs, host):
                 b.copy_(h, non_blocking=True)
                 self.h2d_bytes += h.numel() * h.element_size()
         finally:
-            torch.cuda.set_stream(self.compute_stream)
+            torch.cuda.set_stream(prev)
         self.ready[slot].record(self.copy_stream)
         self.staged.append(slot)
 
@@ -115,8 +116,9 @@ class DeferredScalars:
         out = []
         s = self.slot                              # never a pending one: delay + 1 slots
         self.slot = (s + 1) % (self.delay + 1)
+        cur = torch.cuda.current_stream(self.device)     # the stream the copy is issued on
         self.host[s].copy_(value.detach().reshape(1), non_blocking=True)
-        self.events[s].record(self.stream)
+        self.events[s].record(cur)
         self.d2h_bytes += self.host[s].element_size()
         self.pending.append(s)
         while len(self.pending) > self.delay:
@@ -139,10 +141,17 @@ class GraphedStep:
 
     `fn` runs `warmup` times for real before the capture (on a side stream, as torch requires),
     then once more under capture; what it returns are static tensors that every replay
-    overwrites."""
+    overwrites.
+
+    Not capturable: a TTEmbeddingBag with use_cache=True after cache_populate() (its
+    preprocess_indices_sync reads nnz_tt back with a stream synchronisation and sizes later launches
+    with it; tt_embeddings.preprocess_indices_sync raises under capture).  Every replay rewrites the
+    shared index-plan workspace, so the host-side plan key is cleared: an eager backward after a replay
+    rebuilds its plan instead of trusting the one an earlier eager forward left there."""
 
     def __init__(self, fn, device: torch.device, warmup: int = 2):
         device = torch.device(device)
+        self.device = device
         cur = torch.cuda.current_stream(device)
         side = torch.cuda.Stream(device)
         side.wait_stream(cur)
@@ -155,5 +164,7 @@ class GraphedStep:
             self.outputs = fn()
 
     def __call__(self):
+        import _ttg
         self.graph.replay()
+        _ttg.workspace.set_plan(self.device, None)
         return self.outputs

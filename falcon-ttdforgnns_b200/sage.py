@@ -23,27 +23,46 @@ class SAGE(nn.Module):
     def __init__(self, num_nodes: int, in_feats: int, n_hidden: int, n_classes: int,
                  n_layers: int = 3, dropout: float = 0.5, tt_rank: Sequence[int] = (16, 16),
                  p_shapes: Optional[Sequence[int]] = None, q_shapes: Optional[Sequence[int]] = None,
-                 sparse: bool = True, learning_rate: float = 0.01):
+                 sparse: bool = True, learning_rate: float = 0.01, embed_name: str = "fbtt",
+                 device=None):
+        """embed_name: "fbtt" (TTEmbeddingBag, --emb-name fbtt of the reference drivers) or "eff"
+        (Eff_TTEmbedding, Efficient_TT/efficient_tt.py:214-307: forward by prefix reuse, backward = the
+        fused SGD update of the cores, no gradient reaches autograd)."""
         super().__init__()
+        self.embed_name = embed_name
         self.layers = nn.ModuleList()
         self.layers.append(SAGEConv(in_feats, n_hidden, "mean"))
         for _ in range(1, n_layers - 1):
             self.layers.append(SAGEConv(n_hidden, n_hidden, "mean"))
         self.layers.append(SAGEConv(n_hidden, n_classes, "mean"))
         self.dropout = nn.Dropout(dropout)
-        self.embed_layer = TTEmbeddingBag(
-            num_embeddings=num_nodes, embedding_dim=in_feats, tt_ranks=list(tt_rank),
-            tt_p_shapes=list(p_shapes) if p_shapes else None,
-            tt_q_shapes=list(q_shapes) if q_shapes else None, sparse=sparse,
-            optimizer=OptimType.SGD, learning_rate=learning_rate, use_cache=False,
-            weight_dist="normal")
+        if embed_name == "eff":
+            from Efficient_TT.efficient_tt import Eff_TTEmbedding
+            dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self.embed_layer = Eff_TTEmbedding(
+                num_embeddings=num_nodes, embedding_dim=in_feats, tt_ranks=list(tt_rank),
+                tt_p_shapes=list(p_shapes) if p_shapes else None,
+                tt_q_shapes=list(q_shapes) if q_shapes else None, learning_rate=learning_rate,
+                weight_dist="uniform", device=dev.index or 0, batch_size=4096)
+        elif embed_name == "fbtt":
+            self.embed_layer = TTEmbeddingBag(
+                num_embeddings=num_nodes, embedding_dim=in_feats, tt_ranks=list(tt_rank),
+                tt_p_shapes=list(p_shapes) if p_shapes else None,
+                tt_q_shapes=list(q_shapes) if q_shapes else None, sparse=sparse,
+                optimizer=OptimType.SGD, learning_rate=learning_rate, use_cache=False,
+                weight_dist="normal")
+        else:
+            raise ValueError("Unknown embedding type %r" % (embed_name,))   # gnn_model.py:126
 
     def dense_parameters(self) -> List[nn.Parameter]:
         return [p for layer in self.layers for p in layer.parameters()]
 
     def forward(self, blocks: Sequence[Block], input_nodes: torch.Tensor) -> torch.Tensor:
-        offsets = torch.arange(input_nodes.numel() + 1, device=input_nodes.device)
-        h = self.embed_layer(input_nodes, offsets)
+        if self.embed_name == "eff":
+            h = self.embed_layer(input_nodes)
+        else:
+            offsets = torch.arange(input_nodes.numel() + 1, device=input_nodes.device)
+            h = self.embed_layer(input_nodes, offsets)
         for l, (layer, block) in enumerate(zip(self.layers, blocks)):
             h = layer(block, (h, h[:block.num_dst]))
             if l != len(self.layers) - 1:
@@ -72,10 +91,11 @@ def synthetic_graph(num_nodes: int, num_edges: int, device, seed: int = 0, alpha
 
 
 def synthetic_community_graph(num_nodes: int, num_edges: int, k: int, p_in: float, device,
-                              seed: int = 0):
+                              seed: int = 0, ordered: bool = False):
     """Symmetric graph with k equal communities (an undirected edge stays inside its community
     with probability p_in) whose node ids are scrambled -- what a raw dataset looks like before
-    graphloader.py:399-454 reorders it.  Returns (graph, community id of every node)."""
+    graphloader.py:399-454 reorders it; ordered=True keeps the ids community by community, i.e. the graph
+    AFTER a METIS-k reorder (BASELINE config 3).  Returns (graph, community id of every node)."""
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     half = num_edges // 2
@@ -87,7 +107,8 @@ def synthetic_community_graph(num_nodes: int, num_edges: int, k: int, p_in: floa
     near = lo + (torch.rand(half, generator=g, device=device, dtype=torch.float64) * width).long()
     far = torch.randint(0, num_nodes, (half,), generator=g, device=device)
     dst = torch.where(inside, near, far)
-    scramble = torch.randperm(num_nodes, generator=g, device=device)
+    scramble = (torch.arange(num_nodes, device=device) if ordered
+                else torch.randperm(num_nodes, generator=g, device=device))
     s, d = scramble[torch.cat([src, dst])], scramble[torch.cat([dst, src])]
     order = torch.sort(d * num_nodes + s).indices
     s, d = s[order], d[order]
@@ -121,10 +142,14 @@ class Trainer:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
                 off += p.numel()
             if peer_exchange:
+                # PeerExchange is collective and agrees on success over the group: either every rank has it
+                # or every rank raised (and freed its buffers) -> all fall back to NCCL together
                 try:
                     self.xchg = dp.PeerExchange(model.embed_layer.tt_cores)
                 except RuntimeError:
                     self.xchg = None          # not one node / no peer access: NCCL for the cores too
+        self.steps = 0
+        self.check_every = 64                 # steps between looks at the exchange kernel's error word
 
     def step(self, blocks, input_nodes, labels) -> torch.Tensor:
         m = self.model
@@ -148,7 +173,15 @@ class Trainer:
             for c in emb.tt_cores:
                 c.grad = None
         self.opt.step()
+        self.steps += 1
+        if self.xchg is not None and self.steps % self.check_every == 0 and self.xchg.failed_epoch():
+            raise RuntimeError("Trainer: a peer did not arrive at exchange step %d; the update of that step "
+                               "was skipped on this rank, the replicas may have diverged"
+                               % self.xchg.failed_epoch())
         return loss
+
+    def failed_epoch(self) -> int:
+        return self.xchg.failed_epoch() if self.xchg is not None else 0
 
     def close(self) -> None:
         if self.xchg is not None:

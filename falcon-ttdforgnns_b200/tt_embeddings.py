@@ -81,7 +81,7 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
         if nnz > 0:
             _ttg.workspace.set_plan(dev, _ttg.plan_key_of(
                 _plan_tag(), indices, rowidx, nnz, B,
-                shape.key, cores),
+                shape.key, tt_cores),          # the caller's tensors: a Parameter's own version counter
                 keep=(indices, rowidx))
     return output
 
@@ -169,7 +169,7 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
         if nnz > 0:
             key = _ttg.plan_key_of(_plan_tag(), indices, rowidx, nnz, B,
                                    shape.key,
-                                   cores)
+                                   tt_cores)
             if _ttg.workspace.plan(dev) == key:
                 flags |= _ttg.FLAG_PLAN_VALID  # the forward's sort is still in the workspace
         cp = _ttg.ptr_array(cores)
@@ -279,6 +279,10 @@ def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tab
         if nnz == 0:
             return colidx, rowidx, tableidx, 0, None
         lookup = (not warmup) and num_tables == 1
+        if lookup and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("preprocess_indices_sync: the cached / uncached split returns a host integer "
+                               "(stream synchronisation) and cannot be captured in a CUDA graph; capture with "
+                               "use_cache=False or before cache_populate()")
         part_col = part_row = part_loc = None
         if lookup:
             _ttg.require_cuda(hashtbl, "hashtbl", torch.int64)
