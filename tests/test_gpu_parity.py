@@ -98,9 +98,16 @@ def test_fused_sgd_and_adagrad(te, golden, name):
                                row, torch.zeros_like(idx), dO, state, cores)
         g = orc.tt_backward_dense(p, q, r, want, c["indices"], c["rowidx"], c["d_output"][None])
         orc.apply_optimizer(p, cols, "adagrad", 0.05, 1e-10, want, wstate, g)
+    # state = sum of g^2: 1e-5.  The Adagrad step lr * g / (sqrt(state) + 1e-10) is lr * sign(g) on the first
+    # step whatever |g| is: where the true gradient is at rounding level its SIGN is not determined at fp32,
+    # so the cores are held to 1e-5 where |g| >= 1e-3 max|g| and to one step (2 lr) elsewhere.
+    g0 = orc.tt_backward_dense(p, q, r, case_cores(c), c["indices"], c["rowidx"], c["d_output"][None])
     for t in range(T):
-        assert rel_err(state[t].cpu().numpy(), wstate[t]) < 1e-4
-        assert rel_err(cores[t].cpu().numpy(), want[t]) < 1e-4
+        assert rel_err(state[t].cpu().numpy(), wstate[t]) < TOL
+        well = np.abs(g0[t]) >= 1e-3 * np.abs(g0[t]).max()
+        diff = np.abs(cores[t].cpu().numpy().astype(np.float64) - want[t])
+        assert diff[well].max() < TOL * np.abs(want[t]).max()
+        assert diff.max() <= 2 * 2 * 0.05 + 1e-6
 
 
 def test_empty_and_degenerate_inputs(te, golden):
@@ -258,8 +265,14 @@ def test_full_size_products_properties(ttg_lib, base_flags):
         gg = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, dO, cores)
     finally:
         te.EXTRA_FLAGS = base_flags
-    for a, b in zip(gs, gg):
-        assert float((a - b).abs().max() / b.abs().max()) < 5e-5   # atomics reorder fp32 sums
+    # against the fp64 oracle at the full batch: 1e-5; the generic kernels scatter with float atomics (as the
+    # reference does) and are the ones that need the wider, stated bound
+    orc.use_all_host_threads()
+    truth = orc.tt_backward_dense(p, q, r, [c.cpu().numpy() for c in cores], idx.cpu().numpy(),
+                                  row.cpu().numpy(), dO.cpu().numpy())
+    for t, (a, b) in enumerate(zip(gs, gg)):
+        assert rel_err(a.cpu().numpy(), truth[t]) < TOL, "core %d vs fp64 oracle" % t
+        assert float((a - b).abs().max() / b.abs().max()) < 5e-5   # generic path: float atomics
     g2 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, idx, row, tb, (2.0 * dO).contiguous(), cores)
     for a, b in zip(gs, g2):
         assert float((2.0 * a - b).abs().max() / b.abs().max()) < 1e-6
