@@ -674,3 +674,29 @@ def test_backward_only_after_a_call_with_another_row_count(ttg_lib):
         for t in range(3):
             a, b = outs["mma"][k][t], outs["generic"][k][t]
             assert float((a - b).abs().max() / b.abs().max()) < 5e-5, "call %d core %d" % (k, t)
+
+
+def test_plan_is_rebuilt_after_a_raw_pointer_core_update(ttg_lib):
+    """The index plan and group table of a batch are reused by the backward that follows its forward
+    (TTG_FLAG_PLAN_VALID, keyed on tensor version counters).  dp.apply_optimizer / the peer exchange update the
+    cores through raw pointers, which no version counter sees: they must drop the plan themselves, or the next
+    backward on the same indices would contract with the group table of the OLD cores."""
+    import dp
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["cora"]
+    D = 128
+    cores_cpu = _random_cores(p, q, r, n_emb, 31)
+    cores = [c.to(DEV) for c in cores_cpu]
+    rng = np.random.default_rng(9)
+    nnz = 3000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = np.arange(nnz, dtype=np.int64)
+    dO = (rng.random(size=(1, nnz, D)).astype(np.float32) * 0.1)
+    ti, tr, tb, tdo = _t(idx), _t(row), torch.zeros(nnz, dtype=torch.int64, device=DEV), _t(dO)
+    te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, ti, tr, tb, cores)
+    d1 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, ti, tr, tb, tdo, cores)
+    dp.apply_optimizer(p, q, r, cores, [g.clone() for g in d1], 0.5)      # cores change, versions do not
+    d2 = te.tt_dense_backward(1000, D, p, q, r, None, nnz, ti, tr, tb, tdo, cores)
+    want = orc.tt_backward_dense(p, q, r, [c.cpu().numpy() for c in cores], idx, row, dO)
+    for t in range(3):
+        assert rel_err(d2[t].cpu().numpy(), want[t]) < TOL, "core %d: stale group table" % t
