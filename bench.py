@@ -355,7 +355,13 @@ def run_ours(args, shape):
     from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
 
     lib = _ttg.lib()
-    te.EXTRA_FLAGS = int(args.flags)
+    # --plan-ahead-value: the device-resident loop builds the next batch's plan on a forked stream and the row
+    # kernels leave 8 SMs to it (TTG_FLAG_SHARE_SMS).  Measured neutral on B200 (0.178 vs 0.173 ms/step: a CTA of
+    # the row kernels takes a whole register file and the dependent-launch CTAs of the next kernel take the spare
+    # SMs, so the plan still runs behind the backward; profiles/r2_step_timeline.txt), hence off by default.  The
+    # end-to-end loop prepares batches on the copy stream either way (--no-plan-ahead switches that off).
+    share = _ttg.FLAG_SHARE_SMS if args.plan_ahead_value else 0
+    te.EXTRA_FLAGS = int(args.flags) | share
     p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
     rr = [1] + ranks + [1]
     D = int(np.prod(q))
@@ -385,8 +391,31 @@ def run_ours(args, shape):
             print("bench.py: peer exchange unavailable (%s); using the NCCL all-reduce" % ex,
                   file=sys.stderr)
 
+    plan_stream = torch.cuda.Stream(dev)
+
+    def plan_next(k):
+        """the index plan of the NEXT batch, beside this step's kernels (it depends on the indices only): a fork
+        of the current stream, joined at the end of the step; tt_forward finds it ready and skips its own"""
+        if not args.plan_ahead_value:
+            return None
+        cur = torch.cuda.current_stream(dev)
+        plan_stream.wait_stream(cur)
+        with torch.cuda.stream(plan_stream):
+            kn = (k + 1) % NUM_ROT
+            te.tt_plan(1, nnz, p, q, rr, nnz, idx_dev[kn], rowidx, tableidx, kn & 1)
+        return cur
+
     def raw_step(k):
+        # forward first, then the fork: the plan of batch k + 1 runs beside the long backward kernels instead of
+        # competing with the start of this step's own chain
         out = te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx, cores)
+        cur = plan_next(k)
+        raw_backward(k)
+        if cur is not None:
+            cur.wait_stream(plan_stream)
+        return out
+
+    def raw_backward(k):
         if world == 1:
             te.tt_sgd_backward(1000, D, LR, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx,
                                d_out[k], cores)
@@ -397,7 +426,6 @@ def run_ours(args, shape):
                 xchg.step(dc, cores, "sgd", LR)
             else:
                 dp.apply_optimizer(p, q, rr, cores, dp.allreduce_mean(dc), LR)
-        return out
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -406,12 +434,14 @@ def run_ours(args, shape):
             torch.cuda.synchronize(dev)
 
     # ---- warm-up (eager), then try to capture one CUDA graph per rotating batch
-    for i in range(max(args.warmup, 3)):
+    NROT_W = ((max(args.warmup, 3) + NUM_ROT - 1) // NUM_ROT) * NUM_ROT    # whole rotations: batch k <-> slot k & 1
+    for i in range(NROT_W):
         raw_step(i % NUM_ROT)
     sync_all()
     l0 = lib.ttg_launch_count()
-    raw_step(0)
-    launches_per_step = int(lib.ttg_launch_count() - l0)
+    for k in range(NUM_ROT):
+        raw_step(k)
+    launches_per_step = int(lib.ttg_launch_count() - l0) // NUM_ROT
     sync_all()
     # with the NCCL all-reduce the step stays eager: capturing it works and is 8 % faster (0.2105
     # vs 0.2276 ms/step on 2 GPUs), but the process then hangs in destroy_process_group at exit
@@ -455,7 +485,7 @@ def run_ours(args, shape):
         return ms
 
     step_fn = (lambda i: graphs[i % NUM_ROT].replay()) if use_graph else (lambda i: raw_step(i % NUM_ROT))
-    for i in range(args.warmup):
+    for i in range(((args.warmup + NUM_ROT - 1) // NUM_ROT) * NUM_ROT):
         step_fn(i)
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_fn, args.steps)
@@ -487,12 +517,12 @@ def run_ours(args, shape):
     if world == 1 and not args.no_cpu_baseline and args.flags == 0:
         alt_modes = {}
         for name, fl in (("default_3xtf32", 0), ("tf32_single_pass", 8), ("fp32_ffma_kernels", 16)):
-            te.EXTRA_FLAGS = fl
+            te.EXTRA_FLAGS = fl | share
             for i in range(3):
                 raw_step(i % NUM_ROT)
             ms_alt = timed(lambda i: raw_step(i % NUM_ROT), 10) / 10
             alt_modes[name] = {"ms_per_step_eager": ms_alt, "rows_per_s": nnz / (ms_alt * 1e-3)}
-        te.EXTRA_FLAGS = int(args.flags)
+        te.EXTRA_FLAGS = int(args.flags) | share
 
     # ---- end to end through the module API (host indices in, scalar loss out).  Every step's
     # index arrays go pinned host -> device inside the timed region (on the copy stream of
@@ -514,7 +544,9 @@ def run_ours(args, shape):
                 c.grad = None
         return loss
 
-    pipe = pipeline.HostBatchPipeline(dev, depth=2)
+    # the module prepares a staged batch (bag -> row map, index plan) on the copy stream, beside the running step
+    pipe = pipeline.HostBatchPipeline(
+        dev, depth=2, on_staged=None if args.no_plan_ahead else (lambda slot, i, o: module.prepare(i, o, slot)))
     graphed = {}     # (staging slot, batch) -> the module step captured as a CUDA graph
     e2e_graph = use_graph   # with NCCL in the step it stays eager (see above)
 
@@ -692,6 +724,8 @@ def run_ours(args, shape):
                                   else "fp32 via 3xTF32 split on tensor cores, fp32 accumulation"),
                    "l2": "4 rotating batches, 212 MB touched per step (> 126 MB L2)",
                    "launch": "cuda_graph" if use_graph else "eager",
+                   "index_plan": ("of batch i + 1 built beside step i on a forked stream (ttg_tt_plan, second plan "
+                                  "slot)") if args.plan_ahead_value else "inside the forward",
                    "parallelism": "dp%d, replicated cores%s" % (
                        world, "" if world == 1 else
                        ", d_cores exchanged and the update applied by one kernel over NVLink peer memory"
@@ -706,6 +740,8 @@ def run_ours(args, shape):
                            "; the module step replayed as a CUDA graph (pipeline.GraphedStep)"
                            if e2e_graph else ""),
                 "launch": "cuda_graph" if e2e_graph else "eager",
+                "index_plan": "inside the forward" if args.no_plan_ahead else
+                              "TTEmbeddingBag.prepare on the copy stream right behind the batch's host-to-device copy",
                 "ms_per_step_eager_pipelined": e2e_eager_ms,
                 "ms_per_step_eager_unpipelined": e2e_sync_ms,
                 "loss_last": losses[-1] if losses else None},
@@ -748,6 +784,11 @@ def main():
                     help="TTG_FLAG_* bits OR-ed into every tt_forward / tt_backward call "
                          "(8 = plain TF32 tensor-core mode, 16 = fp32 FFMA kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plan-ahead", action="store_true",
+                    help="e2e: build every batch's index plan inside its own forward (round-1 behaviour) instead "
+                         "of on the copy stream beside the running step")
+    ap.add_argument("--plan-ahead-value", action="store_true",
+                    help="device-resident loop: plan of batch i + 1 on a forked stream beside step i")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the sub-records (GraphSAGE epoch of configs 2 and 3, papers-shape step)")
     ap.add_argument("--sage-epochs", type=int, default=2, help="timed GraphSAGE epochs per sub-record")

@@ -440,6 +440,39 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             tt_embeddings.update_cache_state(indices, self.hashtbl, self.cache_freq)
 
     # -- lookup -------------------------------------------------------------------------------
+    def prepare(self, indices: torch.Tensor, offsets: torch.Tensor, slot: int = 0) -> bool:
+        """Index work of a LATER forward(indices, offsets), on torch's current stream: the bag -> row map and the
+        sorted index plan (tt_embeddings.tt_plan) go into plan slot `slot` while the batch in flight uses the
+        other one.  Not part of the reference's module (DGL's DataLoader prefetches its batches,
+        sage_dgl_partition.py:141-154; the index split stays inside its forward); a loader that stages batches
+        ahead calls this beside the host-to-device copy (pipeline.HostBatchPipeline(on_staged=...)).  forward()
+        recognises the prepared tensors (same storage, unmodified) and skips both steps.  Only without the LFU
+        split (use_cache False or still warming up); returns False when nothing was prepared."""
+        if self.use_cache and not self.warmup:
+            return False
+        if indices.dtype != torch.int64 or offsets.dtype != torch.int64 or not indices.is_contiguous() \
+                or not offsets.is_contiguous():
+            return False
+        (_, rowidx, tableidx, n_tt, _) = tt_embeddings.preprocess_indices_sync(
+            indices, offsets, self.num_tables, True, self.hashtbl, self.cache_state)
+        B = (offsets.numel() - 1) // self.num_tables
+        ok = tt_embeddings.tt_plan(self.num_tables, B, self.tt_p_shapes, self.tt_q_shapes, self.tt_ranks,
+                                   n_tt, indices, rowidx, tableidx, slot)
+        if not ok:
+            return False
+        if not hasattr(self, "_prepared"):
+            self._prepared = {}
+        self._prepared[slot] = ((indices.data_ptr(), indices._version, indices.numel(), offsets.data_ptr(),
+                                 offsets._version, offsets.numel()), indices, offsets, rowidx, tableidx)
+        return True
+
+    def _prepared_for(self, indices, offsets):
+        for slot, (key, i, o, rowidx, tableidx) in getattr(self, "_prepared", {}).items():
+            if key == (indices.data_ptr(), indices._version, indices.numel(), offsets.data_ptr(),
+                       offsets._version, offsets.numel()):
+                return rowidx, tableidx
+        return None
+
     def forward(self, indices: torch.Tensor, offsets: torch.Tensor,
                 warmup: bool = True) -> torch.Tensor:
         """[num_tables, B, D] bag sums.  `warmup` is accepted for signature compatibility; like
@@ -447,8 +480,13 @@ class TableBatchedTTEmbeddingBag(nn.Module):
         indices = indices.long().contiguous()
         offsets = offsets.long().contiguous()
         self.update_cache(indices)
-        (indices, rowidx, tableidx, n_tt, cache_locations) = tt_embeddings.preprocess_indices_sync(
-            indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)
+        prepared = None if (self.use_cache and not self.warmup) else self._prepared_for(indices, offsets)
+        if prepared is not None:
+            rowidx, tableidx = prepared
+            n_tt, cache_locations = indices.numel(), None
+        else:
+            (indices, rowidx, tableidx, n_tt, cache_locations) = tt_embeddings.preprocess_indices_sync(
+                indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)
         n_cached = indices.numel() - n_tt
         return TTLookupFunction.apply(
             (offsets.numel() - 1) // self.num_tables, self.embedding_dim, self.tt_p_shapes,

@@ -18,7 +18,7 @@ TTG_MAX_PEERS = 8
 PEER_HANDLE_BYTES = 64
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
 FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC, FLAG_TF32, FLAG_FFMA = 1, 2, 4, 8, 16
-FLAG_MMA_SYNC, FLAG_TCGEN05 = 32, 64
+FLAG_MMA_SYNC, FLAG_TCGEN05, FLAG_PLAN_READY, FLAG_PLAN_SLOT1, FLAG_SHARE_SMS = 32, 64, 128, 256, 512
 
 
 class Shape(C.Structure):
@@ -49,6 +49,7 @@ SIGNATURES = {
                                          _i32, _f32, _f32, _vp, _vp]),
     "ttg_tt_workspace_bytes": (_sz, [_SP, _i64, _i64]),
     "ttg_tt_forward": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "ttg_tt_plan": (C.c_int, [_SP, _i64, _i64, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "ttg_tt_backward": (C.c_int, [_SP, _i32, _f32, _f32, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _sz, _i32, _vp]),
     "ttg_tt_rows_range_workspace_bytes": (_sz, [_SP]),
@@ -213,6 +214,10 @@ class _Workspace:
         self.plan_key = {}
         self.keep = {}   # tensors the plan was built from: kept alive so their addresses
                          # cannot be recycled while the key is still trusted
+        self.ready = {}  # (device, slot) -> (key, keep): index plans ttg_tt_plan built ahead of their forward
+        self.layout = {} # device -> (shape, B, nnz) the buffer is currently carved for: the C side lays the
+                         # workspace out as a function of these, so a plan prepared under one layout must
+                         # neither be used nor be BUILT (it runs beside the current batch) under another
 
     def get(self, device, nbytes):
         key = (device.type, device.index)
@@ -221,10 +226,39 @@ class _Workspace:
             b = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
             self.buf[key] = b
             self.plan_key[key] = None
+            for k in [k for k in self.ready if k[:2] == key]:   # plans lived in the old buffer
+                del self.ready[k]
         return b
 
     def plan(self, device):
         return self.plan_key.get((device.type, device.index))
+
+    def same_layout(self, device, layout, adopt=True):
+        """Is the buffer carved for `layout`?  adopt: make it so (dropping the plans prepared under the old one)."""
+        key = (device.type, device.index)
+        cur = self.layout.get(key)
+        if cur == layout:
+            return True
+        if adopt:
+            self.layout[key] = layout
+            for k in [k for k in self.ready if k[:2] == key]:
+                del self.ready[k]
+            self.plan_key[key] = None
+        return cur is None
+
+    def set_ready(self, device, slot, key, keep=None):
+        self.ready[(device.type, device.index, int(slot))] = (key, keep)
+
+    def ready_slot(self, device, key):
+        """Plan slot that holds the ready plan `key`, or None."""
+        for slot in (0, 1):
+            e = self.ready.get((device.type, device.index, slot))
+            if e is not None and e[0] == key:
+                return slot
+        return None
+
+    def drop_ready(self, device, slot):
+        self.ready.pop((device.type, device.index, int(slot)), None)
 
     def set_plan(self, device, key, keep=None):
         self.plan_key[(device.type, device.index)] = key
@@ -232,6 +266,13 @@ class _Workspace:
 
 
 workspace = _Workspace()
+
+
+def index_key_of(tag, indices, rowidx, nnz, B, shape_tuple):
+    """Identity of an index plan alone (no stream: it is handed from the stream that built it to the one that
+    uses it through an event the caller owns; no cores: the plan does not depend on them)."""
+    return (tag, indices.data_ptr(), indices._version, rowidx.data_ptr(), rowidx._version, int(nnz), int(B),
+            shape_tuple)
 
 
 def plan_key_of(tag, indices, rowidx, nnz, B, shape_tuple, cores=()):

@@ -238,6 +238,23 @@ extern "C" int ttg_tt_forward(const ttg_shape* shape, int64_t B, int64_t nnz,
                              workspace_bytes, flags, (cudaStream_t)stream);
 }
 
+extern "C" int ttg_tt_plan(const ttg_shape* shape, int64_t B, int64_t nnz, const int64_t* indices,
+                           const int64_t* rowidx, const int64_t* tableidx, void* workspace,
+                           size_t workspace_bytes, int32_t flags, void* stream) {
+  TTDev tt;
+  const float* dummy[TTG_MAX_CORES] = {nullptr, nullptr, nullptr, nullptr};
+  int rc = make_ttdev(shape, dummy, &tt);
+  if (rc != TTG_OK) return rc;
+  TTG_CHECK_ARG(B > 0 && nnz >= 0, "tt_plan: bad B / nnz");
+  TTG_CHECK_ARG(nnz == 0 || (indices && rowidx && tableidx), "tt_plan: null index arrays");
+  if ((flags & TTG_FLAG_FORCE_GENERIC) || !sorted_supported(tt)) {
+    set_error("tt_plan: the shape-generic kernels have no index plan");
+    return TTG_ENOTSUP;
+  }
+  return sorted_plan(tt, B, nnz, indices, rowidx, tableidx, workspace, workspace_bytes, flags,
+                     (cudaStream_t)stream);
+}
+
 extern "C" int ttg_tt_backward(const ttg_shape* shape, int32_t optim, float lr, float eps, int64_t B,
                                int64_t nnz, const int64_t* indices, const int64_t* rowidx,
                                const int64_t* tableidx, const float* d_output,

@@ -194,6 +194,9 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
                     float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
                     void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream);
 
+int sorted_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                const int64_t* tableidx, void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream);
+
 int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* output, void* ws,
                       size_t ws_bytes, int32_t flags, cudaStream_t stream);
 
@@ -207,6 +210,7 @@ struct MmaPlan {
   float* S;                // [groups][q0 q1][r2]
   float* d0parts;          // [p1][core0 elements]: per-i1 partial products of d_core0
   uint32_t first_key;      // skeys == nullptr: the keys are first_key, first_key + 1, ...
+  int32_t spare_sms;       // SMs the persistent row kernels leave to other streams (TTG_FLAG_SHARE_SMS)
 };
 bool mma_supported(const TTDev& tt);       // table, forward and backward
 bool mma_fwd_supported(const TTDev& tt);   // table and forward (ranks 32: the backward stays FFMA)

@@ -1254,7 +1254,7 @@ struct Shape {
     auto kern = mma_fwd_kernel<Q0, Q1, Q2, R2, TERMS, kC2S>;
     TTG_ENSURE_SMEM(kern, smem);
     constexpr int RB = fwd_rb(Q2);
-    int64_t grid = kNumSMs;
+    int64_t grid = kNumSMs - pl.spare_sms;
     if (grid * kWarps * RB > nnz) grid = ceil_div(nnz, kWarps * RB);
     int64_t rpw = ceil_div(nnz, grid * kWarps);
     rpw = ceil_div(rpw, RB) * RB;
@@ -1303,10 +1303,11 @@ struct Shape {
       const size_t smem = bwd_smem(npairs);
       auto kern = mma_bwd_rows_kernel<Q0, Q1, Q2, R2, TERMS>;
       TTG_ENSURE_SMEM(kern, smem);
-      int64_t chunk = ceil_div(nnz, (int64_t)kNumSMs * kWarps);
+      const int64_t sms = kNumSMs - pl.spare_sms;
+      int64_t chunk = ceil_div(nnz, sms * kWarps);
       if (chunk < 32) chunk = 32;
       int64_t grid = ceil_div(ceil_div(nnz, chunk), kWarps);
-      if (grid > kNumSMs) grid = kNumSMs;
+      if (grid > sms) grid = sms;
       prof_begin(K_BWD_ROWS, stream);
       TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreads), smem, stream, tt, nnz, total_rows,
                           groups, pl.skeys, pl.srow, pl.cnt, pl.base, d_output, pl.Ttab, pl.S, dcore[2],

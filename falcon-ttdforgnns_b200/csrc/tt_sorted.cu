@@ -97,6 +97,7 @@ struct SortedWs {
   float* d0partsR;     // [kNumSMs][core0 elements]                (tcgen05 kernels)
   int32_t* cnt;        // [cnt_elems] rows per group (+1: invalid keys), padded to scan tiles
   int32_t* rowcount;   // [tables * B] valid indices per output row; directly behind cnt
+  int32_t* fill_flag;  // one word (inside cnt's padding): some output row has 0 or >= 2 indices
   size_t cnt_bytes;    // cnt alone (backward-only plan)
   size_t clear_bytes;  // cnt + rowcount, cleared by one memset
   int32_t* base;       // [cnt_elems] exclusive scan of cnt
@@ -106,7 +107,9 @@ struct SortedWs {
   bool smem_acc;
 };
 
-SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
+// The index plan (sorted keys, output rows, group counters, bucket starts) exists twice: while the row kernels
+// of one batch read slot s, ttg_tt_plan may build the plan of the next batch into slot 1 - s on another stream.
+SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base, int slot = 0) {
   SortedWs w;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -124,8 +127,14 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
   w.keys_in = (uint32_t*)take(sizeof(uint32_t) * n);
   w.vals_in = (int32_t*)take(sizeof(int32_t) * n);
   w.ranks = (int32_t*)take(sizeof(int32_t) * n);
-  w.skeys = (uint32_t*)take(sizeof(uint32_t) * (n + 64));
-  w.srow = (int32_t*)take(sizeof(int32_t) * (n + 64));
+  for (int sl = 0; sl < 2; ++sl) {
+    uint32_t* k = (uint32_t*)take(sizeof(uint32_t) * (n + 64));
+    int32_t* r = (int32_t*)take(sizeof(int32_t) * (n + 64));
+    if (sl == slot) {
+      w.skeys = k;
+      w.srow = r;
+    }
+  }
   w.touched = (uint8_t*)take(groups);
   w.S = (float*)take(sizeof(float) * groups * (size_t)(tt.q[0] * tt.q[1] * tt.r[2]));
   w.Ttab = use_group_table(tt, nnz)
@@ -138,12 +147,21 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base) {
   w.S1R = rpath ? (float*)take(sizeof(float) * r_table_floats(tt) / 2) : nullptr;
   w.d0partsR = rpath ? (float*)take(sizeof(float) * (size_t)kNumSMs * e0) : nullptr;
   // counters (padded to whole 4096-counter scan tiles) and the per-row counts share one memset
-  const size_t cnt_elems = align_up((rpath && groups_r > groups ? groups_r : groups) + 1, 4096);
+  const size_t cnt_elems = align_up((rpath && groups_r > groups ? groups_r : groups) + 2, 4096);   // + invalid bucket + fill flag
   w.cnt_bytes = sizeof(int32_t) * cnt_elems;
   w.clear_bytes = sizeof(int32_t) * (cnt_elems + out_rows);
-  w.cnt = (int32_t*)take(w.clear_bytes);
-  w.rowcount = base ? w.cnt + cnt_elems : nullptr;
-  w.base = (int32_t*)take(sizeof(int32_t) * cnt_elems);
+  for (int sl = 0; sl < 2; ++sl) {
+    int32_t* c = (int32_t*)take(w.clear_bytes);
+    int32_t* b = (int32_t*)take(sizeof(int32_t) * cnt_elems);
+    if (sl == slot) {
+      w.cnt = c;
+      w.rowcount = base ? c + cnt_elems : nullptr;
+      w.base = b;
+      // last counter of the padded array: set by the scatter kernel when some output row does NOT have exactly
+      // one index (then the forward must zero-fill / accumulate); cleared with the counters
+      w.fill_flag = base ? c + cnt_elems - 1 : nullptr;
+    }
+  }
   w.smem_acc = (core2 * sizeof(float) <= kSmemAccLimit);
   w.partials = w.smem_acc ? (float*)take(sizeof(float) * core2 * kBwdGrid) : nullptr;
   w.cub_bytes = 0;
@@ -263,9 +281,11 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
                       const int32_t* __restrict__ ranks, const int32_t* __restrict__ base,
                       const int32_t* __restrict__ rowcount, uint32_t* __restrict__ skeys,
                       int32_t* __restrict__ srow, float* __restrict__ output, int64_t out_rows,
-                      int32_t D4) {
+                      int32_t D4, int32_t* fill_flag) {
   pdl_trigger();
   pdl_wait();      // keys, ranks and the scanned bucket starts are complete
+  // zero-fill pass alone (plan built earlier): nothing to do when every output row has exactly one index
+  if (nnz == 0 && fill_flag != nullptr && ld_dep_s32(fill_flag) == 0) return;
   const int64_t n0 = (int64_t)blockIdx.x * (256 * kPlanItems) + threadIdx.x;
   if (ranks != nullptr) {
     uint32_t key[kPlanItems];
@@ -283,21 +303,37 @@ bucket_scatter_kernel(int64_t nnz, uint32_t total_rows, uint32_t p2, int32_t num
       pos[k] += ld_dep_s32(base + g);
       rc[k] = rowcount ? ld_dep_s32(rowcount + val[k]) : 1;
     }
+    bool odd = false;
 #pragma unroll
     for (int k = 0; k < kPlanItems; ++k) {
       if (n0 + k * 256 < nnz) {
         skeys[pos[k]] = key[k];
         srow[pos[k]] = (int32_t)((uint32_t)val[k] | (rc[k] == 1 ? 0u : kMultiBit));
+        odd |= (rc[k] != 1);
       }
     }
+    if (rowcount != nullptr && fill_flag != nullptr) {
+      // rows with several indices, or fewer valid indices than output rows (then some row has none)
+      if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)ld_dep_s32(base + num_groups) != out_rows) odd = true;
+      if (__any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(fill_flag, 1);
+    }
   } else if (rowcount != nullptr) {
+    bool odd = false;
 #pragma unroll
     for (int k = 0; k < kPlanItems; ++k) {
       const int64_t n = n0 + k * 256;
       if (n < nnz) {
         const int32_t v = srow[n];
-        if (ld_dep_s32(rowcount + v) != 1) srow[n] = (int32_t)((uint32_t)v | kMultiBit);
+        // radix-sorted plan: invalid keys sit at the end with output row 0 (never read by the row kernels)
+        if (ld_dep_s32(rowcount + v) != 1) {
+          srow[n] = (int32_t)((uint32_t)v | kMultiBit);
+          odd = true;
+        }
       }
+    }
+    if (fill_flag != nullptr) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && (int64_t)ld_dep_s32(base + num_groups) != out_rows) odd = true;
+      if (__any_sync(0xffffffffu, odd) && (threadIdx.x & 31) == 0) atomicOr(fill_flag, 1);
     }
   }
   if (output != nullptr) {
@@ -1449,24 +1485,25 @@ const Entry* find_entry(const TTDev& tt) {
 int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                const int64_t* rowidx, const int64_t* tableidx, const SortedWs& w,
                bool deterministic, float* output, bool zero_only, cudaStream_t stream,
-               bool right = false) {
+               bool right = false, bool count_rows = false) {
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
   const int32_t groups = right ? tt.num_tables * tt.p[1] * tt.p[2] : tt.num_tables * tt.p[0] * tt.p[1];
   const uint32_t gdiv = (uint32_t)(right ? tt.p[0] : tt.p[2]);   // group = key / gdiv
   const uint32_t hp = right ? (uint32_t)(tt.p[1] * tt.p[2]) : 0u;
   const int64_t out_rows = (int64_t)tt.num_tables * B;
   const unsigned nblk = (unsigned)ceil_div(nnz, 256 * kPlanItems);
-  int32_t* rowcount = output ? w.rowcount : nullptr;
+  int32_t* rowcount = (output || count_rows) ? w.rowcount : nullptr;
   if (zero_only) {
     prof_begin(K_SORT, stream);
-    bucket_scatter_kernel<<<nblk, 256, 0, stream>>>(0, total_rows, gdiv, groups,
-                                                    nullptr, nullptr, nullptr, nullptr, w.rowcount,
-                                                    nullptr, nullptr, output, out_rows, tt.D / 4);
+    TTG_CUDA(launch_pdl(bucket_scatter_kernel, dim3(nblk), dim3(256), 0, stream, (int64_t)0, total_rows, gdiv,
+                        groups, (const uint32_t*)nullptr, (const int32_t*)nullptr, (const int32_t*)nullptr,
+                        (const int32_t*)nullptr, (const int32_t*)w.rowcount, (uint32_t*)nullptr, (int32_t*)nullptr,
+                        output, out_rows, tt.D / 4, w.fill_flag));
     prof_end(K_SORT, stream);
     TTG_LAUNCH_CHECK();
     return TTG_OK;
   }
-  TTG_CUDA(cudaMemsetAsync(w.cnt, 0, output ? w.clear_bytes : w.cnt_bytes, stream));
+  TTG_CUDA(cudaMemsetAsync(w.cnt, 0, rowcount ? w.clear_bytes : w.cnt_bytes, stream));
   prof_begin(K_PLAN, stream);
   plan_kernel<<<nblk, 256, 0, stream>>>(nnz, B, tt.num_rows, tt.num_tables, total_rows, indices,
                                         rowidx, tableidx, w.keys_in, w.vals_in, w.ranks, w.cnt,
@@ -1488,7 +1525,7 @@ int build_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
   }
   TTG_CUDA(launch_pdl<2>(bucket_scatter_kernel, dim3(nblk), dim3(256), 0, stream, nnz, total_rows,
                       gdiv, groups, w.keys_in, w.vals_in, deterministic ? nullptr : w.ranks,
-                      w.base, rowcount, w.skeys, w.srow, output, out_rows, tt.D / 4));
+                      w.base, rowcount, w.skeys, w.srow, output, out_rows, tt.D / 4, w.fill_flag));
   TTG_LAUNCH_CHECK();
   prof_end(K_SORT, stream);
   return TTG_OK;
@@ -1502,8 +1539,12 @@ bool use_mma_fwd(const TTDev& tt, const SortedWs& w, int32_t flags) {
   return w.Ttab != nullptr && !(flags & TTG_FLAG_FFMA) && mma_fwd_supported(tt);
 }
 
-MmaPlan mma_plan(const SortedWs& w) {
+constexpr int kSpareSMs = 8;   // TTG_FLAG_SHARE_SMS: the row kernels fill 140 SMs with their persistent CTAs (one CTA
+                               // takes a whole register file), the rest serves whatever other streams enqueue
+
+MmaPlan mma_plan(const SortedWs& w, int32_t flags = 0) {
   MmaPlan pl;
+  pl.spare_sms = (flags & TTG_FLAG_SHARE_SMS) ? kSpareSMs : 0;
   pl.skeys = w.skeys;
   pl.srow = w.srow;
   pl.cnt = w.cnt;
@@ -1587,30 +1628,34 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
     set_error("sorted_forward: output must be 16-byte aligned");
     return TTG_EINVAL;
   }
-  SortedWs w = carve(tt, B, nnz, (char*)ws);
+  SortedWs w = carve(tt, B, nnz, (char*)ws, (flags & TTG_FLAG_PLAN_SLOT1) ? 1 : 0);
   if (ws == nullptr || ws_bytes < w.total) {
     set_error("sorted_forward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
   }
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
-  const bool zero_only = (flags & TTG_FLAG_PLAN_VALID) != 0;
+  // PLAN_VALID: plan AND group table of this batch are in the workspace; PLAN_READY: only the plan (ttg_tt_plan)
+  const bool table_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
+  const bool zero_only = table_valid || (flags & TTG_FLAG_PLAN_READY) != 0;
   if (use_r(tt, w, flags)) {
     rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, output,
                     zero_only, stream, true);
     if (rc != TTG_OK) return rc;
-    if (!zero_only) {   // otherwise the table of this batch is still in the workspace
+    if (!table_valid) {   // otherwise the table of this batch is still in the workspace
       rc = r_table(tt, r_plan(w), stream);
       if (rc != TTG_OK) return rc;
     }
     return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
   }
   if (use_mma_fwd(tt, w, flags)) {
-    if (zero_only)  // plan and table of this batch are still in the workspace
+    if (zero_only) {  // the plan of this batch is in the workspace (and, PLAN_VALID, its group table)
       rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, false, output, true, stream);
-    else
+      if (rc == TTG_OK && !table_valid) rc = mma_table(tt, mma_plan(w), (flags & TTG_FLAG_TF32) != 0, true, stream);
+    } else {
       rc = table_then_plan(tt, B, nnz, indices, rowidx, tableidx, w, flags, output, stream);
+    }
     if (rc != TTG_OK) return rc;
-    return mma_forward(tt, nnz, total_rows, mma_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
+    return mma_forward(tt, nnz, total_rows, mma_plan(w, flags), output, (flags & TTG_FLAG_TF32) != 0, stream);
   }
   rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0,
                   output, zero_only, stream);
@@ -1652,6 +1697,25 @@ int sorted_rows_range(const TTDev& tt, int64_t first_row, int64_t num, float* ou
   return mma_forward(tt, num, (uint32_t)tt.num_rows, pl, output, tf32, stream);
 }
 
+// the index plan alone (it depends on the indices only): what ttg_tt_forward(TTG_FLAG_PLAN_READY) then skips
+int sorted_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices, const int64_t* rowidx,
+                const int64_t* tableidx, void* ws, size_t ws_bytes, int32_t flags, cudaStream_t stream) {
+  if (!find_entry(tt)) {
+    set_error("tt_plan: shape has no sorted kernels (nothing to prepare)");
+    return TTG_ENOTSUP;
+  }
+  if (nnz == 0) return TTG_OK;
+  int rc = check_common(tt, B, nnz, "tt_plan");
+  if (rc != TTG_OK) return rc;
+  SortedWs w = carve(tt, B, nnz, (char*)ws, (flags & TTG_FLAG_PLAN_SLOT1) ? 1 : 0);
+  if (ws == nullptr || ws_bytes < w.total) {
+    set_error("tt_plan: workspace %zu < %zu bytes", ws_bytes, w.total);
+    return TTG_ENOMEM;
+  }
+  return build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, nullptr, false,
+                    stream, use_r(tt, w, flags), true);
+}
+
 int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                     const int64_t* rowidx, const int64_t* tableidx, const float* d_output,
                     float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
@@ -1684,7 +1748,7 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
     set_error("sorted_backward: adagrad needs optimizer_state");
     return TTG_EINVAL;
   }
-  SortedWs w = carve(tt, B, nnz, (char*)ws);
+  SortedWs w = carve(tt, B, nnz, (char*)ws, (flags & TTG_FLAG_PLAN_SLOT1) ? 1 : 0);
   if (ws == nullptr || ws_bytes < w.total) {
     set_error("sorted_backward: workspace %zu < %zu bytes", ws_bytes, w.total);
     return TTG_ENOMEM;
@@ -1707,7 +1771,7 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
       rc = table_then_plan(tt, B, nnz, indices, rowidx, tableidx, w, flags, nullptr, stream);
       if (rc != TTG_OK) return rc;
     }
-    return mma_backward(tt, nnz, total_rows, mma_plan(w), d_output, dcore, optim, lr, eps, state,
+    return mma_backward(tt, nnz, total_rows, mma_plan(w, flags), d_output, dcore, optim, lr, eps, state,
                         (flags & TTG_FLAG_TF32) != 0, stream);
   }
   if (!plan_valid) {

@@ -25,7 +25,12 @@ class HostBatchPipeline:
     compute stream that the copy stream waits for), so the index tensors a backward still needs
     are never clobbered by a prefetch."""
 
-    def __init__(self, device: torch.device, depth: int = 2, stream: Optional[torch.cuda.Stream] = None):
+    def __init__(self, device: torch.device, depth: int = 2, stream: Optional[torch.cuda.Stream] = None,
+                 on_staged=None):
+        """on_staged(slot, *device_tensors): called by put() right after the copies of a batch were enqueued, with
+        the copy stream current -- index work that depends on the batch alone (TTEmbeddingBag.prepare) then runs
+        beside the compute stream's current step; get() makes the compute stream wait for it."""
+        self.on_staged = on_staged
         if depth < 2:
             raise ValueError("HostBatchPipeline: depth must be at least 2 to overlap anything")
         self.device = torch.device(device)
@@ -70,6 +75,8 @@ class HostBatchPipeline:
             for b, h in zip(bufs, host):
                 b.copy_(h, non_blocking=True)
                 self.h2d_bytes += h.numel() * h.element_size()
+            if self.on_staged is not None:
+                self.on_staged(slot, *bufs)
         finally:
             torch.cuda.set_stream(prev)
         self.ready[slot].record(self.copy_stream)

@@ -51,6 +51,47 @@ def _shape_tuple(p, q, r, num_tables):
             int(num_tables))
 
 
+def tt_plan(num_tables: int, B: int, tt_p_shapes: List[int], tt_q_shapes: List[int], tt_ranks: List[int],
+            nnz: int, indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor, slot: int,
+            device=None) -> bool:
+    """Build the index plan of a batch ahead of its tt_forward, on torch's CURRENT stream, into plan slot `slot`
+    (0 / 1; the batch being processed meanwhile uses the other one).  Not an op of the reference: its forward
+    splits the indices inside every call (FBTT/tt_embeddings_cuda.cu:757-921); here a data loader that knows
+    the next batch prepares it beside the host-to-device copy (pipeline.HostBatchPipeline(on_staged=...)).
+    tt_forward / tt_*_backward recognise the prepared batch by its tensors and skip the plan.  The caller orders
+    the streams (the forward's stream must wait for this one).  Returns False when the shape has no index plan
+    (shape-generic kernels): nothing was prepared, the forward simply plans itself."""
+    dev = indices.device if device is None else device
+    shape = _ttg.make_shape(tt_p_shapes, tt_q_shapes, tt_ranks, num_tables)
+    nnz = int(nnz)
+    if nnz == 0:
+        return False
+    _ttg.require_cuda(indices, "indices", torch.int64)
+    _ttg.require_cuda(rowidx, "rowidx", torch.int64)
+    _ttg.require_cuda(tableidx, "tableidx", torch.int64)
+    with _ttg.on_device(dev):
+        lib = _ttg.lib()
+        nbytes = _ttg.tt_workspace_bytes(shape, B, nnz)
+        ws = _ttg.workspace.get(dev, nbytes)
+        # the plan is built BESIDE the batch in flight: only under the layout that batch uses (same shape, B, nnz)
+        if not _ttg.workspace.same_layout(dev, (shape.key, int(B), nnz), adopt=False):
+            return False
+        _ttg.workspace.same_layout(dev, (shape.key, int(B), nnz))
+        flags = EXTRA_FLAGS | (_ttg.FLAG_PLAN_SLOT1 if slot else 0)
+        rc = lib.ttg_tt_plan(C.byref(shape), B, nnz, _ttg.ptr(indices), _ttg.ptr(rowidx), _ttg.ptr(tableidx),
+                             _ttg.ptr(ws), ws.numel(), flags, _ttg.stream_of(dev))
+        if rc == -4:                                # TTG_ENOTSUP
+            return False
+        _ttg.check(rc, "tt_plan")
+        _ttg.workspace.set_ready(dev, slot, _ttg.index_key_of(_plan_tag(), indices, rowidx, nnz, B, shape.key),
+                                 keep=(indices, rowidx))
+        # whatever batch's full plan (plan + table) this slot held is gone
+        cur = _ttg.workspace.plan(dev)
+        if cur is not None and cur[-1] == slot:
+            _ttg.workspace.set_plan(dev, None)
+    return True
+
+
 def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: List[int],
                tt_q_shapes: List[int], tt_ranks: List[int], L: torch.Tensor, nnz: int,
                indices: torch.Tensor, rowidx: torch.Tensor, tableidx: torch.Tensor,
@@ -74,14 +115,24 @@ def tt_forward(batch_count: int, num_tables: int, B: int, D: int, tt_p_shapes: L
         nbytes = _ttg.tt_workspace_bytes(shape, B, nnz)
         ws = _ttg.workspace.get(dev, nbytes)
         cp = _ttg.ptr_array(cores)
+        flags, slot = EXTRA_FLAGS, 0
+        _ttg.workspace.same_layout(dev, (shape.key, int(B), nnz))
+        if nnz > 0:
+            ready = _ttg.workspace.ready_slot(dev, _ttg.index_key_of(_plan_tag(), indices, rowidx, nnz, B,
+                                                                     shape.key))
+            if ready is not None:                  # tt_plan prepared this batch
+                slot = ready
+                flags |= _ttg.FLAG_PLAN_READY | (_ttg.FLAG_PLAN_SLOT1 if slot else 0)
+            else:                                  # planning in slot 0 overwrites what was prepared there
+                _ttg.workspace.drop_ready(dev, 0)
         rc = lib.ttg_tt_forward(C.byref(shape), B, nnz, _ttg.ptr(indices), _ttg.ptr(rowidx),
                                 _ttg.ptr(tableidx), cp, _ttg.ptr(output), _ttg.ptr(ws),
-                                ws.numel(), EXTRA_FLAGS, _ttg.stream_of(dev))
+                                ws.numel(), flags, _ttg.stream_of(dev))
         _ttg.check(rc, "tt_forward")
         if nnz > 0:
             _ttg.workspace.set_plan(dev, _ttg.plan_key_of(
                 _plan_tag(), indices, rowidx, nnz, B,
-                shape.key, tt_cores),          # the caller's tensors: a Parameter's own version counter
+                shape.key, tt_cores) + (slot,),   # the caller's tensors: a Parameter's own version counter
                 keep=(indices, rowidx))
     return output
 
@@ -107,6 +158,7 @@ def tt_rows_range(first_row: int, num_rows: int, tt_p_shapes: List[int], tt_q_sh
             return None
         out = torch.empty((int(num_rows), D), dtype=torch.float32, device=dev)
         ws = _ttg.workspace.get(dev, nbytes)
+        _ttg.workspace.same_layout(dev, ("rows_range", shape.key))   # its own carving: prepared plans are gone
         _ttg.workspace.set_plan(dev, None)          # the workspace no longer holds a batch's plan
         rc = lib.ttg_tt_rows_range(C.byref(shape), int(first_row), int(num_rows), _ttg.ptr_array(cores),
                                    _ttg.ptr(out), _ttg.ptr(ws), ws.numel(), EXTRA_FLAGS,
@@ -164,14 +216,20 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
         lib = _ttg.lib()
         nbytes = _ttg.tt_workspace_bytes(shape, B, nnz)
         ws = _ttg.workspace.get(dev, nbytes)
+        _ttg.workspace.same_layout(dev, (shape.key, int(B), nnz))
         flags = 0
         key = None
         if nnz > 0:
             key = _ttg.plan_key_of(_plan_tag(), indices, rowidx, nnz, B,
                                    shape.key,
                                    tt_cores)
-            if _ttg.workspace.plan(dev) == key:
+            cur = _ttg.workspace.plan(dev)
+            if cur is not None and cur[:-1] == key:
                 flags |= _ttg.FLAG_PLAN_VALID  # the forward's sort is still in the workspace
+                if cur[-1]:
+                    flags |= _ttg.FLAG_PLAN_SLOT1
+            else:
+                _ttg.workspace.drop_ready(dev, 0)  # this call plans in slot 0
         cp = _ttg.ptr_array(cores)
         dp = _ttg.ptr_array(d_cores)
         rc = lib.ttg_tt_backward(C.byref(shape), optim, float(lr), float(eps), B, nnz,
@@ -184,7 +242,7 @@ def _backward(optim, D, lr, eps, tt_p_shapes, tt_q_shapes, tt_ranks, nnz, indice
                 # the cores were updated in place by the kernel: the group table is stale
                 _ttg.workspace.set_plan(dev, None)
             elif not flags:
-                _ttg.workspace.set_plan(dev, key, keep=(indices, rowidx))
+                _ttg.workspace.set_plan(dev, key + (0,), keep=(indices, rowidx))
     return d_cores
 
 

@@ -60,6 +60,14 @@ enum {
   TTG_FLAG_FFMA = 16,         /* fp32 FFMA kernels instead of the tensor-core kernels     */
   TTG_FLAG_MMA_SYNC = 32,     /* force the mma.sync (warp-level) tensor-core kernels: the default,
                                  the flag exists so that a caller can name it           */
+  TTG_FLAG_PLAN_READY = 128,  /* forward: the workspace slot holds the index plan ttg_tt_plan built for
+                                 the SAME (indices, rowidx, tableidx, nnz, B); only the group table is
+                                 still computed (it depends on the cores)              */
+  TTG_FLAG_PLAN_SLOT1 = 256,  /* use the second of the two plan slots of the workspace (ttg_tt_plan,
+                                 forward and backward of one batch must name the same slot) */
+  TTG_FLAG_SHARE_SMS = 512,   /* the persistent row kernels leave 8 of the 148 SMs to other streams (a CTA
+                                 of theirs takes a whole register file, so nothing co-resides with them):
+                                 for callers that run ttg_tt_plan, a sampler or copies beside a step */
   TTG_FLAG_TCGEN05 = 64       /* the tcgen05 / tensor-memory kernels (csrc/tt_tc5.cu; q0 = 4, ranks
                                  16,16, batch dense in (i1, i2) groups): same results, measured
                                  slower than the mma.sync kernels on B200 at the BASELINE batch
@@ -106,6 +114,19 @@ int ttg_tt_forward(const ttg_shape* shape, int64_t B, int64_t nnz,
                    const float* const* host_core_ptrs, /* host array of T device pointers */
                    float* output, void* workspace, size_t workspace_bytes, int32_t flags,
                    void* stream);
+
+/* The index plan of a batch alone: sorted keys, output rows, group counters and bucket starts depend on
+ * (indices, rowidx, tableidx) only, so a caller that knows the next batch -- the data loader's prefetch, which the
+ * reference gets from DGL's DataLoader (sage_dgl_partition.py:141-154) -- builds its plan on another stream
+ * while the current batch is still being processed, into the plan slot the current batch does not use
+ * (TTG_FLAG_PLAN_SLOT1 selects the second slot), and then calls ttg_tt_forward with TTG_FLAG_PLAN_READY and
+ * the same slot flag.  It replaces the index split at the head of the reference's forward
+ * (FBTT/tt_embeddings_cuda.cu:757-921 / :1015-1027), which there runs inside every call.  Same workspace, same
+ * (shape, B, nnz) as the forward that follows; TTG_ENOTSUP for shapes without the sorted kernels (the caller then
+ * simply does not pass TTG_FLAG_PLAN_READY). */
+int ttg_tt_plan(const ttg_shape* shape, int64_t B, int64_t nnz, const int64_t* indices,
+                const int64_t* rowidx, const int64_t* tableidx, void* workspace, size_t workspace_bytes,
+                int32_t flags, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (b) backward + optimizer.

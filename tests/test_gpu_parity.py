@@ -700,3 +700,70 @@ def test_plan_is_rebuilt_after_a_raw_pointer_core_update(ttg_lib):
     want = orc.tt_backward_dense(p, q, r, [c.cpu().numpy() for c in cores], idx, row, dO)
     for t in range(3):
         assert rel_err(d2[t].cpu().numpy(), want[t]) < TOL, "core %d: stale group table" % t
+
+
+def test_plan_built_ahead_on_another_stream(ttg_lib):
+    """ttg_tt_plan: the index plan of the next batch built on a side stream into the other plan slot while the
+    current batch runs; the forward / backward that follow recognise it (same tensors) and give bit-identical
+    results to the calls that plan for themselves.  A batch of another size is refused (the workspace layout
+    depends on nnz) and then simply plans for itself."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = SHAPES["products"]
+    D = 100
+    cores = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 41)]
+    g = torch.Generator().manual_seed(3)
+    nnz = 50000
+    batches = [torch.randint(0, n_emb, (nnz,), generator=g).to(DEV) for _ in range(3)]
+    dOs = [(torch.rand(1, nnz, D, generator=g) * 0.1).to(DEV) for _ in range(3)]
+    row = torch.arange(nnz, device=DEV)
+    tb = torch.zeros_like(row)
+    want = []
+    for k in range(3):
+        o = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, batches[k], row, tb, cores)
+        d = te.tt_dense_backward(1000, D, p, q, r, None, nnz, batches[k], row, tb, dOs[k], cores)
+        want.append((o.clone(), [x.clone() for x in d]))
+    side = torch.cuda.Stream()
+    cur = torch.cuda.current_stream()
+    assert te.tt_plan(1, nnz, p, q, r, nnz, batches[0], row, tb, 0)
+    for k in range(3):
+        if k + 1 < 3:                       # plan of batch k + 1 beside batch k
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                assert te.tt_plan(1, nnz, p, q, r, nnz, batches[k + 1], row, tb, (k + 1) & 1)
+        assert _ttg.workspace.ready_slot(torch.device(DEV), _ttg.index_key_of(
+            te._plan_tag(), batches[k], row, nnz, nnz, _ttg.make_shape(p, q, r, 1).key)) == (k & 1)
+        o = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, batches[k], row, tb, cores)
+        d = te.tt_dense_backward(1000, D, p, q, r, None, nnz, batches[k], row, tb, dOs[k], cores)
+        cur.wait_stream(side)
+        assert torch.equal(o, want[k][0])
+        for a, b in zip(d, want[k][1]):
+            # the bucket plan orders the rows of a group by atomics: fp32 sums reorder between two plans
+            assert float((a - b).abs().max() / b.abs().max()) < 1e-6
+    # another batch size: not prepared (the layout would differ), the forward plans for itself
+    small = batches[0][:30000].contiguous()
+    assert not te.tt_plan(1, 30000, p, q, r, 30000, small, row[:30000].contiguous(), tb[:30000].contiguous(), 1)
+    o = te.tt_forward(1000, 1, 30000, D, p, q, r, None, 30000, small, row[:30000].contiguous(),
+                      tb[:30000].contiguous(), cores)
+    assert torch.equal(o[0], want[0][0][0, :30000])
+
+
+def test_module_prepare_matches_plain_forward(ttg_lib):
+    from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
+    torch.manual_seed(5)
+    m = TTEmbeddingBag(2449029, 100, [16, 16], [125, 140, 140], [4, 5, 5], optimizer=OptimType.SGD,
+                       learning_rate=0.01, sparse=False, use_cache=False, weight_dist="normal").to(DEV)
+    g = torch.Generator().manual_seed(7)
+    idx = torch.randint(0, 2449029, (40000,), generator=g).to(DEV)
+    off = torch.arange(40001, device=DEV)
+    want = m(idx, off).detach().clone()
+    assert m.prepare(idx, off, 1)
+    got = m(idx, off)
+    assert torch.equal(got.detach(), want)
+    got.sum().backward()
+    g1 = [c.grad.clone() for c in m.tt_cores]
+    for c in m.tt_cores:
+        c.grad = None
+    m(idx, off).sum().backward()
+    for a, c in zip(g1, m.tt_cores):
+        assert float((a - c.grad).abs().max() / c.grad.abs().max()) < 1e-6
