@@ -355,12 +355,12 @@ def run_ours(args, shape):
     from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
 
     lib = _ttg.lib()
-    # --plan-ahead-value: the device-resident loop builds the next batch's plan on a forked stream and the row
-    # kernels leave 8 SMs to it (TTG_FLAG_SHARE_SMS).  Measured neutral on B200 (0.178 vs 0.173 ms/step: a CTA of
-    # the row kernels takes a whole register file and the dependent-launch CTAs of the next kernel take the spare
-    # SMs, so the plan still runs behind the backward; profiles/r2_step_timeline.txt), hence off by default.  The
-    # end-to-end loop prepares batches on the copy stream either way (--no-plan-ahead switches that off).
-    share = _ttg.FLAG_SHARE_SMS if args.plan_ahead_value else 0
+    # The device-resident loop builds the next batch's plan on a stream forked at the START of the step (beside the
+    # group table and the head of the forward): 172 vs 179 us per step.  Forked behind the forward, or with 8 SMs
+    # left free (TTG_FLAG_SHARE_SMS), it gains nothing: a CTA of the row kernels takes a whole register file and
+    # the dependent-launch CTAs of the next kernel take the spare SMs (profiles/r2_step_timeline.txt).
+    # --no-plan-ahead restores the round-1 flow in both loops.
+    share = 0
     te.EXTRA_FLAGS = int(args.flags) | share
     p, q, ranks, N = shape["p"], shape["q"], shape["ranks"], shape["n"]
     rr = [1] + ranks + [1]
@@ -396,7 +396,7 @@ def run_ours(args, shape):
     def plan_next(k):
         """the index plan of the NEXT batch, beside this step's kernels (it depends on the indices only): a fork
         of the current stream, joined at the end of the step; tt_forward finds it ready and skips its own"""
-        if not args.plan_ahead_value:
+        if args.no_plan_ahead:
             return None
         cur = torch.cuda.current_stream(dev)
         plan_stream.wait_stream(cur)
@@ -406,10 +406,8 @@ def run_ours(args, shape):
         return cur
 
     def raw_step(k):
-        # forward first, then the fork: the plan of batch k + 1 runs beside the long backward kernels instead of
-        # competing with the start of this step's own chain
-        out = te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx, cores)
         cur = plan_next(k)
+        out = te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx_dev[k], rowidx, tableidx, cores)
         raw_backward(k)
         if cur is not None:
             cur.wait_stream(plan_stream)
@@ -724,8 +722,8 @@ def run_ours(args, shape):
                                   else "fp32 via 3xTF32 split on tensor cores, fp32 accumulation"),
                    "l2": "4 rotating batches, 212 MB touched per step (> 126 MB L2)",
                    "launch": "cuda_graph" if use_graph else "eager",
-                   "index_plan": ("of batch i + 1 built beside step i on a forked stream (ttg_tt_plan, second plan "
-                                  "slot)") if args.plan_ahead_value else "inside the forward",
+                   "index_plan": "inside the forward" if args.no_plan_ahead else
+                                 "of batch i + 1 built beside step i on a forked stream (ttg_tt_plan, second plan slot)",
                    "parallelism": "dp%d, replicated cores%s" % (
                        world, "" if world == 1 else
                        ", d_cores exchanged and the update applied by one kernel over NVLink peer memory"
@@ -785,10 +783,8 @@ def main():
                          "(8 = plain TF32 tensor-core mode, 16 = fp32 FFMA kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-plan-ahead", action="store_true",
-                    help="e2e: build every batch's index plan inside its own forward (round-1 behaviour) instead "
-                         "of on the copy stream beside the running step")
-    ap.add_argument("--plan-ahead-value", action="store_true",
-                    help="device-resident loop: plan of batch i + 1 on a forked stream beside step i")
+                    help="build every batch's index plan inside its own forward (round-1 behaviour) instead of "
+                         "beside the running step (forked stream / copy stream)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the sub-records (GraphSAGE epoch of configs 2 and 3, papers-shape step)")
     ap.add_argument("--sage-epochs", type=int, default=2, help="timed GraphSAGE epochs per sub-record")

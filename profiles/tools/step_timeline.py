@@ -10,7 +10,7 @@ from torch.profiler import ProfilerActivity, profile
 import tt_embeddings as te
 
 ahead = "--plan-ahead" in sys.argv
-if ahead:
+if ahead and '--share' in sys.argv:
     te.EXTRA_FLAGS = 512      # TTG_FLAG_SHARE_SMS
 p, q, rr, N, D, nnz = [125, 140, 140], [4, 5, 5], [1, 16, 16, 1], 2449029, 100, 262144
 dev = torch.device("cuda", 0)
@@ -23,8 +23,13 @@ side = torch.cuda.Stream(dev)
 
 def step(k):
     cur = torch.cuda.current_stream(dev)
+    first = "--fork-first" in sys.argv
+    if ahead and first:
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            te.tt_plan(1, nnz, p, q, rr, nnz, idx[(k + 1) % 4], row, tb, (k + 1) & 1)
     te.tt_forward(1000, 1, nnz, D, p, q, rr, None, nnz, idx[k], row, tb, cores)
-    if ahead:
+    if ahead and not first:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             te.tt_plan(1, nnz, p, q, rr, nnz, idx[(k + 1) % 4], row, tb, (k + 1) & 1)
