@@ -19,6 +19,7 @@ PEER_HANDLE_BYTES = 64
 OPTIM_SGD, OPTIM_ADAGRAD, OPTIM_DENSE = 0, 1, 2
 FLAG_FORCE_GENERIC, FLAG_PLAN_VALID, FLAG_DETERMINISTIC, FLAG_TF32, FLAG_FFMA = 1, 2, 4, 8, 16
 FLAG_MMA_SYNC, FLAG_TCGEN05, FLAG_PLAN_READY, FLAG_PLAN_SLOT1, FLAG_SHARE_SMS = 32, 64, 128, 256, 512
+FLAG_RIGHT = 1024
 
 
 class Shape(C.Structure):

@@ -131,6 +131,11 @@ __device__ __forceinline__ uint32_t ld_dep_u32(const void* p) {
   return v;
 }
 __device__ __forceinline__ int32_t ld_dep_s32(const void* p) { return (int32_t)ld_dep_u32(p); }
+__device__ __forceinline__ float ld_dep_f32(const void* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ int4 ld_dep_int4(const void* p) {
   int4 v;
   asm volatile("ld.global.v4.s32 {%0,%1,%2,%3}, [%4];"
@@ -244,6 +249,8 @@ int r_table(const TTDev& tt, const RPlan& pl, cudaStream_t stream);
 int r_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream);
 int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
                int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream);
+// the same path on mma.sync (warp-level tensor cores), tt_rmma.cu
+int rm_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream);
 // d_core0 = sum of `nparts` partial copies (fixed order) + optimizer step on all three cores, tt_mma.cu
 int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float* const* dcore, int32_t optim,
                        float lr, float eps, float* const* state, cudaStream_t stream);

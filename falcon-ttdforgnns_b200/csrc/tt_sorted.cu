@@ -1574,7 +1574,8 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
 // tcgen05 kernels (right-grouped): opt-in (TTG_FLAG_TCGEN05), when the shape has them and the batch is dense
 // in groups
 bool use_r(const TTDev& tt, const SortedWs& w, int32_t flags) {
-  return w.tabR != nullptr && (flags & TTG_FLAG_TCGEN05) && !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
+  return w.tabR != nullptr && (flags & (TTG_FLAG_TCGEN05 | TTG_FLAG_RIGHT)) &&
+         !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
 }
 
 RPlan r_plan(const SortedWs& w) {
@@ -1645,7 +1646,9 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
       rc = r_table(tt, r_plan(w), stream);
       if (rc != TTG_OK) return rc;
     }
-    return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
+    if (flags & TTG_FLAG_TCGEN05)
+      return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
+    return rm_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
   }
   if (use_mma_fwd(tt, w, flags)) {
     if (zero_only) {  // the plan of this batch is in the workspace (and, PLAN_VALID, its group table)

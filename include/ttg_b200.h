@@ -68,6 +68,8 @@ enum {
   TTG_FLAG_SHARE_SMS = 512,   /* the persistent row kernels leave 8 of the 148 SMs to other streams (a CTA
                                  of theirs takes a whole register file, so nothing co-resides with them):
                                  for callers that run ttg_tt_plan, a sampler or copies beside a step */
+  TTG_FLAG_RIGHT = 1024,      /* the right-grouped mma.sync kernels (csrc/tt_rmma.cu; q0 = 4, ranks 16,16, batch
+                                 dense in (i1, i2) groups): groups (i1, i2), tr1 = core1 core2 from a table   */
   TTG_FLAG_TCGEN05 = 64       /* the tcgen05 / tensor-memory kernels (csrc/tt_tc5.cu; q0 = 4, ranks
                                  16,16, batch dense in (i1, i2) groups): same results, measured
                                  slower than the mma.sync kernels on B200 at the BASELINE batch

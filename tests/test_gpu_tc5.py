@@ -32,17 +32,20 @@ def _cores(p, q, r, n_emb, seed, num_tables=1):
             for t in range(3)]
 
 
-@pytest.fixture
-def te(ttg_lib):
+@pytest.fixture(params=[64, 1024], ids=["tcgen05", "right_mma"])
+def te(ttg_lib, request):
+    """the two engines of the right-grouped path: TTG_FLAG_TCGEN05 and TTG_FLAG_RIGHT (mma.sync)"""
     import tt_embeddings
+    global TC5
+    TC5 = request.param
     tt_embeddings.EXTRA_FLAGS = 0
     yield tt_embeddings
     tt_embeddings.EXTRA_FLAGS = 0
 
 
-def _fwd(te, shape, cores, idx, row, B, tb=None, num_tables=1, flags=TC5):
+def _fwd(te, shape, cores, idx, row, B, tb=None, num_tables=1, flags=None):
     p, q, r, _ = shape
-    te.EXTRA_FLAGS = flags
+    te.EXTRA_FLAGS = TC5 if flags is None else flags
     try:
         idx_t = torch.from_numpy(idx).to(DEV)
         row_t = torch.from_numpy(row).to(DEV)
@@ -149,10 +152,10 @@ def test_forward_tf32_mode_stated_bound(te):
     assert rel_err(out.cpu().numpy(), want) < 3e-3
 
 
-def _bwd(te, shape, cores, idx, row, dO, tb=None, flags=TC5, mode="dense", lr=0.1, state=None):
+def _bwd(te, shape, cores, idx, row, dO, tb=None, flags=None, mode="dense", lr=0.1, state=None):
     p, q, r, _ = shape
     D = int(np.prod(q))
-    te.EXTRA_FLAGS = flags
+    te.EXTRA_FLAGS = TC5 if flags is None else flags
     try:
         idx_t = torch.from_numpy(idx).to(DEV)
         row_t = torch.from_numpy(row).to(DEV)
