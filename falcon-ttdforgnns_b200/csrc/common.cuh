@@ -242,6 +242,7 @@ struct RPlan {
   float* tab;              // [groups][2][r1 * q1 q2]  tr1 operand images, hi plane then lo plane
   float* S1;               // [groups][r1][q1 q2]      d(tr1), written by the backward row kernel
   float* d0parts;          // [kNumSMs][core0 elements] per-CTA copies of d_core0
+  float* d2parts;          // [tables][p1][p2][r2 q2]  d_core2 per i1 (right-grouped mma.sync cores kernel)
 };
 bool r_supported(const TTDev& tt);
 size_t r_table_floats(const TTDev& tt);
@@ -251,8 +252,15 @@ int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_out
                int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream);
 // the same path on mma.sync (warp-level tensor cores), tt_rmma.cu
 int rm_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream);
+int rm_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
+                int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream);
+bool rm_supported(const TTDev& tt);
+// d_core1 / d_core2 from S1 (tt_tc5.cu)
+int r_cores(const TTDev& tt, const RPlan& pl, float* const* dcore, cudaStream_t stream);
 // d_core0 = sum of `nparts` partial copies (fixed order) + optimizer step on all three cores, tt_mma.cu
-int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float* const* dcore, int32_t optim,
-                       float lr, float eps, float* const* state, cudaStream_t stream);
+// (+ d_core2 = sum over its n2parts copies per table when d2parts is given)
+int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, const float* d2parts, int n2parts,
+                       float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
+                       cudaStream_t stream);
 
 }  // namespace ttg

@@ -1120,6 +1120,11 @@ struct MmaFinalArgs {
   int32_t optim;
   float lr, eps;
   int nb0;                   // blocks that reduce d_core0 (kFinCols float4 columns each)
+  // right-grouped kernels: d_core2 also arrives as partial copies, [table][part][e2t] (one part per i1)
+  const float* d2parts;
+  int n2parts;
+  int64_t e2t;               // elements of one table's core2
+  int nb2;                   // blocks that reduce d_core2
 };
 
 __device__ __forceinline__ void final_update4(const MmaFinalArgs& a, int t, int64_t o, float4 g) {
@@ -1152,20 +1157,29 @@ constexpr int kFinPer = 12;      // partial copies one thread sums (all loads in
 __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
   __shared__ float4 sm[kFinSlices][kFinCols];
   pdl_wait();
-  if ((int)blockIdx.x < a.nb0) {
-    // 16 float4 columns x 16 slices of the i1 axis; a slice is summed in order, then the slices
+  if ((int)blockIdx.x < a.nb0 + a.nb2) {
+    // 16 float4 columns x 16 slices of the partial copies; a slice is summed in order, then the slices
+    const bool c2 = (int)blockIdx.x >= a.nb0;
+    const int t = c2 ? 2 : 0;
     const int col = threadIdx.x % kFinCols, sl = threadIdx.x / kFinCols;
-    const int64_t o = ((int64_t)blockIdx.x * kFinCols + col) * 4;
+    const int64_t o = ((int64_t)(c2 ? blockIdx.x - a.nb0 : blockIdx.x) * kFinCols + col) * 4;
+    const int64_t e = c2 ? a.e2 : a.e0;
+    const int nparts = c2 ? a.n2parts : a.nparts;
+    const int64_t stride = c2 ? a.e2t : a.e0;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (o < a.e0) {
-      const int per = (a.nparts + kFinSlices - 1) / kFinSlices;
-      const int lo = sl * per, hi = (lo + per < a.nparts) ? lo + per : a.nparts;
+    if (o < e) {
+      const float* base = a.d0parts + o;
+      if (c2) {
+        const int64_t tb = o / a.e2t;
+        base = a.d2parts + tb * a.n2parts * a.e2t + (o - tb * a.e2t);
+      }
+      const int per = (nparts + kFinSlices - 1) / kFinSlices;
+      const int lo = sl * per, hi = (lo + per < nparts) ? lo + per : nparts;
       for (int p = lo; p < hi; p += kFinPer) {
         float4 v[kFinPer];
 #pragma unroll
         for (int u = 0; u < kFinPer; ++u)
-          v[u] = (p + u < hi) ? ld_dep_float4(a.d0parts + (size_t)(p + u) * a.e0 + o)
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[u] = (p + u < hi) ? ld_dep_float4(base + (size_t)(p + u) * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int u = 0; u < kFinPer; ++u) {
           g.x += v[u].x;
@@ -1177,7 +1191,7 @@ __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
     }
     sm[sl][col] = g;
     __syncthreads();
-    if (sl == 0 && o < a.e0) {
+    if (sl == 0 && o < e) {
 #pragma unroll
       for (int q = 1; q < kFinSlices; ++q) {
         g.x += sm[q][col].x;
@@ -1185,12 +1199,14 @@ __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
         g.z += sm[q][col].z;
         g.w += sm[q][col].w;
       }
-      *reinterpret_cast<float4*>(a.dcore[0] + o) = g;
-      final_update4(a, 0, o, g);
+      *reinterpret_cast<float4*>(a.dcore[t] + o) = g;
+      final_update4(a, t, o, g);
     }
   } else {
-    const int64_t i = ((int64_t)(blockIdx.x - a.nb0) * 256 + threadIdx.x) * 4;
-    if (i >= a.e1 + a.e2) return;
+    // cores whose gradient is complete: the optimizer only (core1, and core2 unless it came in parts)
+    const int64_t i = ((int64_t)(blockIdx.x - a.nb0 - a.nb2) * 256 + threadIdx.x) * 4;
+    const int64_t n12 = a.e1 + (a.d2parts ? 0 : a.e2);
+    if (i >= n12) return;
     const int t = (i < a.e1) ? 1 : 2;
     const int64_t o = (t == 1) ? i : i - a.e1;
     final_update4(a, t, o, *reinterpret_cast<const float4*>(a.dcore[t] + o));
@@ -1445,8 +1461,9 @@ int mma_cores_finalize(const TTDev& tt, const MmaPlan& pl, float* const* dcore, 
   return e->finalize(tt, pl, dcore, optim, lr, eps, state, stream);
 }
 
-int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float* const* dcore, int32_t optim,
-                       float lr, float eps, float* const* state, cudaStream_t stream) {
+int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, const float* d2parts, int n2parts,
+                       float* const* dcore, int32_t optim, float lr, float eps, float* const* state,
+                       cudaStream_t stream) {
   MmaFinalArgs a;
   memset(&a, 0, sizeof(a));
   a.e0 = (int64_t)tt.num_tables * tt.p[0] * tt.cols[0];
@@ -1454,6 +1471,9 @@ int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float*
   a.e2 = (int64_t)tt.num_tables * tt.p[2] * tt.cols[2];
   a.nparts = nparts;
   a.d0parts = d0parts;
+  a.d2parts = d2parts;
+  a.n2parts = n2parts;
+  a.e2t = (int64_t)tt.p[2] * tt.cols[2];
   for (int t = 0; t < 3; ++t) {
     a.dcore[t] = dcore[t];
     a.core[t] = tt.core[t];
@@ -1463,9 +1483,10 @@ int mma_finalize_parts(const TTDev& tt, const float* d0parts, int nparts, float*
   a.lr = lr;
   a.eps = eps;
   a.nb0 = (int)ceil_div(a.e0, 4 * kFinCols);
-  const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(a.e1 + a.e2, 1024);
+  a.nb2 = d2parts ? (int)ceil_div(a.e2, 4 * kFinCols) : 0;
+  const int nb12 = (optim == TTG_OPTIM_DENSE) ? 0 : (int)ceil_div(a.e1 + (d2parts ? 0 : a.e2), 1024);
   prof_begin(K_REDUCE, stream);
-  TTG_CUDA(launch_pdl(mma_finalize_kernel, dim3(a.nb0 + nb12), dim3(256), 0, stream, a));
+  TTG_CUDA(launch_pdl(mma_finalize_kernel, dim3(a.nb0 + a.nb2 + nb12), dim3(256), 0, stream, a));
   prof_end(K_REDUCE, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;

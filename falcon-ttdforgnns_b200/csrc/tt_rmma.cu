@@ -91,6 +91,8 @@ struct RmArgs {
   int32_t c0_rows;
   int32_t hp;
   FastDiv div_p0, div_hp;
+  int32_t nnz;            // rows the plan was built for (>= the rows it holds: invalid indices are dropped)
+  int32_t rpw;            // backward: nominal rows per warp
 };
 
 // core0 -> shared memory, hi plane (as stored) and lo plane, [c0_rows * 4][kCS]
@@ -271,6 +273,592 @@ __global__ void __launch_bounds__(kThreads, 1) rm_fwd_kernel(RmArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// backward rows
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// shared-memory float adds without the serialising loop nvcc emits for atomicAdd(float*) on shared memory: read
+// all targets, try one compare-and-swap each (independent, latencies overlap); only a loser takes the loop
+__device__ __forceinline__ uint32_t lds_volatile_u32(const float* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t cas_shared_u32(float* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(smem_u32(p)), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+template <int N>
+__device__ __forceinline__ void shared_add_batch(float* const (&addr)[N], const float (&val)[N]) {
+  uint32_t old[N], got[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) old[i] = lds_volatile_u32(addr[i]);
+  uint32_t lost = 0;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    got[i] = cas_shared_u32(addr[i], old[i], __float_as_uint(__uint_as_float(old[i]) + val[i]));
+    lost |= got[i] ^ old[i];
+  }
+  if (lost != 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (got[i] != old[i]) atomicAdd(addr[i], val[i]);
+  }
+}
+
+// d_core0 accumulators in shared memory: k1 of row (i0, j0) sits at k1 ^ swizzle, which spreads the lanes of a
+// tile's scatter (2 rows x 4 j0 x 4 even k1) over the banks
+__device__ __forceinline__ int d0_swizzle(int row) { return ((row >> 1) & 1) | (((row >> 2) & 1) << 3); }
+
+constexpr int kCSB = 24;     // floats per (i0, j0) row of the backward's shared core0 copy: lanes (t, g) -> banks 24 t + g
+constexpr int kChain = 16;   // tiles (64 rows) a group's S1 stays in the accumulators
+#ifndef TTG_RM_BT
+#define TTG_RM_BT 512
+#endif
+#ifndef TTG_RM_RING
+#define TTG_RM_RING 16
+#endif
+constexpr int kBT = TTG_RM_BT, kBW = kBT / 32;   // threads and warps of the backward row kernel
+constexpr int kRing = TTG_RM_RING;   // d_output rows a warp keeps in shared memory: four in use, the others on their way
+
+// position of column c of pair j0 inside a staged d_output row (D = 128: the 8-column blocks of a pair are
+// permuted by j0 so that the four pairs of a row spread over the banks)
+template <int C>
+__device__ __forceinline__ int xoff(int j0, int c) {
+  return (C % 8 == 0) ? j0 * C + (c ^ (j0 << 3)) : j0 * C + c;
+}
+
+// Which column c of a pair the tensor-core index stands for.  Any bijection works as long as both operands of a
+// product use the same one; these make the four pairs of a staged row (25 j0 + c) and the rows of a tile meet
+// 32 different banks (D = 100; D = 128 gets there through xoff's permutation of the staged row).
+//   G0's k index (step ks, half h, lane t)          S1's n index (tile nt, lane g)
+template <int C>
+__device__ __forceinline__ constexpr int col_k(int ks, int h, int t) {
+  return (C % 8 == 0) ? t + 4 * h + 8 * ks : 2 * ks + h + 8 * t;
+}
+template <int C>
+__device__ __forceinline__ constexpr int col_n(int nt, int g) {
+  return (C % 8 == 0) ? g + 8 * nt : nt + 4 * g;
+}
+
+// B fragments of tr1[group]^T for G0 = X tr1^T: b[ks][nt][h] = tr1[k1 = g + 8 nt][c = col_k(ks, h, t)]
+template <int C, int TERMS>
+__device__ __forceinline__ void load_tr1_bwd(const float* tab, uint32_t group, int g, int t, uint32_t (&bh)[4][2][2],
+                                             uint32_t (&bl)[4][2][2]) {
+  // only the table's first plane is read: the low parts cost two instructions per register and group here,
+  // against a second 16 C floats from memory
+  const float* img = tab + (size_t)group * (2 * 16 * C) + (g >> 2) * (4 * C) + (g & 3);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = col_k<C>(ks, h, t);
+        const bool on = (C % 8 == 0) || c < C;
+        bh[ks][nt][h] = on ? __float_as_uint(ld_dep_f32(img + 2 * nt * (4 * C) + c * 4)) : 0u;
+      }
+  if (TERMS == 3) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) bl[ks][nt][h] = __float_as_uint(lo_of(__uint_as_float(bh[ks][nt][h])));
+  }
+}
+// the 16 C floats of a group's first plane on their way into L1 (one 128-byte line per lane)
+template <int C>
+__device__ __forceinline__ void prefetch_tr1(const float* tab, uint32_t group, int lane) {
+  if (lane < (16 * C * 4 + 127) / 128)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(tab + (size_t)group * (2 * 16 * C) + lane * 32));
+}
+
+// Rows are handed to warps in runs that begin and end at group boundaries, so that a group's S1 = A0^T X is
+// summed in one warp's registers and stored once.  first_start(x) = the first row >= x that begins a group.
+__device__ int first_group_start(const RmArgs& a, int x, int total, int lane) {
+  if (x <= 0) return 0;
+  while (x < total) {
+    const int r = x - 1 + lane;
+    const uint32_t key = ld_dep_u32(a.skeys + min(r, total - 1));
+    const uint32_t grp = fdiv(key, a.div_p0);
+    const uint32_t prev = __shfl_up_sync(kFull, grp, 1);
+    const uint32_t m = __ballot_sync(kFull, lane >= 1 && r < total && grp != prev);
+    if (m) return x - 1 + (__ffs(m) - 1);
+    x += 31;
+  }
+  return total;
+}
+
+#ifdef TTG_R_TIMING
+// per warp: globaltimer at kernel entry, after the wait for the preceding kernel, at the first tile, after the
+// last tile, and at the end (profiles/tools/rm_timing.py)
+__device__ unsigned long long g_rm_marks[148 * 32 * 6];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long v;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
+  return v;
+}
+#define RM_MARK(i)                                                                                     \
+  if (lane == 0) g_rm_marks[((size_t)blockIdx.x * kBW + warp) * 6 + (i)] = gtime()
+// cycles per phase of the tile loop, summed over the warps of CTA 3
+__device__ unsigned long long g_rm_phase[8];
+#define RM_PHASE_DECL long long ph_t = clock64(), ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define RM_PHASE(i)                      \
+  {                                      \
+    const long long now_ = clock64();    \
+    ph_acc[i] += now_ - ph_t;            \
+    ph_t = now_;                         \
+  }
+#define RM_PHASE_FLUSH                                                      \
+  if (blockIdx.x == 3 && lane == 0)                                         \
+    for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_rm_phase[i_], (unsigned long long)ph_acc[i_])
+#else
+#define RM_MARK(i)
+#define RM_PHASE_DECL
+#define RM_PHASE(i)
+#define RM_PHASE_FLUSH
+#endif
+
+template <int Q1, int Q2, int TERMS>
+__global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
+  constexpr int C = Q1 * Q2, D = 4 * C;
+  constexpr int RS = (C % 8 == 0) ? D + 4 : D;     // row stride inside the ring
+  constexpr int kRingFloats = kRing * RS + 8;      // + 8: the last pair's padded columns read past the last row
+  extern __shared__ __align__(16) float sm[];
+  // a tile's unused rows land behind the real ones: a row of zeros to multiply with in c0s, and one dummy
+  // accumulator row per warp in d0s (a shared one would make the warps' compare-and-swaps collide)
+  float* c0s = sm;                                              // [(c0_rows + 1) * 4][kCSB]
+  float* d0s = c0s + (size_t)(a.c0_rows + 1) * 4 * kCSB;        // [(c0_rows + kBW) * 64]
+  float* rings = d0s + (size_t)(a.c0_rows + kBW) * 64;       // [kBW][kRingFloats]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int j0 = g & 3, rg = g >> 2;
+  RM_MARK(0);
+  pdl_trigger();
+  for (int i = threadIdx.x; i < (a.c0_rows + 1) * 16; i += kBT) {
+    const int row = i >> 2, q = i & 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < a.c0_rows * 16) v = __ldg(reinterpret_cast<const float4*>(a.core0) + i);
+    *reinterpret_cast<float4*>(c0s + row * kCSB + 4 * q) = v;
+  }
+  for (int i = threadIdx.x; i < (a.c0_rows + kBW) * 16; i += kBT)
+    reinterpret_cast<float4*>(d0s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x; i < kBW * kRingFloats; i += kBT) rings[i] = 0.f;   // padded columns meet zeros, not NaNs
+  int total, rs, re;
+  pdl_wait();
+  __syncthreads();
+  RM_MARK(1);
+  // Rows are handed to warps in runs of about rpw that begin and end at group boundaries (a group's S1 is then
+  // summed in one warp's registers and stored once).  Everything the set-up needs is requested in one go: the
+  // row count, the windows of sorted rows at the nominal start (which also hold the boundary), and the keys
+  // around the nominal end.
+  const int nw = (int)gridDim.x * kBW;
+  const int w = (int)blockIdx.x * kBW + warp;
+  const int x1 = min(w * a.rpw, a.nnz), x2 = min((w + 1) * a.rpw, a.nnz);
+  auto load_key = [&](int at) -> uint32_t { return ld_dep_u32(a.skeys + max(0, min(at + lane, a.nnz - 1))); };
+  auto load_src = [&](int at) -> uint32_t { return ld_dep_u32(a.srow + max(0, min(at + lane, a.nnz - 1))); };
+  auto split_key = [&](uint32_t key, uint32_t& grp, int32_t& i0c) {
+    grp = fdiv(key, a.div_p0);
+    const uint32_t tbl = (a.c0_rows == a.p0) ? 0u : fdiv(grp, a.div_hp);
+    i0c = (int32_t)(tbl * a.p0 + (key - grp * (uint32_t)a.p0));
+  };
+  auto src_units = [&](uint32_t o) -> uint32_t { return (o & 0x7fffffffu) * (uint32_t)(D / 4); };   // 16-byte units
+  // One sorted row per lane and register: its group, its core0 row, and where its d_output row starts.  The
+  // window [cb, cb + 64) covers the tile and the look-ahead; [wb, wb + 64) the rows being requested.  What is
+  // loaded for a later window is only looked at when the window moves, so that nobody waits for the load.
+  int cb = max(x1 - 1, 0), wb = cb;
+  uint32_t gc, gn, oc, on, kraw, oraw;
+  int32_t ic, in;
+  {
+    const uint32_t k1 = load_key(cb), k2 = load_key(cb + 32), o1 = load_src(wb), o2 = load_src(wb + 32);
+    const uint32_t ke = load_key(max(x2 - 1, 0));
+    kraw = load_key(cb + 64);
+    oraw = load_src(wb + 64);
+    const int total_ = ld_dep_s32(a.base + a.num_groups);
+    split_key(k1, gc, ic);
+    split_key(k2, gn, in);
+    oc = src_units(o1);
+    on = src_units(o2);
+    // boundary at or after x: the first row x - 1 + l (l >= 1) that differs in group from the row before it
+    auto boundary = [&](int x, uint32_t grp) -> int {
+      if (x <= 0) return 0;
+      if (x >= total_) return total_;
+      const uint32_t prev = __shfl_up_sync(kFull, grp, 1);
+      const uint32_t m = __ballot_sync(kFull, lane >= 1 && (x - 1 + lane >= total_ || grp != prev));
+      if (m) return min(x - 1 + (__ffs(m) - 1), total_);
+      return first_group_start(a, x + 31, total_, lane);      // a group longer than the window
+    };
+    total = total_;
+    rs = boundary(x1, gc);
+    re = (w + 1 == nw) ? total_ : boundary(x2, fdiv(ke, a.div_p0));
+  }
+  float* ring = rings + warp * kRingFloats;
+  uint32_t bgh[4][2][2], bgl[4][2][2];
+  if (rs < re) {
+    if (rs - cb >= 32) {     // rare: the boundary lies beyond the first window
+      cb = wb = rs;
+      split_key(load_key(cb), gc, ic);
+      split_key(load_key(cb + 32), gn, in);
+      oc = src_units(load_src(wb));
+      on = src_units(load_src(wb + 32));
+      kraw = load_key(cb + 64);
+      oraw = load_src(wb + 64);
+    }
+    const int d0 = rs - cb;
+    load_tr1_bwd<C, TERMS>(a.tab, __shfl_sync(kFull, d0 < 32 ? gc : gn, d0 & 31), g, t, bgh, bgl);
+  }
+
+  if (rs < re) {
+    int pos = rs, issued = rs;
+    // lane's piece of a staged row: 16 bytes at ring_lane + slot * RS
+    float* ring_lane = ring + ((C % 8 == 0) ? xoff<C>(lane / (C / 4), 4 * (lane % (C / 4))) : 4 * lane);
+    const float4* src_lane = reinterpret_cast<const float4*>(a.d_output) + lane;
+    auto issue_rows = [&](int upto) {      // the next four rows, as far as they are below upto
+      if (issued - wb >= 32) {
+        wb += 32;
+        oc = on;
+        on = src_units(oraw);
+        oraw = load_src(wb + 64);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = issued + j, d = r - wb;
+        const uint32_t o = __shfl_sync(kFull, d < 32 ? oc : on, d & 31);
+        if (r < upto && lane < D / 4) cp_async16(ring_lane + ((r - rs) & (kRing - 1)) * RS, src_lane + o);
+      }
+      issued = min(issued + 4, max(upto, issued));
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kRing / 4 - 1; ++i) issue_rows(re);
+
+    float s1[4][4];
+    int chain = 0;
+    bool stored = false;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s1[nt][e] = 0.f;
+    RM_MARK(2);
+    RM_PHASE_DECL;
+    while (pos < re) {
+      if (pos - cb >= 32) {
+        cb += 32;
+        gc = gn;
+        ic = in;
+        split_key(kraw, gn, in);
+        kraw = load_key(cb + 64);
+      }
+      issue_rows(min(re, pos + kRing));
+      // the tile: rows pos .. pos + n - 1 of one group (n <= 4); lanes 0..7 look at rows pos + lane
+      const int dl = pos - cb + (lane & 7);
+      const uint32_t g1 = __shfl_sync(kFull, gc, dl & 31), g2 = __shfl_sync(kFull, gn, dl & 31);
+      const int32_t i1 = __shfl_sync(kFull, ic, dl & 31), i2 = __shfl_sync(kFull, in, dl & 31);
+      const uint32_t my_grp = dl < 32 ? g1 : g2;
+      const int32_t my_i0 = dl < 32 ? i1 : i2;
+      const uint32_t grp = __shfl_sync(kFull, my_grp, 0);
+      const uint32_t same = __ballot_sync(kFull, pos + (lane & 7) < re && my_grp == grp) & 0xffu;
+      const int n = min(4, __ffs(~same) - 1);
+      const bool group_ends = ((same >> n) & 1u) == 0;
+      const bool more = pos + n < re;
+      const uint32_t next_grp = __shfl_sync(kFull, my_grp, n);
+      if (group_ends && more) prefetch_tr1<C>(a.tab, next_grp, lane);
+      int i0r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = __shfl_sync(kFull, my_i0, j);
+        i0r[j] = (j < n) ? v : -1;
+      }
+      const int slot_pos = (pos - rs) & (kRing - 1);
+      RM_PHASE(0);
+      cp_async_wait<kRing / 4 - 1>();
+      __syncwarp();
+      RM_PHASE(1);
+#ifdef TTG_R_TIMING
+      if (pos == rs) RM_MARK(3);
+#endif
+
+      // ---- G0[pair][k1] = X[pair][c] tr1^T[c][k1] ----
+      float g0[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) g0[nt][e] = 0.f;
+      {
+        const float* pa = ring + ((slot_pos + rg) & (kRing - 1)) * RS;
+        const float* pb = ring + ((slot_pos + rg + 2) & (kRing - 1)) * RS;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const float x0 = pa[xoff<C>(j0, col_k<C>(ks, 0, t))], x2 = pa[xoff<C>(j0, col_k<C>(ks, 1, t))];
+          const float x1 = pb[xoff<C>(j0, col_k<C>(ks, 0, t))], x3 = pb[xoff<C>(j0, col_k<C>(ks, 1, t))];
+          const uint32_t h0 = __float_as_uint(x0), h1 = __float_as_uint(x1), h2 = __float_as_uint(x2),
+                         h3 = __float_as_uint(x3);
+          if (TERMS == 3) {
+            const uint32_t l0 = __float_as_uint(lo_of(x0)), l1 = __float_as_uint(lo_of(x1)),
+                           l2 = __float_as_uint(lo_of(x2)), l3 = __float_as_uint(lo_of(x3));
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(g0[nt], l0, l1, l2, l3, bgh[ks][nt][0], bgh[ks][nt][1]);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_tf32(g0[nt], h0, h1, h2, h3, bgl[ks][nt][0], bgl[ks][nt][1]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(g0[nt], h0, h1, h2, h3, bgh[ks][nt][0], bgh[ks][nt][1]);
+        }
+      }
+      RM_PHASE(2);
+      // the next group's operand is requested as soon as this group's last use is issued
+      if (group_ends && more) load_tr1_bwd<C, TERMS>(a.tab, next_grp, g, t, bgh, bgl);
+      RM_PHASE(3);
+
+      // ---- S1[k1][c] += A0^T[k1][pair] X[pair][c] ----
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const float* ce = c0s + ((i0r[2 * ks] < 0 ? a.c0_rows : i0r[2 * ks]) * 4 + t) * kCSB + g;
+        const float* co = c0s + ((i0r[2 * ks + 1] < 0 ? a.c0_rows : i0r[2 * ks + 1]) * 4 + t) * kCSB + g;
+        const float a0 = ce[0], a1 = ce[8], a2 = co[0], a3 = co[8];
+        const uint32_t ah0 = __float_as_uint(a0), ah1 = __float_as_uint(a1), ah2 = __float_as_uint(a2),
+                       ah3 = __float_as_uint(a3);
+        const uint32_t al0 = __float_as_uint(lo_of(a0)), al1 = __float_as_uint(lo_of(a1)),
+                       al2 = __float_as_uint(lo_of(a2)), al3 = __float_as_uint(lo_of(a3));
+        const float* pe = ring + ((slot_pos + 2 * ks) & (kRing - 1)) * RS;
+        const float* po = ring + ((slot_pos + 2 * ks + 1) & (kRing - 1)) * RS;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float b0 = pe[xoff<C>(t, col_n<C>(nt, g))], b1 = po[xoff<C>(t, col_n<C>(nt, g))];
+          if (TERMS == 3) {
+            mma_tf32(s1[nt], al0, al1, al2, al3, __float_as_uint(b0), __float_as_uint(b1));
+            mma_tf32(s1[nt], ah0, ah1, ah2, ah3, __float_as_uint(lo_of(b0)), __float_as_uint(lo_of(b1)));
+          }
+          mma_tf32(s1[nt], ah0, ah1, ah2, ah3, __float_as_uint(b0), __float_as_uint(b1));
+        }
+      }
+
+      RM_PHASE(4);
+      // ---- d_core0[i0][j0][k1] += G0 (unused rows add into the dummy row) ----
+      {
+        int i0a = rg ? i0r[1] : i0r[0], i0b = rg ? i0r[3] : i0r[2];
+        i0a = i0a < 0 ? a.c0_rows + warp : i0a;
+        i0b = i0b < 0 ? a.c0_rows + warp : i0b;
+        const int ra = i0a * 4 + j0, rb = i0b * 4 + j0;
+        float* da = d0s + ra * 16;
+        float* db = d0s + rb * 16;
+        const int swa = d0_swizzle(ra), swb = d0_swizzle(rb);
+        float* addr[8];
+        float val[8];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            addr[4 * nt + e] = da + ((2 * t + 8 * nt + e) ^ swa);
+            val[4 * nt + e] = g0[nt][e];
+            addr[4 * nt + 2 + e] = db + ((2 * t + 8 * nt + e) ^ swb);
+            val[4 * nt + 2 + e] = g0[nt][2 + e];
+          }
+        shared_add_batch<8>(addr, val);
+      }
+
+      // S1 leaves the accumulators when the group ends, and every kChain tiles inside a long group (the
+      // accumulation error of the tensor-core accumulator grows with the length of the chain); the warp owns
+      // the group, so a later part simply adds to what it stored before
+      RM_PHASE(5);
+      ++chain;
+      if (group_ends || chain == kChain) {
+        float* dst = a.S1 + (size_t)grp * (16 * C);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = col_n<C>(nt, 2 * t + e);
+            if ((C % 8 == 0) || c < C) {
+              float* d0 = dst + g * C + c;
+              float* d1 = dst + (g + 8) * C + c;
+              float v0 = s1[nt][e], v1 = s1[nt][2 + e];
+              if (stored) {
+                v0 += ld_dep_f32(d0);
+                v1 += ld_dep_f32(d1);
+              }
+              *d0 = v0;
+              *d1 = v1;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) s1[nt][e] = 0.f;
+        }
+        stored = !group_ends;
+        chain = 0;
+      }
+      __syncwarp();
+      pos += n;
+      RM_PHASE(6);
+    }
+    RM_PHASE_FLUSH;
+    cp_async_wait<0>();
+  }
+  RM_MARK(4);
+  __syncthreads();
+  float* part = a.d0parts + (size_t)blockIdx.x * a.c0_rows * 64;
+  for (int i = threadIdx.x; i < a.c0_rows * 64; i += kBT) part[i] = d0s[(i & ~15) + ((i & 15) ^ d0_swizzle(i >> 4))];
+  RM_MARK(5);
+}
+
+// ---------------------------------------------------------------------------------------------
+// d_core1, d_core2 from S1
+//   d_core1[i1][r = (k1, j1)][k2] = sum_{i2, j2} S1[(i1, i2)][r][j2] core2[i2][k2][j2]
+//   d_core2[i2][k2][j2]           = sum_{i1, r}  core1[i1][r][k2]    S1[(i1, i2)][r][j2]
+// One CTA per (table, i1); its warps take the i2 in turn, each S1[(i1, i2)] (16 C floats) arriving in the warp's
+// own double buffer.  The first product runs on the FP32 pipe (lane = rows r, accumulators for all k2, summed
+// over the warps at the end); the second on the tensor cores (M = k2, N = j2, K = r, core1[i1]^T as the A operand
+// in registers for the whole CTA) and leaves as this i1's copy of d_core2[i2], summed over i1 by the finalize
+// kernel in fixed order.
+// ---------------------------------------------------------------------------------------------
+constexpr int kCoresThreads = 256, kCoresWarps = kCoresThreads / 32;
+
+template <int Q1, int Q2>
+__global__ void __launch_bounds__(kCoresThreads, 1)
+rm_cores_kernel(TTDev tt, const float* S1, const int32_t* cnt, float* __restrict__ dcore1, float* __restrict__ parts2) {
+  constexpr int C = Q1 * Q2, NR = 16 * Q1, IMG = 16 * C, U = (NR + 31) / 32, KS = NR / 8, R2 = 16;
+  static_assert(NR % 8 == 0 && IMG % 4 == 0, "shape");
+  extern __shared__ __align__(16) float sm[];
+  const int p1 = tt.p[1], p2 = tt.p[2];
+  float* c2s = sm;                                         // [p2][Q2][16]   core2 of the table, k2 innermost
+  float* sbuf = c2s + (size_t)p2 * Q2 * R2;                // [warps][2][IMG]
+  float* red = sbuf + kCoresWarps * 2 * IMG;               // [warps][NR * 16]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int ti1 = blockIdx.x, table = ti1 / p1;
+  pdl_trigger();
+  {   // operands nobody in this call writes
+    const float* core2 = tt.core[2] + (size_t)table * p2 * (R2 * Q2);
+    for (int i = threadIdx.x; i < p2 * R2 * Q2; i += kCoresThreads) {
+      const int i2 = i / (R2 * Q2), e = i % (R2 * Q2), k2 = e / Q2, j2 = e % Q2;
+      c2s[((size_t)i2 * Q2 + j2) * R2 + k2] = __ldg(core2 + i);
+    }
+  }
+  // core1[i1]^T fragments: a0 (k2 = g, r = t + 8 ks), a1 (k2 = g + 8, r), a2 (g, r + 4), a3 (g + 8, r + 4)
+  uint32_t ah[KS][4], al[KS][4];
+  {
+    const float* c1 = tt.core[1] + (size_t)ti1 * (NR * R2);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float v0 = __ldg(c1 + (t + 8 * ks) * R2 + g), v1 = __ldg(c1 + (t + 8 * ks) * R2 + g + 8);
+      const float v2 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g), v3 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g + 8);
+      ah[ks][0] = __float_as_uint(v0);
+      ah[ks][1] = __float_as_uint(v1);
+      ah[ks][2] = __float_as_uint(v2);
+      ah[ks][3] = __float_as_uint(v3);
+      al[ks][0] = __float_as_uint(lo_of(v0));
+      al[ks][1] = __float_as_uint(lo_of(v1));
+      al[ks][2] = __float_as_uint(lo_of(v2));
+      al[ks][3] = __float_as_uint(lo_of(v3));
+    }
+  }
+  pdl_wait();
+  __syncthreads();
+  const size_t h0 = (size_t)ti1 * p2;
+  float* mybuf = sbuf + warp * 2 * IMG;
+  auto stage = [&](int i2, int b) {
+    if (i2 < p2 && ld_dep_s32(cnt + h0 + i2) > 0) {
+      const float* src = S1 + (h0 + i2) * IMG;
+      for (int i = lane; i < IMG / 4; i += 32) cp_async16(mybuf + b * IMG + 4 * i, src + 4 * i);
+    }
+    cp_async_commit();
+  };
+  float acc1[U][R2];
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+#pragma unroll
+    for (int k = 0; k < R2; ++k) acc1[u][k] = 0.f;
+  int b = 0;
+  stage(warp, 0);
+  for (int i2 = warp; i2 < p2; i2 += kCoresWarps, b ^= 1) {
+    stage(i2 + kCoresWarps, b ^ 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    float* out2 = parts2 + (h0 + i2) * (R2 * Q2);
+    if (ld_dep_s32(cnt + h0 + i2) > 0) {
+      const float* sb = mybuf + b * IMG;
+      // ---- d_core1 ----
+      float sv[U][Q2];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = min(lane + 32 * u, NR - 1);
+#pragma unroll
+        for (int j2 = 0; j2 < Q2; ++j2) sv[u][j2] = sb[r * Q2 + j2];
+      }
+      const float* c2 = c2s + (size_t)i2 * Q2 * R2;
+#pragma unroll
+      for (int j2 = 0; j2 < Q2; ++j2) {
+#pragma unroll
+        for (int k4 = 0; k4 < R2 / 4; ++k4) {
+          const float4 cv = *reinterpret_cast<const float4*>(c2 + j2 * R2 + 4 * k4);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            acc1[u][4 * k4 + 0] = fmaf(sv[u][j2], cv.x, acc1[u][4 * k4 + 0]);
+            acc1[u][4 * k4 + 1] = fmaf(sv[u][j2], cv.y, acc1[u][4 * k4 + 1]);
+            acc1[u][4 * k4 + 2] = fmaf(sv[u][j2], cv.z, acc1[u][4 * k4 + 2]);
+            acc1[u][4 * k4 + 3] = fmaf(sv[u][j2], cv.w, acc1[u][4 * k4 + 3]);
+          }
+        }
+      }
+      // ---- this i1's copy of d_core2[i2] ----
+      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const bool on = (Q2 == 8) || g < Q2;
+        const float b0 = on ? sb[(t + 8 * ks) * Q2 + g] : 0.f, b1 = on ? sb[(t + 4 + 8 * ks) * Q2 + g] : 0.f;
+        mma_tf32(acc2, al[ks][0], al[ks][1], al[ks][2], al[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+        mma_tf32(acc2, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(lo_of(b0)),
+                 __float_as_uint(lo_of(b1)));
+        mma_tf32(acc2, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+      }
+      // c0 (k2 = g, j2 = 2 t), c1 (g, 2 t + 1), c2 (g + 8, 2 t), c3 (g + 8, 2 t + 1)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (2 * t + e < Q2) {
+          out2[g * Q2 + 2 * t + e] = acc2[e];
+          out2[(g + 8) * Q2 + 2 * t + e] = acc2[2 + e];
+        }
+    } else {
+      for (int i = lane; i < R2 * Q2; i += 32) out2[i] = 0.f;
+    }
+    __syncwarp();
+  }
+  cp_async_wait<0>();
+  // d_core1[i1] = sum of the warps' accumulators
+  float* myred = red + (size_t)warp * (NR * R2);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int r = lane + 32 * u;
+    if (r < NR) {
+#pragma unroll
+      for (int k4 = 0; k4 < R2 / 4; ++k4)
+        *reinterpret_cast<float4*>(myred + r * R2 + 4 * k4) =
+            make_float4(acc1[u][4 * k4], acc1[u][4 * k4 + 1], acc1[u][4 * k4 + 2], acc1[u][4 * k4 + 3]);
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < NR * R2 / 4; o += kCoresThreads) {
+    float4 v = reinterpret_cast<const float4*>(red)[o];
+#pragma unroll
+    for (int w = 1; w < kCoresWarps; ++w) {
+      const float4 x = reinterpret_cast<const float4*>(red + (size_t)w * (NR * R2))[o];
+      v.x += x.x;
+      v.y += x.y;
+      v.z += x.z;
+      v.w += x.w;
+    }
+    reinterpret_cast<float4*>(dcore1 + (size_t)ti1 * (NR * R2))[o] = v;
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -323,21 +911,76 @@ int rm_fwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, 
   return TTG_OK;
 }
 
+template <int Q1, int Q2>
+size_t rm_bwd_smem(int c0_rows) {
+  constexpr int C = Q1 * Q2, D = 4 * C, RS = (C % 8 == 0) ? D + 4 : D;
+  return sizeof(float) * ((size_t)(c0_rows + 1) * 4 * kCSB + (size_t)(c0_rows + kBW) * 64 +
+                          (size_t)kBW * (kRing * RS + 8));
+}
+
+template <int Q1, int Q2, int TERMS>
+int rm_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, int* nparts,
+                  cudaStream_t stream) {
+  RmArgs a;
+  fill_args(tt, pl, &a);
+  a.d_output = d_output;
+  const size_t smem = rm_bwd_smem<Q1, Q2>(a.c0_rows);
+  auto kern = rm_bwd_kernel<Q1, Q2, TERMS>;
+  TTG_ENSURE_SMEM(kern, smem);
+  int64_t grid = kNumSMs;
+  if (grid * kBW * 8 > nnz) grid = ceil_div(nnz, kBW * 8);
+  *nparts = (int)grid;
+  a.nnz = (int32_t)nnz;
+  a.rpw = (int32_t)ceil_div(nnz, grid * kBW);
+  prof_begin(K_BWD_ROWS, stream);
+  TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kBT), smem, stream, a));
+  prof_end(K_BWD_ROWS, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
+template <int Q1, int Q2>
+size_t rm_cores_smem(int p2) {
+  return sizeof(float) * ((size_t)p2 * Q2 * 16 + (size_t)kCoresWarps * 2 * 16 * Q1 * Q2 + (size_t)kCoresWarps * 16 * Q1 * 16);
+}
+
+template <int Q1, int Q2>
+int rm_cores_launch(const TTDev& tt, const RPlan& pl, float* const* dcore, cudaStream_t stream) {
+  const size_t smem = rm_cores_smem<Q1, Q2>(tt.p[2]);
+  auto kern = rm_cores_kernel<Q1, Q2>;
+  TTG_ENSURE_SMEM(kern, smem);
+  prof_begin(K_BWD_CORES, stream);
+  TTG_CUDA(launch_pdl(kern, dim3((unsigned)(tt.num_tables * tt.p[1])), dim3(kCoresThreads), smem, stream, tt,
+                      (const float*)pl.S1, pl.cnt, dcore[1], pl.d2parts));
+  prof_end(K_BWD_CORES, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
 struct RmEntry {
   int q1, q2;
   int (*fwd[2])(const TTDev&, int64_t, const RPlan&, float*, cudaStream_t);
+  int (*bwd[2])(const TTDev&, int64_t, const RPlan&, const float*, int*, cudaStream_t);
+  size_t (*bwd_smem)(int);
+  int (*cores)(const TTDev&, const RPlan&, float* const*, cudaStream_t);
+  size_t (*cores_smem)(int);
 };
 
 const RmEntry kRmEntries[] = {
-    {5, 5, {rm_fwd_launch<5, 5, 3>, rm_fwd_launch<5, 5, 1>}},   // ogbn-products, D = 100
-    {4, 8, {rm_fwd_launch<4, 8, 3>, rm_fwd_launch<4, 8, 1>}},   // cora / ogbn-arxiv, D = 128
+    {5, 5, {rm_fwd_launch<5, 5, 3>, rm_fwd_launch<5, 5, 1>}, {rm_bwd_launch<5, 5, 3>, rm_bwd_launch<5, 5, 1>},
+     rm_bwd_smem<5, 5>, rm_cores_launch<5, 5>, rm_cores_smem<5, 5>},   // ogbn-products, D = 100
+    {4, 8, {rm_fwd_launch<4, 8, 3>, rm_fwd_launch<4, 8, 1>}, {rm_bwd_launch<4, 8, 3>, rm_bwd_launch<4, 8, 1>},
+     rm_bwd_smem<4, 8>, rm_cores_launch<4, 8>, rm_cores_smem<4, 8>},   // cora / ogbn-arxiv, D = 128
 };
 
 const RmEntry* find_rm(const TTDev& tt) {
   if (!r_supported(tt)) return nullptr;
   if ((int64_t)tt.num_tables * tt.p[0] * tt.p[1] * tt.p[2] >= ((int64_t)1 << 31)) return nullptr;
   for (const RmEntry& e : kRmEntries)
-    if (e.q1 == tt.q[1] && e.q2 == tt.q[2]) return &e;
+    if (e.q1 == tt.q[1] && e.q2 == tt.q[2]) {
+      if (e.bwd_smem(tt.num_tables * tt.p[0]) > 220 * 1024 || e.cores_smem(tt.p[2]) > 220 * 1024) return nullptr;
+      return &e;
+    }
   return nullptr;
 }
 
@@ -347,6 +990,34 @@ int rm_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, boo
   const RmEntry* e = find_rm(tt);
   if (!e) return TTG_ENOTSUP;
   return e->fwd[tf32 ? 1 : 0](tt, nnz, pl, output, stream);
+}
+
+#ifdef TTG_R_TIMING
+extern "C" void ttg_rm_marks(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_rm_marks, sizeof(g_rm_marks)); }
+extern "C" void ttg_rm_phases(unsigned long long* out, int reset) {
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_rm_phase, z, sizeof(z));
+  } else {
+    cudaMemcpyFromSymbol(out, g_rm_phase, sizeof(g_rm_phase));
+  }
+}
+#endif
+
+bool rm_supported(const TTDev& tt) { return find_rm(tt) != nullptr; }
+
+int rm_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
+                int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream) {
+  const RmEntry* e = find_rm(tt);
+  if (!e) return TTG_ENOTSUP;
+  int nparts = 0;
+  int rc = e->bwd[tf32 ? 1 : 0](tt, nnz, pl, d_output, &nparts, stream);
+  if (rc != TTG_OK) return rc;
+  rc = e->cores(tt, pl, dcore, stream);
+  if (rc != TTG_OK) return rc;
+  // d_core0 = sum of the CTAs' copies, d_core2 = sum of the copies per i1 (both in fixed order), then the
+  // optimizer on all three cores
+  return mma_finalize_parts(tt, pl.d0parts, nparts, pl.d2parts, tt.p[1], dcore, optim, lr, eps, state, stream);
 }
 
 }  // namespace ttg

@@ -95,6 +95,7 @@ struct SortedWs {
   float* tabR;         // [tables * p1 * p2][2][r1 q1 q2]  tr1 operand images (tcgen05 kernels)
   float* S1R;          // [tables * p1 * p2][r1][q1 q2]    d(tr1)          (tcgen05 kernels)
   float* d0partsR;     // [kNumSMs][core0 elements]                (tcgen05 kernels)
+  float* d2partsR;     // [tables][p1][p2][core2 row]              (right-grouped mma.sync kernels)
   int32_t* cnt;        // [cnt_elems] rows per group (+1: invalid keys), padded to scan tiles
   int32_t* rowcount;   // [tables * B] valid indices per output row; directly behind cnt
   int32_t* fill_flag;  // one word (inside cnt's padding): some output row has 0 or >= 2 indices
@@ -146,6 +147,7 @@ SortedWs carve(const TTDev& tt, int64_t B, int64_t nnz, char* base, int slot = 0
   w.tabR = rpath ? (float*)take(sizeof(float) * r_table_floats(tt)) : nullptr;
   w.S1R = rpath ? (float*)take(sizeof(float) * r_table_floats(tt) / 2) : nullptr;
   w.d0partsR = rpath ? (float*)take(sizeof(float) * (size_t)kNumSMs * e0) : nullptr;
+  w.d2partsR = rpath ? (float*)take(sizeof(float) * (size_t)tt.num_tables * tt.p[1] * tt.p[2] * tt.cols[2]) : nullptr;
   // counters (padded to whole 4096-counter scan tiles) and the per-row counts share one memset
   const size_t cnt_elems = align_up((rpath && groups_r > groups ? groups_r : groups) + 2, 4096);   // + invalid bucket + fill flag
   w.cnt_bytes = sizeof(int32_t) * cnt_elems;
@@ -1587,6 +1589,7 @@ RPlan r_plan(const SortedWs& w) {
   pl.tab = w.tabR;
   pl.S1 = w.S1R;
   pl.d0parts = w.d0partsR;
+  pl.d2parts = w.d2partsR;
   return pl;
 }
 
@@ -1766,6 +1769,9 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
       rc = r_table(tt, r_plan(w), stream);
       if (rc != TTG_OK) return rc;
     }
+    if (!(flags & TTG_FLAG_TCGEN05) && rm_supported(tt))
+      return rm_backward(tt, nnz, r_plan(w), d_output, dcore, optim, lr, eps, state, (flags & TTG_FLAG_TF32) != 0,
+                         stream);
     return r_backward(tt, nnz, r_plan(w), d_output, dcore, optim, lr, eps, state, (flags & TTG_FLAG_TF32) != 0,
                       stream);
   }

@@ -1340,10 +1340,20 @@ size_t r_bwd_smem(int c0_rows) {
          sizeof(float) * (size_t)c0_rows * 64 + sizeof(int32_t) * ((c0_rows + 3) & ~3) + sizeof(RBSmem) + 64;
 }
 
+template <int Q1, int Q2>
+int r_cores_launch(const TTDev& tt, const RPlan& pl, float* const* dcore, cudaStream_t stream) {
+  const int nb = tt.num_tables * (tt.p[1] + tt.p[2]);
+  prof_begin(K_BWD_CORES, stream);
+  TTG_CUDA(launch_pdl(r_cores_kernel<Q1, Q2, 16>, dim3(nb), dim3(256), 0, stream, tt, (const float*)pl.S1, pl.cnt,
+                      dcore[1], dcore[2]));
+  prof_end(K_BWD_CORES, stream);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
 template <int Q1, int Q2, int TERMS>
 int r_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
                  int* nparts, cudaStream_t stream) {
-  constexpr int R2 = 16;
   RBwdArgs a;
   a.skeys = pl.skeys;
   a.srow = pl.srow;
@@ -1367,13 +1377,7 @@ int r_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_o
   TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kThreadsRB), smem, stream, a));
   prof_end(K_BWD_ROWS, stream);
   TTG_LAUNCH_CHECK();
-  const int nb = tt.num_tables * (tt.p[1] + tt.p[2]);
-  prof_begin(K_BWD_CORES, stream);
-  TTG_CUDA(launch_pdl(r_cores_kernel<Q1, Q2, R2>, dim3(nb), dim3(256), 0, stream, tt, (const float*)pl.S1, pl.cnt,
-                      dcore[1], dcore[2]));
-  prof_end(K_BWD_CORES, stream);
-  TTG_LAUNCH_CHECK();
-  return TTG_OK;
+  return r_cores_launch<Q1, Q2>(tt, pl, dcore, stream);
 }
 
 struct REntry {
@@ -1441,7 +1445,14 @@ int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_out
   int rc = e->bwd[tf32 ? 1 : 0](tt, nnz, pl, d_output, dcore, &nparts, stream);
   if (rc != TTG_OK) return rc;
   // d_core0 = sum of the CTAs' copies (fixed order), then the optimizer on all three cores
-  return mma_finalize_parts(tt, pl.d0parts, nparts, dcore, optim, lr, eps, state, stream);
+  return mma_finalize_parts(tt, pl.d0parts, nparts, nullptr, 0, dcore, optim, lr, eps, state, stream);
+}
+
+int r_cores(const TTDev& tt, const RPlan& pl, float* const* dcore, cudaStream_t stream) {
+  if (!find_r(tt)) return TTG_ENOTSUP;
+  if (tt.q[1] == 5 && tt.q[2] == 5) return r_cores_launch<5, 5>(tt, pl, dcore, stream);
+  if (tt.q[1] == 4 && tt.q[2] == 8) return r_cores_launch<4, 8>(tt, pl, dcore, stream);
+  return TTG_ENOTSUP;
 }
 
 int r_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream) {
