@@ -246,7 +246,8 @@ struct RPlan {
 };
 bool r_supported(const TTDev& tt);
 size_t r_table_floats(const TTDev& tt);
-int r_table(const TTDev& tt, const RPlan& pl, cudaStream_t stream);
+// planes: 2 = operand image and its TF32 remainder (tcgen05 kernels), 1 = the image only (mma.sync kernels)
+int r_table(const TTDev& tt, const RPlan& pl, int planes, cudaStream_t stream);
 int r_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, bool tf32, cudaStream_t stream);
 int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
                int32_t optim, float lr, float eps, float* const* state, bool tf32, cudaStream_t stream);

@@ -122,8 +122,15 @@ __device__ __forceinline__ void load_tr1_fwd(const float* tab, int group, int g,
         const int off = (2 * ks + h) * (4 * C) + c * 4 + t;
         const bool on = (C % 8 == 0) || c < C;
         bh[ks][nt][h] = on ? __float_as_uint(ld_dep_f32(img + off)) : 0u;
-        if (TERMS == 3) bl[ks][nt][h] = on ? __float_as_uint(ld_dep_f32(img + 16 * C + off)) : 0u;
       }
+  if (TERMS == 3) {     // the remainders are split off here: the table's second plane is not read (nor written)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) bl[ks][nt][h] = __float_as_uint(lo_of(__uint_as_float(bh[ks][nt][h])));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -720,7 +727,9 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
 // in registers for the whole CTA) and leaves as this i1's copy of d_core2[i2], summed over i1 by the finalize
 // kernel in fixed order.
 // ---------------------------------------------------------------------------------------------
-constexpr int kCoresThreads = 256, kCoresWarps = kCoresThreads / 32;
+constexpr int kCoresThreads = 512, kCoresWarps = kCoresThreads / 32;
+constexpr int kCoresA = 10, kCoresB = kCoresWarps - kCoresA;   // warps on d_core1 / on d_core2 (about equal time)
+constexpr int kCoresBufs = 4;   // S1 groups a warp keeps in flight / in use
 
 template <int Q1, int Q2>
 __global__ void __launch_bounds__(kCoresThreads, 1)
@@ -730,125 +739,150 @@ rm_cores_kernel(TTDev tt, const float* S1, const int32_t* cnt, float* __restrict
   extern __shared__ __align__(16) float sm[];
   const int p1 = tt.p[1], p2 = tt.p[2];
   float* c2s = sm;                                         // [p2][Q2][16]   core2 of the table, k2 innermost
-  float* sbuf = c2s + (size_t)p2 * Q2 * R2;                // [warps][2][IMG]
-  float* red = sbuf + kCoresWarps * 2 * IMG;               // [warps][NR * 16]
+  float* sbuf = c2s + (size_t)p2 * Q2 * R2;                // [warps][kCoresBufs][IMG]
+  float* red = sbuf + kCoresWarps * kCoresBufs * IMG;      // [kCoresA][NR * 16]
+  __shared__ int32_t cnts[512];                            // rows of the CTA's groups (p2 <= 512, find_r)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int ti1 = blockIdx.x, table = ti1 / p1;
+  const bool second = warp >= kCoresA;                     // warps 0..9: d_core1 (FP32 pipe), 10..15: d_core2 (tensor)
+  const int w8 = second ? warp - kCoresA : warp;
+  const int nws = second ? kCoresB : kCoresA;              // warps that share this warp's role
   pdl_trigger();
   {   // operands nobody in this call writes
     const float* core2 = tt.core[2] + (size_t)table * p2 * (R2 * Q2);
-    for (int i = threadIdx.x; i < p2 * R2 * Q2; i += kCoresThreads) {
-      const int i2 = i / (R2 * Q2), e = i % (R2 * Q2), k2 = e / Q2, j2 = e % Q2;
-      c2s[((size_t)i2 * Q2 + j2) * R2 + k2] = __ldg(core2 + i);
-    }
+    constexpr int PER = kCoresThreads / (R2 * Q2);         // core2 rows per pass; a thread keeps its (k2, j2)
+    const int e = threadIdx.x % (R2 * Q2), k2 = e / Q2, j2 = e % Q2;
+    if (threadIdx.x < PER * R2 * Q2)
+      for (int i2 = threadIdx.x / (R2 * Q2); i2 < p2; i2 += PER)
+        c2s[((size_t)i2 * Q2 + j2) * R2 + k2] = __ldg(core2 + (size_t)i2 * (R2 * Q2) + e);
   }
-  // core1[i1]^T fragments: a0 (k2 = g, r = t + 8 ks), a1 (k2 = g + 8, r), a2 (g, r + 4), a3 (g + 8, r + 4)
-  uint32_t ah[KS][4], al[KS][4];
-  {
-    const float* c1 = tt.core[1] + (size_t)ti1 * (NR * R2);
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      const float v0 = __ldg(c1 + (t + 8 * ks) * R2 + g), v1 = __ldg(c1 + (t + 8 * ks) * R2 + g + 8);
-      const float v2 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g), v3 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g + 8);
-      ah[ks][0] = __float_as_uint(v0);
-      ah[ks][1] = __float_as_uint(v1);
-      ah[ks][2] = __float_as_uint(v2);
-      ah[ks][3] = __float_as_uint(v3);
-      al[ks][0] = __float_as_uint(lo_of(v0));
-      al[ks][1] = __float_as_uint(lo_of(v1));
-      al[ks][2] = __float_as_uint(lo_of(v2));
-      al[ks][3] = __float_as_uint(lo_of(v3));
-    }
-  }
-  pdl_wait();
-  __syncthreads();
   const size_t h0 = (size_t)ti1 * p2;
-  float* mybuf = sbuf + warp * 2 * IMG;
+  float* mybuf = sbuf + warp * kCoresBufs * IMG;
   auto stage = [&](int i2, int b) {
-    if (i2 < p2 && ld_dep_s32(cnt + h0 + i2) > 0) {
+    if (i2 < p2 && cnts[i2] > 0) {
       const float* src = S1 + (h0 + i2) * IMG;
       for (int i = lane; i < IMG / 4; i += 32) cp_async16(mybuf + b * IMG + 4 * i, src + 4 * i);
     }
     cp_async_commit();
   };
-  float acc1[U][R2];
+  if (!second) {
+    pdl_wait();
+    for (int i = threadIdx.x; i < p2; i += kCoresThreads) cnts[i] = ld_dep_s32(cnt + h0 + i);
+    __syncthreads();
+    float acc1[U][R2];
 #pragma unroll
-  for (int u = 0; u < U; ++u)
+    for (int u = 0; u < U; ++u)
 #pragma unroll
-    for (int k = 0; k < R2; ++k) acc1[u][k] = 0.f;
-  int b = 0;
-  stage(warp, 0);
-  for (int i2 = warp; i2 < p2; i2 += kCoresWarps, b ^= 1) {
-    stage(i2 + kCoresWarps, b ^ 1);
-    cp_async_wait<1>();
-    __syncwarp();
-    float* out2 = parts2 + (h0 + i2) * (R2 * Q2);
-    if (ld_dep_s32(cnt + h0 + i2) > 0) {
-      const float* sb = mybuf + b * IMG;
-      // ---- d_core1 ----
-      float sv[U][Q2];
+      for (int k = 0; k < R2; ++k) acc1[u][k] = 0.f;
+    int b = 0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = min(lane + 32 * u, NR - 1);
+    for (int k = 0; k < kCoresBufs - 1; ++k) stage(w8 + k * nws, k);
+    for (int i2 = w8; i2 < p2; i2 += nws, b = (b + 1) % kCoresBufs) {
+      stage(i2 + (kCoresBufs - 1) * nws, (b + kCoresBufs - 1) % kCoresBufs);
+      cp_async_wait<kCoresBufs - 1>();
+      __syncwarp();
+      if (cnts[i2] > 0) {
+        const float* sb = mybuf + b * IMG;
+        float sv[U][Q2];
 #pragma unroll
-        for (int j2 = 0; j2 < Q2; ++j2) sv[u][j2] = sb[r * Q2 + j2];
-      }
-      const float* c2 = c2s + (size_t)i2 * Q2 * R2;
+        for (int u = 0; u < U; ++u) {
+          const int r = min(lane + 32 * u, NR - 1);
 #pragma unroll
-      for (int j2 = 0; j2 < Q2; ++j2) {
+          for (int j2 = 0; j2 < Q2; ++j2) sv[u][j2] = sb[r * Q2 + j2];
+        }
+        const float* c2 = c2s + (size_t)i2 * Q2 * R2;
 #pragma unroll
-        for (int k4 = 0; k4 < R2 / 4; ++k4) {
-          const float4 cv = *reinterpret_cast<const float4*>(c2 + j2 * R2 + 4 * k4);
+        for (int j2 = 0; j2 < Q2; ++j2) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            acc1[u][4 * k4 + 0] = fmaf(sv[u][j2], cv.x, acc1[u][4 * k4 + 0]);
-            acc1[u][4 * k4 + 1] = fmaf(sv[u][j2], cv.y, acc1[u][4 * k4 + 1]);
-            acc1[u][4 * k4 + 2] = fmaf(sv[u][j2], cv.z, acc1[u][4 * k4 + 2]);
-            acc1[u][4 * k4 + 3] = fmaf(sv[u][j2], cv.w, acc1[u][4 * k4 + 3]);
+          for (int k4 = 0; k4 < R2 / 4; ++k4) {
+            const float4 cv = *reinterpret_cast<const float4*>(c2 + j2 * R2 + 4 * k4);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              acc1[u][4 * k4 + 0] = fmaf(sv[u][j2], cv.x, acc1[u][4 * k4 + 0]);
+              acc1[u][4 * k4 + 1] = fmaf(sv[u][j2], cv.y, acc1[u][4 * k4 + 1]);
+              acc1[u][4 * k4 + 2] = fmaf(sv[u][j2], cv.z, acc1[u][4 * k4 + 2]);
+              acc1[u][4 * k4 + 3] = fmaf(sv[u][j2], cv.w, acc1[u][4 * k4 + 3]);
+            }
           }
         }
       }
-      // ---- this i1's copy of d_core2[i2] ----
-      float acc2[4] = {0.f, 0.f, 0.f, 0.f};
+      __syncwarp();
+    }
+    cp_async_wait<0>();
+    // d_core1[i1] = sum of these warps' accumulators
+    float* myred = red + (size_t)w8 * (NR * R2);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = lane + 32 * u;
+      if (r < NR) {
+#pragma unroll
+        for (int k4 = 0; k4 < R2 / 4; ++k4)
+          *reinterpret_cast<float4*>(myred + r * R2 + 4 * k4) =
+              make_float4(acc1[u][4 * k4], acc1[u][4 * k4 + 1], acc1[u][4 * k4 + 2], acc1[u][4 * k4 + 3]);
+      }
+    }
+  } else {
+    // core1[i1]^T fragments: a0 (k2 = g, r = t + 8 ks), a1 (k2 = g + 8, r), a2 (g, r + 4), a3 (g + 8, r + 4)
+    uint32_t ah[KS][4], al[KS][4];
+    {
+      const float* c1 = tt.core[1] + (size_t)ti1 * (NR * R2);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const bool on = (Q2 == 8) || g < Q2;
-        const float b0 = on ? sb[(t + 8 * ks) * Q2 + g] : 0.f, b1 = on ? sb[(t + 4 + 8 * ks) * Q2 + g] : 0.f;
-        mma_tf32(acc2, al[ks][0], al[ks][1], al[ks][2], al[ks][3], __float_as_uint(b0), __float_as_uint(b1));
-        mma_tf32(acc2, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(lo_of(b0)),
-                 __float_as_uint(lo_of(b1)));
-        mma_tf32(acc2, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+        const float v0 = __ldg(c1 + (t + 8 * ks) * R2 + g), v1 = __ldg(c1 + (t + 8 * ks) * R2 + g + 8);
+        const float v2 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g), v3 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g + 8);
+        ah[ks][0] = __float_as_uint(v0);
+        ah[ks][1] = __float_as_uint(v1);
+        ah[ks][2] = __float_as_uint(v2);
+        ah[ks][3] = __float_as_uint(v3);
+        al[ks][0] = __float_as_uint(lo_of(v0));
+        al[ks][1] = __float_as_uint(lo_of(v1));
+        al[ks][2] = __float_as_uint(lo_of(v2));
+        al[ks][3] = __float_as_uint(lo_of(v3));
       }
-      // c0 (k2 = g, j2 = 2 t), c1 (g, 2 t + 1), c2 (g + 8, 2 t), c3 (g + 8, 2 t + 1)
+    }
+    pdl_wait();
+    for (int i = threadIdx.x; i < p2; i += kCoresThreads) cnts[i] = ld_dep_s32(cnt + h0 + i);
+    __syncthreads();
+    int b = 0;
 #pragma unroll
-      for (int e = 0; e < 2; ++e)
-        if (2 * t + e < Q2) {
-          out2[g * Q2 + 2 * t + e] = acc2[e];
-          out2[(g + 8) * Q2 + 2 * t + e] = acc2[2 + e];
+    for (int k = 0; k < kCoresBufs - 1; ++k) stage(w8 + k * nws, k);
+    for (int i2 = w8; i2 < p2; i2 += nws, b = (b + 1) % kCoresBufs) {
+      stage(i2 + (kCoresBufs - 1) * nws, (b + kCoresBufs - 1) % kCoresBufs);
+      cp_async_wait<kCoresBufs - 1>();
+      __syncwarp();
+      float* out2 = parts2 + (h0 + i2) * (R2 * Q2);
+      if (cnts[i2] > 0) {
+        const float* sb = mybuf + b * IMG;
+        // three independent chains, one per term of the split
+        float a_lh[4] = {0.f, 0.f, 0.f, 0.f}, a_hl[4] = {0.f, 0.f, 0.f, 0.f}, a_hh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          const bool on = (Q2 == 8) || g < Q2;
+          const float b0 = on ? sb[(t + 8 * ks) * Q2 + g] : 0.f, b1 = on ? sb[(t + 4 + 8 * ks) * Q2 + g] : 0.f;
+          mma_tf32(a_lh, al[ks][0], al[ks][1], al[ks][2], al[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+          mma_tf32(a_hl, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(lo_of(b0)),
+                   __float_as_uint(lo_of(b1)));
+          mma_tf32(a_hh, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(b0), __float_as_uint(b1));
         }
-    } else {
-      for (int i = lane; i < R2 * Q2; i += 32) out2[i] = 0.f;
-    }
-    __syncwarp();
-  }
-  cp_async_wait<0>();
-  // d_core1[i1] = sum of the warps' accumulators
-  float* myred = red + (size_t)warp * (NR * R2);
+        // c0 (k2 = g, j2 = 2 t), c1 (g, 2 t + 1), c2 (g + 8, 2 t), c3 (g + 8, 2 t + 1)
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int r = lane + 32 * u;
-    if (r < NR) {
-#pragma unroll
-      for (int k4 = 0; k4 < R2 / 4; ++k4)
-        *reinterpret_cast<float4*>(myred + r * R2 + 4 * k4) =
-            make_float4(acc1[u][4 * k4], acc1[u][4 * k4 + 1], acc1[u][4 * k4 + 2], acc1[u][4 * k4 + 3]);
+        for (int e = 0; e < 2; ++e)
+          if (2 * t + e < Q2) {
+            out2[g * Q2 + 2 * t + e] = (a_lh[e] + a_hl[e]) + a_hh[e];
+            out2[(g + 8) * Q2 + 2 * t + e] = (a_lh[2 + e] + a_hl[2 + e]) + a_hh[2 + e];
+          }
+      } else {
+        for (int i = lane; i < R2 * Q2; i += 32) out2[i] = 0.f;
+      }
+      __syncwarp();
     }
+    cp_async_wait<0>();
   }
   __syncthreads();
   for (int o = threadIdx.x; o < NR * R2 / 4; o += kCoresThreads) {
     float4 v = reinterpret_cast<const float4*>(red)[o];
 #pragma unroll
-    for (int w = 1; w < kCoresWarps; ++w) {
+    for (int w = 1; w < kCoresA; ++w) {
       const float4 x = reinterpret_cast<const float4*>(red + (size_t)w * (NR * R2))[o];
       v.x += x.x;
       v.y += x.y;
@@ -941,7 +975,7 @@ int rm_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_
 
 template <int Q1, int Q2>
 size_t rm_cores_smem(int p2) {
-  return sizeof(float) * ((size_t)p2 * Q2 * 16 + (size_t)kCoresWarps * 2 * 16 * Q1 * Q2 + (size_t)kCoresWarps * 16 * Q1 * 16);
+  return sizeof(float) * ((size_t)p2 * Q2 * 16 + (size_t)kCoresWarps * kCoresBufs * 16 * Q1 * Q2 + (size_t)kCoresA * 16 * Q1 * 16);
 }
 
 template <int Q1, int Q2>

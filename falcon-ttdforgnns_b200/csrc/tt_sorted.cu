@@ -1575,9 +1575,17 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
 
 // tcgen05 kernels (right-grouped): opt-in (TTG_FLAG_TCGEN05), when the shape has them and the batch is dense
 // in groups
-bool use_r(const TTDev& tt, const SortedWs& w, int32_t flags) {
-  return w.tabR != nullptr && (flags & (TTG_FLAG_TCGEN05 | TTG_FLAG_RIGHT)) &&
-         !(flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC));
+// Which right-grouped kernels run this call: 0 none (left-grouped path), 1 the mma.sync ones (tt_rmma.cu), 2 the
+// tcgen05 ones (tt_tc5.cu, on request only).  Without a request the mma.sync ones take over from
+// kRightAutoRows rows per call on: their row kernels cost less per row and more per call (tr1 table, cores kernel;
+// profiles/r2c_right_mma.md).
+constexpr int64_t kRightAutoRows = 393216;
+int use_r(const TTDev& tt, const SortedWs& w, int32_t flags, int64_t nnz) {
+  if (w.tabR == nullptr || (flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC | TTG_FLAG_FORCE_GENERIC))) return 0;
+  if (flags & TTG_FLAG_TCGEN05) return 2;
+  if (!rm_supported(tt)) return 0;
+  if (flags & TTG_FLAG_RIGHT) return 1;
+  return (!(flags & TTG_FLAG_DETERMINISTIC) && nnz >= kRightAutoRows) ? 1 : 0;
 }
 
 RPlan r_plan(const SortedWs& w) {
@@ -1641,16 +1649,15 @@ int sorted_forward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indic
   // PLAN_VALID: plan AND group table of this batch are in the workspace; PLAN_READY: only the plan (ttg_tt_plan)
   const bool table_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
   const bool zero_only = table_valid || (flags & TTG_FLAG_PLAN_READY) != 0;
-  if (use_r(tt, w, flags)) {
+  if (const int eng = use_r(tt, w, flags, nnz)) {
     rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, output,
                     zero_only, stream, true);
     if (rc != TTG_OK) return rc;
     if (!table_valid) {   // otherwise the table of this batch is still in the workspace
-      rc = r_table(tt, r_plan(w), stream);
+      rc = r_table(tt, r_plan(w), eng, stream);
       if (rc != TTG_OK) return rc;
     }
-    if (flags & TTG_FLAG_TCGEN05)
-      return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
+    if (eng == 2) return r_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
     return rm_forward(tt, nnz, r_plan(w), output, (flags & TTG_FLAG_TF32) != 0, stream);
   }
   if (use_mma_fwd(tt, w, flags)) {
@@ -1719,7 +1726,7 @@ int sorted_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
     return TTG_ENOMEM;
   }
   return build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, nullptr, false,
-                    stream, use_r(tt, w, flags), true);
+                    stream, use_r(tt, w, flags, nnz) != 0, true);
 }
 
 int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
@@ -1761,15 +1768,15 @@ int sorted_backward(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
   }
   bool plan_valid = (flags & TTG_FLAG_PLAN_VALID) != 0;
   const uint32_t total_rows = (uint32_t)((uint64_t)tt.num_tables * (uint64_t)tt.num_rows);
-  if (use_r(tt, w, flags)) {
+  if (const int eng = use_r(tt, w, flags, nnz)) {
     if (!plan_valid) {   // otherwise the forward that built the plan also built the table
       rc = build_plan(tt, B, nnz, indices, rowidx, tableidx, w, (flags & TTG_FLAG_DETERMINISTIC) != 0, nullptr,
                       false, stream, true);
       if (rc != TTG_OK) return rc;
-      rc = r_table(tt, r_plan(w), stream);
+      rc = r_table(tt, r_plan(w), eng, stream);
       if (rc != TTG_OK) return rc;
     }
-    if (!(flags & TTG_FLAG_TCGEN05) && rm_supported(tt))
+    if (eng == 1)
       return rm_backward(tt, nnz, r_plan(w), d_output, dcore, optim, lr, eps, state, (flags & TTG_FLAG_TF32) != 0,
                          stream);
     return r_backward(tt, nnz, r_plan(w), d_output, dcore, optim, lr, eps, state, (flags & TTG_FLAG_TF32) != 0,

@@ -159,7 +159,7 @@ __device__ int build_tiles(const int32_t* base, int& g, int& off, int g_hi, Tile
 // CTA = (table, i1) x a slice of i2; thread = one float4 of the image.
 // ---------------------------------------------------------------------------------------------
 template <int Q1, int Q2, int R2>
-__global__ void __launch_bounds__(128) r_table_kernel(TTDev tt, float* __restrict__ tab, int i2_per_cta) {
+__global__ void __launch_bounds__(128) r_table_kernel(TTDev tt, float* __restrict__ tab, int i2_per_cta, int planes) {
   using S = RShape<Q1, Q2>;
   constexpr int C = S::C, R1 = S::R1, NF4 = S::kImg / 4;
   extern __shared__ __align__(16) float c2s[];          // [i2_per_cta][R2 * Q2]
@@ -203,8 +203,9 @@ __global__ void __launch_bounds__(128) r_table_kernel(TTDev tt, float* __restric
     }
     float* dst = tab + (h0 + i) * (2 * S::kImg) + 4 * f;
     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(dst + S::kImg) =
-        make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
+    if (planes == 2)      // the mma.sync kernels split in registers and never read the second plane
+      *reinterpret_cast<float4*>(dst + S::kImg) =
+          make_float4(tf32_lo(v[0]), tf32_lo(v[1]), tf32_lo(v[2]), tf32_lo(v[3]));
   }
 }
 
@@ -1287,7 +1288,7 @@ size_t r_fwd_smem(int c0_rows) {
 }
 
 template <int Q1, int Q2>
-int r_table_launch(const TTDev& tt, const RPlan& pl, cudaStream_t stream) {
+int r_table_launch(const TTDev& tt, const RPlan& pl, int planes, cudaStream_t stream) {
   constexpr int R2 = 16;
   const int nb = tt.num_tables * tt.p[1];
   int split = (int)ceil_div(4 * kNumSMs, nb);
@@ -1300,7 +1301,7 @@ int r_table_launch(const TTDev& tt, const RPlan& pl, cudaStream_t stream) {
   auto kern = r_table_kernel<Q1, Q2, R2>;
   TTG_ENSURE_SMEM(kern, sizeof(float) * 128 * R2 * Q2);
   prof_begin(K_TABLE, stream);
-  TTG_CUDA(launch_pdl<2>(kern, dim3(nb, split), dim3(128), smem, stream, tt, pl.tab, per));
+  TTG_CUDA(launch_pdl<2>(kern, dim3(nb, split), dim3(128), smem, stream, tt, pl.tab, per, planes));
   prof_end(K_TABLE, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -1382,7 +1383,7 @@ int r_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_o
 
 struct REntry {
   int q1, q2;
-  int (*table)(const TTDev&, const RPlan&, cudaStream_t);
+  int (*table)(const TTDev&, const RPlan&, int, cudaStream_t);
   int (*fwd[2])(const TTDev&, int64_t, const RPlan&, float*, cudaStream_t);
   int (*bwd[2])(const TTDev&, int64_t, const RPlan&, const float*, float* const*, int*, cudaStream_t);
   size_t (*fwd_smem)(int);
@@ -1431,10 +1432,10 @@ size_t r_table_floats(const TTDev& tt) {
   return (size_t)tt.num_tables * tt.p[1] * tt.p[2] * 2 * 16 * (tt.q[1] * tt.q[2]);
 }
 
-int r_table(const TTDev& tt, const RPlan& pl, cudaStream_t stream) {
+int r_table(const TTDev& tt, const RPlan& pl, int planes, cudaStream_t stream) {
   const REntry* e = find_r(tt);
   if (!e) return TTG_ENOTSUP;
-  return e->table(tt, pl, stream);
+  return e->table(tt, pl, planes, stream);
 }
 
 int r_backward(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_output, float* const* dcore,
