@@ -721,176 +721,181 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
 // d_core1, d_core2 from S1
 //   d_core1[i1][r = (k1, j1)][k2] = sum_{i2, j2} S1[(i1, i2)][r][j2] core2[i2][k2][j2]
 //   d_core2[i2][k2][j2]           = sum_{i1, r}  core1[i1][r][k2]    S1[(i1, i2)][r][j2]
-// One CTA per (table, i1); its warps take the i2 in turn, each S1[(i1, i2)] (16 C floats) arriving in the warp's
-// own double buffer.  The first product runs on the FP32 pipe (lane = rows r, accumulators for all k2, summed
-// over the warps at the end); the second on the tensor cores (M = k2, N = j2, K = r, core1[i1]^T as the A operand
-// in registers for the whole CTA) and leaves as this i1's copy of d_core2[i2], summed over i1 by the finalize
-// kernel in fixed order.
+// One CTA per (table, i1).  Its S1 groups (consecutive i2, contiguous in memory) arrive eight at a time in a
+// three-deep cp.async ring shared by the CTA; over such a block both products are plain GEMMs on the flattened
+// index (i2, j2) -- no padding of q2 = 5 to 8:
+//   d_core1[i1]: M = r (NR / 16 tiles), N = k2 (2 tiles), K = (i2, j2) of the block; one warp per (m, n) tile,
+//                accumulating over all blocks in four registers and storing once
+//   d_core2    : M = k2, N = (i2, j2) of the block (one warp per 8 columns), K = r with core1[i1]^T as the A operand
+//                in registers for the whole CTA; the block's columns leave as this i1's copy of d_core2, summed
+//                over i1 by the finalize kernel in fixed order.
+// TF32 products with the 3-term split (remainders computed in registers).
 // ---------------------------------------------------------------------------------------------
 constexpr int kCoresThreads = 512, kCoresWarps = kCoresThreads / 32;
-constexpr int kCoresA = 10, kCoresB = kCoresWarps - kCoresA;   // warps on d_core1 / on d_core2 (about equal time)
-constexpr int kCoresBufs = 4;   // S1 groups a warp keeps in flight / in use
+constexpr int kCoresGB = 8;      // groups per block
+constexpr int kCoresBufs = 3;
+constexpr int kC2S = 24;         // floats per (i2, j2) row of the shared core2 copy: lanes (t, g) -> banks 24 t + g
+
+#ifdef TTG_R_TIMING
+__device__ unsigned long long g_rc_marks[1024 * 6];
+#define RC_MARK(i) \
+  if (threadIdx.x == 0 && blockIdx.x < 1024) g_rc_marks[blockIdx.x * 6 + (i)] = gtime()
+#else
+#define RC_MARK(i)
+#endif
 
 template <int Q1, int Q2>
 __global__ void __launch_bounds__(kCoresThreads, 1)
-rm_cores_kernel(TTDev tt, const float* S1, const int32_t* cnt, float* __restrict__ dcore1, float* __restrict__ parts2) {
-  constexpr int C = Q1 * Q2, NR = 16 * Q1, IMG = 16 * C, U = (NR + 31) / 32, KS = NR / 8, R2 = 16;
-  static_assert(NR % 8 == 0 && IMG % 4 == 0, "shape");
+rm_cores_kernel(TTDev tt, const float* S1, const int32_t* cnt, float* __restrict__ dcore1, float* __restrict__ parts2,
+                int dbg) {
+  constexpr int C = Q1 * Q2, NR = 16 * Q1, IMG = 16 * C, R2 = 16, GB = kCoresGB;
+  constexpr int KB = GB * Q2;            // flattened (i2, j2) indices per block
+  constexpr int KSA = KB / 8;            // k-steps of the d_core1 product per block
+  constexpr int MT = NR / 16;            // m-tiles of d_core1
+  constexpr int NTB = KB / 8;            // n-tiles of the d_core2 product per block
+  constexpr int KSB = NR / 8;            // its k-steps
+  constexpr int BLK4 = GB * IMG / 4;     // 16-byte pieces per block
+  static_assert(KB % 8 == 0 && NR % 16 == 0 && 2 * MT + NTB <= kCoresWarps, "tile shapes");
   extern __shared__ __align__(16) float sm[];
   const int p1 = tt.p[1], p2 = tt.p[2];
-  float* c2s = sm;                                         // [p2][Q2][16]   core2 of the table, k2 innermost
-  float* sbuf = c2s + (size_t)p2 * Q2 * R2;                // [warps][kCoresBufs][IMG]
-  float* red = sbuf + kCoresWarps * kCoresBufs * IMG;      // [kCoresA][NR * 16]
-  __shared__ int32_t cnts[512];                            // rows of the CTA's groups (p2 <= 512, find_r)
+  const int nblk = (p2 + GB - 1) / GB;
+  float* c2s = sm;                                         // [nblk * KB][kC2S]  core2[i2][k2][j2] at row i2 Q2 + j2
+  float* sbuf = c2s + (size_t)nblk * KB * kC2S;            // [kCoresBufs][GB * IMG]
+  __shared__ int32_t cnts[512 + kCoresGB];                 // rows of the CTA's groups (p2 <= 512, find_r)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int ti1 = blockIdx.x, table = ti1 / p1;
-  const bool second = warp >= kCoresA;                     // warps 0..9: d_core1 (FP32 pipe), 10..15: d_core2 (tensor)
-  const int w8 = second ? warp - kCoresA : warp;
-  const int nws = second ? kCoresB : kCoresA;              // warps that share this warp's role
+  const size_t h0 = (size_t)ti1 * p2;
+  RC_MARK(0);
   pdl_trigger();
   {   // operands nobody in this call writes
     const float* core2 = tt.core[2] + (size_t)table * p2 * (R2 * Q2);
     constexpr int PER = kCoresThreads / (R2 * Q2);         // core2 rows per pass; a thread keeps its (k2, j2)
     const int e = threadIdx.x % (R2 * Q2), k2 = e / Q2, j2 = e % Q2;
     if (threadIdx.x < PER * R2 * Q2)
-      for (int i2 = threadIdx.x / (R2 * Q2); i2 < p2; i2 += PER)
-        c2s[((size_t)i2 * Q2 + j2) * R2 + k2] = __ldg(core2 + (size_t)i2 * (R2 * Q2) + e);
+      for (int i2 = threadIdx.x / (R2 * Q2); i2 < nblk * GB; i2 += PER)
+        c2s[((size_t)i2 * Q2 + j2) * kC2S + k2] = (i2 < p2) ? __ldg(core2 + (size_t)i2 * (R2 * Q2) + e) : 0.f;
   }
-  const size_t h0 = (size_t)ti1 * p2;
-  float* mybuf = sbuf + warp * kCoresBufs * IMG;
-  auto stage = [&](int i2, int b) {
-    if (i2 < p2 && cnts[i2] > 0) {
-      const float* src = S1 + (h0 + i2) * IMG;
-      for (int i = lane; i < IMG / 4; i += 32) cp_async16(mybuf + b * IMG + 4 * i, src + 4 * i);
+  const bool role_a = warp < 2 * MT, role_b = !role_a && warp < 2 * MT + NTB;
+  // d_core2 warps: core1[i1]^T fragments a0 (k2 = g, r = t + 8 ks), a1 (g + 8, r), a2 (g, r + 4), a3 (g + 8, r + 4)
+  uint32_t ah[KSB][4], al[KSB][4];
+  if (role_b) {
+    const float* c1 = tt.core[1] + (size_t)ti1 * (NR * R2);
+#pragma unroll
+    for (int ks = 0; ks < KSB; ++ks) {
+      const float v0 = __ldg(c1 + (t + 8 * ks) * R2 + g), v1 = __ldg(c1 + (t + 8 * ks) * R2 + g + 8);
+      const float v2 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g), v3 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g + 8);
+      ah[ks][0] = __float_as_uint(v0);
+      ah[ks][1] = __float_as_uint(v1);
+      ah[ks][2] = __float_as_uint(v2);
+      ah[ks][3] = __float_as_uint(v3);
+      al[ks][0] = __float_as_uint(lo_of(v0));
+      al[ks][1] = __float_as_uint(lo_of(v1));
+      al[ks][2] = __float_as_uint(lo_of(v2));
+      al[ks][3] = __float_as_uint(lo_of(v3));
+    }
+  }
+  RC_MARK(1);
+  pdl_wait();
+  RC_MARK(2);
+  for (int i = threadIdx.x; i < nblk * GB; i += kCoresThreads) cnts[i] = (i < p2) ? ld_dep_s32(cnt + h0 + i) : 0;
+  __syncthreads();
+  RC_MARK(3);
+  auto stage = [&](int blk) {     // everybody copies its pieces of the block; untouched groups become zeros
+    if (blk < nblk && !(dbg & 2)) {
+      float* dst = sbuf + (size_t)(blk % kCoresBufs) * (GB * IMG);
+      const float* src = S1 + (h0 + (size_t)blk * GB) * IMG;
+      for (int i = threadIdx.x; i < BLK4; i += kCoresThreads) {
+        if (cnts[blk * GB + i / (IMG / 4)] > 0)
+          cp_async16(dst + 4 * i, src + 4 * i);
+        else
+          *reinterpret_cast<float4*>(dst + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
     cp_async_commit();
   };
-  if (!second) {
-    pdl_wait();
-    for (int i = threadIdx.x; i < p2; i += kCoresThreads) cnts[i] = ld_dep_s32(cnt + h0 + i);
-    __syncthreads();
-    float acc1[U][R2];
+  // d_core1 warps: tile (mt, nt); per k-step and half, where the lane's flattened index t + 4 h + 8 ks sits in a block
+  const int mt = warp >> 1, nt = warp & 1;
+  int offa[KSA][2];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+  for (int ks = 0; ks < KSA; ++ks)
 #pragma unroll
-      for (int k = 0; k < R2; ++k) acc1[u][k] = 0.f;
-    int b = 0;
+    for (int h = 0; h < 2; ++h) {
+      const int kk = t + 4 * h + 8 * ks;
+      offa[ks][h] = (kk / Q2) * IMG + (kk % Q2) + (g + 16 * mt) * Q2;
+    }
+  // d_core2 warps: n-tile ntb; the lane's column g + 8 ntb of the block = (group gi, j2)
+  const int ntb = warp - 2 * MT;
+  const int nnb = g + 8 * ntb, offb = (nnb / Q2) * IMG + (nnb % Q2) + t * Q2;
+  float acc1[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  stage(0);
+  stage(1);
+  for (int blk = 0; blk < nblk; ++blk) {
+    cp_async_wait<1>();
+    __syncthreads();                 // block blk has landed; everybody is done with block blk - 1
+#ifdef TTG_R_TIMING
+    if (blk == 0) RC_MARK(4);
+#endif
+    stage(blk + 2);
+    const float* sb = sbuf + (size_t)(blk % kCoresBufs) * (GB * IMG);
+    if (dbg & 1) continue;
+    if (role_a) {
+      const float* cb = c2s + (size_t)blk * KB * kC2S + g + 8 * nt;
+      // a block's products run in fresh tensor-core accumulators (their additions truncate: short chains) and
+      // join the sums over the blocks by ordinary FP32 additions
+      float part[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-    for (int k = 0; k < kCoresBufs - 1; ++k) stage(w8 + k * nws, k);
-    for (int i2 = w8; i2 < p2; i2 += nws, b = (b + 1) % kCoresBufs) {
-      stage(i2 + (kCoresBufs - 1) * nws, (b + kCoresBufs - 1) % kCoresBufs);
-      cp_async_wait<kCoresBufs - 1>();
-      __syncwarp();
-      if (cnts[i2] > 0) {
-        const float* sb = mybuf + b * IMG;
-        float sv[U][Q2];
+      for (int ks = 0; ks < KSA; ++ks) {
+        const float a0 = sb[offa[ks][0]], a1 = sb[offa[ks][0] + 8 * Q2];
+        const float a2 = sb[offa[ks][1]], a3 = sb[offa[ks][1] + 8 * Q2];
+        const float b0 = cb[(t + 8 * ks) * kC2S], b1 = cb[(t + 4 + 8 * ks) * kC2S];
+        // one accumulator per term of the split: three short chains instead of a long one
+        mma_tf32(part[0], __float_as_uint(lo_of(a0)), __float_as_uint(lo_of(a1)), __float_as_uint(lo_of(a2)),
+                 __float_as_uint(lo_of(a3)), __float_as_uint(b0), __float_as_uint(b1));
+        mma_tf32(part[1], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3),
+                 __float_as_uint(lo_of(b0)), __float_as_uint(lo_of(b1)));
+        mma_tf32(part[2], __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3),
+                 __float_as_uint(b0), __float_as_uint(b1));
+      }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int r = min(lane + 32 * u, NR - 1);
+      for (int e = 0; e < 4; ++e) {
+        acc1[0][e] += part[0][e] + part[1][e];     // the two small terms
+        acc1[1][e] += part[2][e];
+      }
+    } else if (role_b) {
+      // six independent chains: one per term of the split and parity of the k-step
+      float a_lh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, a_hl[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}},
+            a_hh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-          for (int j2 = 0; j2 < Q2; ++j2) sv[u][j2] = sb[r * Q2 + j2];
+      for (int ks = 0; ks < KSB; ++ks) {
+        const float b0 = sb[offb + 8 * ks * Q2], b1 = sb[offb + (4 + 8 * ks) * Q2];
+        mma_tf32(a_lh[ks & 1], al[ks][0], al[ks][1], al[ks][2], al[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+        mma_tf32(a_hl[ks & 1], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(lo_of(b0)),
+                 __float_as_uint(lo_of(b1)));
+        mma_tf32(a_hh[ks & 1], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(b0), __float_as_uint(b1));
+      }
+      // c0 (k2 = g, column 2 t), c1 (g, 2 t + 1), c2 (g + 8, 2 t), c3 (g + 8, 2 t + 1) of this n-tile
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int nn = 2 * t + e + 8 * ntb, gi = nn / Q2, j2 = nn % Q2, i2 = blk * GB + gi;
+        if (i2 < p2) {
+          float* out2 = parts2 + (h0 + i2) * (R2 * Q2) + j2;
+          out2[g * Q2] = ((a_lh[0][e] + a_lh[1][e]) + (a_hl[0][e] + a_hl[1][e])) + (a_hh[0][e] + a_hh[1][e]);
+          out2[(g + 8) * Q2] = ((a_lh[0][2 + e] + a_lh[1][2 + e]) + (a_hl[0][2 + e] + a_hl[1][2 + e])) +
+                               (a_hh[0][2 + e] + a_hh[1][2 + e]);
         }
-        const float* c2 = c2s + (size_t)i2 * Q2 * R2;
-#pragma unroll
-        for (int j2 = 0; j2 < Q2; ++j2) {
-#pragma unroll
-          for (int k4 = 0; k4 < R2 / 4; ++k4) {
-            const float4 cv = *reinterpret_cast<const float4*>(c2 + j2 * R2 + 4 * k4);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-              acc1[u][4 * k4 + 0] = fmaf(sv[u][j2], cv.x, acc1[u][4 * k4 + 0]);
-              acc1[u][4 * k4 + 1] = fmaf(sv[u][j2], cv.y, acc1[u][4 * k4 + 1]);
-              acc1[u][4 * k4 + 2] = fmaf(sv[u][j2], cv.z, acc1[u][4 * k4 + 2]);
-              acc1[u][4 * k4 + 3] = fmaf(sv[u][j2], cv.w, acc1[u][4 * k4 + 3]);
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-    cp_async_wait<0>();
-    // d_core1[i1] = sum of these warps' accumulators
-    float* myred = red + (size_t)w8 * (NR * R2);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int r = lane + 32 * u;
-      if (r < NR) {
-#pragma unroll
-        for (int k4 = 0; k4 < R2 / 4; ++k4)
-          *reinterpret_cast<float4*>(myred + r * R2 + 4 * k4) =
-              make_float4(acc1[u][4 * k4], acc1[u][4 * k4 + 1], acc1[u][4 * k4 + 2], acc1[u][4 * k4 + 3]);
       }
     }
-  } else {
-    // core1[i1]^T fragments: a0 (k2 = g, r = t + 8 ks), a1 (k2 = g + 8, r), a2 (g, r + 4), a3 (g + 8, r + 4)
-    uint32_t ah[KS][4], al[KS][4];
-    {
-      const float* c1 = tt.core[1] + (size_t)ti1 * (NR * R2);
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const float v0 = __ldg(c1 + (t + 8 * ks) * R2 + g), v1 = __ldg(c1 + (t + 8 * ks) * R2 + g + 8);
-        const float v2 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g), v3 = __ldg(c1 + (t + 4 + 8 * ks) * R2 + g + 8);
-        ah[ks][0] = __float_as_uint(v0);
-        ah[ks][1] = __float_as_uint(v1);
-        ah[ks][2] = __float_as_uint(v2);
-        ah[ks][3] = __float_as_uint(v3);
-        al[ks][0] = __float_as_uint(lo_of(v0));
-        al[ks][1] = __float_as_uint(lo_of(v1));
-        al[ks][2] = __float_as_uint(lo_of(v2));
-        al[ks][3] = __float_as_uint(lo_of(v3));
-      }
-    }
-    pdl_wait();
-    for (int i = threadIdx.x; i < p2; i += kCoresThreads) cnts[i] = ld_dep_s32(cnt + h0 + i);
-    __syncthreads();
-    int b = 0;
-#pragma unroll
-    for (int k = 0; k < kCoresBufs - 1; ++k) stage(w8 + k * nws, k);
-    for (int i2 = w8; i2 < p2; i2 += nws, b = (b + 1) % kCoresBufs) {
-      stage(i2 + (kCoresBufs - 1) * nws, (b + kCoresBufs - 1) % kCoresBufs);
-      cp_async_wait<kCoresBufs - 1>();
-      __syncwarp();
-      float* out2 = parts2 + (h0 + i2) * (R2 * Q2);
-      if (cnts[i2] > 0) {
-        const float* sb = mybuf + b * IMG;
-        // three independent chains, one per term of the split
-        float a_lh[4] = {0.f, 0.f, 0.f, 0.f}, a_hl[4] = {0.f, 0.f, 0.f, 0.f}, a_hh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-          const bool on = (Q2 == 8) || g < Q2;
-          const float b0 = on ? sb[(t + 8 * ks) * Q2 + g] : 0.f, b1 = on ? sb[(t + 4 + 8 * ks) * Q2 + g] : 0.f;
-          mma_tf32(a_lh, al[ks][0], al[ks][1], al[ks][2], al[ks][3], __float_as_uint(b0), __float_as_uint(b1));
-          mma_tf32(a_hl, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(lo_of(b0)),
-                   __float_as_uint(lo_of(b1)));
-          mma_tf32(a_hh, ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], __float_as_uint(b0), __float_as_uint(b1));
-        }
-        // c0 (k2 = g, j2 = 2 t), c1 (g, 2 t + 1), c2 (g + 8, 2 t), c3 (g + 8, 2 t + 1)
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-          if (2 * t + e < Q2) {
-            out2[g * Q2 + 2 * t + e] = (a_lh[e] + a_hl[e]) + a_hh[e];
-            out2[(g + 8) * Q2 + 2 * t + e] = (a_lh[2 + e] + a_hl[2 + e]) + a_hh[2 + e];
-          }
-      } else {
-        for (int i = lane; i < R2 * Q2; i += 32) out2[i] = 0.f;
-      }
-      __syncwarp();
-    }
-    cp_async_wait<0>();
   }
-  __syncthreads();
-  for (int o = threadIdx.x; o < NR * R2 / 4; o += kCoresThreads) {
-    float4 v = reinterpret_cast<const float4*>(red)[o];
+  cp_async_wait<0>();
+  if (role_a) {   // c0 (r = g + 16 mt, k2 = 2 t + 8 nt), c1 (r, k2 + 1), c2 (r + 8, k2), c3 (r + 8, k2 + 1)
+    float* out1 = dcore1 + (size_t)ti1 * (NR * R2) + (g + 16 * mt) * R2 + 2 * t + 8 * nt;
+    float v[4];
 #pragma unroll
-    for (int w = 1; w < kCoresA; ++w) {
-      const float4 x = reinterpret_cast<const float4*>(red + (size_t)w * (NR * R2))[o];
-      v.x += x.x;
-      v.y += x.y;
-      v.z += x.z;
-      v.w += x.w;
-    }
-    reinterpret_cast<float4*>(dcore1 + (size_t)ti1 * (NR * R2))[o] = v;
+    for (int e = 0; e < 4; ++e) v[e] = acc1[0][e] + acc1[1][e];
+    *reinterpret_cast<float2*>(out1) = make_float2(v[0], v[1]);
+    *reinterpret_cast<float2*>(out1 + 8 * R2) = make_float2(v[2], v[3]);
   }
+  RC_MARK(5);
 }
 
 }  // namespace
@@ -975,7 +980,8 @@ int rm_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_
 
 template <int Q1, int Q2>
 size_t rm_cores_smem(int p2) {
-  return sizeof(float) * ((size_t)p2 * Q2 * 16 + (size_t)kCoresWarps * kCoresBufs * 16 * Q1 * Q2 + (size_t)kCoresA * 16 * Q1 * 16);
+  const size_t nblk = (size_t)(p2 + kCoresGB - 1) / kCoresGB;
+  return sizeof(float) * (nblk * kCoresGB * Q2 * kC2S + (size_t)kCoresBufs * kCoresGB * 16 * Q1 * Q2);
 }
 
 template <int Q1, int Q2>
@@ -985,7 +991,7 @@ int rm_cores_launch(const TTDev& tt, const RPlan& pl, float* const* dcore, cudaS
   TTG_ENSURE_SMEM(kern, smem);
   prof_begin(K_BWD_CORES, stream);
   TTG_CUDA(launch_pdl(kern, dim3((unsigned)(tt.num_tables * tt.p[1])), dim3(kCoresThreads), smem, stream, tt,
-                      (const float*)pl.S1, pl.cnt, dcore[1], pl.d2parts));
+                      (const float*)pl.S1, pl.cnt, dcore[1], pl.d2parts, getenv("TTG_DBG_CORES") ? atoi(getenv("TTG_DBG_CORES")) : 0));
   prof_end(K_BWD_CORES, stream);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -1028,6 +1034,7 @@ int rm_forward(const TTDev& tt, int64_t nnz, const RPlan& pl, float* output, boo
 
 #ifdef TTG_R_TIMING
 extern "C" void ttg_rm_marks(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_rm_marks, sizeof(g_rm_marks)); }
+extern "C" void ttg_rc_marks(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_rc_marks, sizeof(g_rc_marks)); }
 extern "C" void ttg_rm_phases(unsigned long long* out, int reset) {
   if (reset) {
     unsigned long long z[8] = {0};

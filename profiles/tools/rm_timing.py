@@ -30,9 +30,9 @@ lib.ttg_rm_phases(ph, 1)
 step()
 torch.cuda.synchronize()
 lib.ttg_rm_phases(ph, 0)
-buf = (C.c_ulonglong * (148 * 16 * 6))()
+buf = (C.c_ulonglong * (148 * 32 * 6))()
 lib.ttg_rm_marks(buf)
-m = np.frombuffer(buf, dtype=np.uint64).reshape(148 * 16, 6).astype(np.int64)
+m = np.frombuffer(buf, dtype=np.uint64).reshape(148 * 32, 6)[:148 * 16].astype(np.int64)
 t0 = m[:, 0].min()
 m = (m - t0) / 1e3
 names = ["entry", "after wait+staging", "run set up", "first tile ready", "loop done", "kernel end"]
@@ -47,3 +47,10 @@ tot = sum(ph[i] for i in range(7))
 print("tile loop of CTA 3, cycles summed over its warps (clock64 between phases; asynchronous work lands where it is waited for):")
 for i, n in enumerate(pn):
     print("  %-28s %10d  %5.1f%%" % (n, ph[i], 100.0 * ph[i] / tot))
+rc = (C.c_ulonglong * (1024 * 6))()
+lib.ttg_rc_marks(rc)
+c = np.frombuffer(rc, dtype=np.uint64).reshape(1024, 6)[:p[1]].astype(np.int64)
+c = (c - c[:, 0].min()) / 1e3
+print("cores kernel, us since its first CTA entered: min / median / max over %d CTAs" % len(c))
+for i, n in enumerate(["entry", "operands staged", "preceding kernel done", "row counts in", "first block in", "end"]):
+    print("  %-22s %8.1f %8.1f %8.1f" % (n, c[:, i].min(), np.median(c[:, i]), c[:, i].max()))
