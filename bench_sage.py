@@ -40,7 +40,8 @@ DEFAULTS = dict(nodes=2449029, edges=123718280, train=196615, hidden=256, classe
 
 def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0, matmul="fp32",
                       nodes=DEFAULTS["nodes"], edges=DEFAULTS["edges"], train=DEFAULTS["train"],
-                      hidden=DEFAULTS["hidden"], classes=DEFAULTS["classes"], clock_sampler=None):
+                      hidden=DEFAULTS["hidden"], classes=DEFAULTS["classes"], clock_sampler=None,
+                      fuse_input=False, other_steps=40):
     """One warm-up epoch + `epochs` timed ones on an initialised process group (world > 1) or alone.
     Returns the record (every rank; the timing is already the max over ranks)."""
     import torch.distributed as dist
@@ -64,18 +65,20 @@ def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0,
     eff = (config == 3 and world == 1)
     model = sage.SAGE(nodes, 100, hidden, classes, 3, 0.5, (16, 16), (125, 140, 140), (4, 5, 5),
                       sparse=(world == 1), learning_rate=0.01, embed_name="eff" if eff else "fbtt",
-                      device=dev).to(dev)
+                      device=dev, fuse_input=fuse_input).to(dev)
     if world > 1:   # identical replicas
         for p in list(model.parameters()):
             dist.broadcast(p.data, 0)
     trainer = sage.Trainer(model, lr=0.003, world=world)
     smp = sampler.NeighborSampler([5, 10, 15])
 
-    def run_epoch(epoch):
+    def run_epoch(epoch, max_steps=None):
         perm = dp.epoch_permutation(train, epoch, seed=3)
         lo, hi = dp.shard_range(train, rank, world)
         mine = train_idx[perm[lo:hi]].to(dev)
         nsteps = (mine.numel() + batch - 1) // batch
+        if max_steps is not None:
+            nsteps = min(nsteps, max_steps)
         if world > 1:     # every rank runs the same number of steps (collectives inside)
             t = torch.tensor([nsteps], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -115,6 +118,15 @@ def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0,
         secs.append(s)
         losses.append(l)
     clocks = sampler_proc.stop() if sampler_proc else None
+    # the same steps with the other data flow of the first layer (a short run): fused = the neighbour mean taken
+    # by the TT lookup itself, plain = all num_src rows reconstructed and then aggregated (gnn_model.py:199-217)
+    ms_other = None
+    if not eff and other_steps > 0:
+        model.fuse_input = not model.fuse_input
+        run_epoch(epochs + 1, max_steps=8)
+        s_u, n_u, _, _ = run_epoch(epochs + 2, max_steps=other_steps)
+        ms_other = s_u / n_u * 1e3
+        model.fuse_input = not model.fuse_input
     # replicas must still be identical after the epochs (cores and dense layers)
     identical = None
     if world > 1:
@@ -134,6 +146,10 @@ def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0,
         "metric": "GraphSAGE epoch seconds @ogbn-products shape", "value": best, "unit": "s",
         "n_gpus": world, "higher_is_better": False, "scaling": "strong", "epochs_timed": secs,
         "steps_per_epoch_per_rank": steps, "ms_per_step": best / steps * 1e3,
+        "first_layer": ("neighbour mean taken by the TT lookup (one EmbeddingBag call, bags = destinations + their "
+                        "sampled neighbours); [num_src, 100] is never written" if model.fuse_input else
+                        "all num_src rows reconstructed, then aggregated (gnn_model.py:199-217)"),
+        ("ms_per_step_plain_first_layer" if model.fuse_input else "ms_per_step_fused_first_layer"): ms_other,
         "seeds_per_s": train / best, "data": "synthetic", "dtype": "f32",
         "dense_layer_matmul": matmul, "loss_last": losses[-1], "clocks": clocks,
         "replicas_bit_identical": identical, "exchange_failed": failed,

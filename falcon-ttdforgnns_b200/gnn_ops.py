@@ -174,6 +174,16 @@ class SAGEConv(nn.Module):
             out = out + self.bias
         return out
 
+    def forward_aggregated(self, h_dst: torch.Tensor, h_mean: torch.Tensor) -> torch.Tensor:
+        """The same layer when the caller already holds the destination rows and the neighbour mean
+        (sage.SAGE with fuse_input: the TT lookup sums the neighbours' rows per destination itself)."""
+        if self.in_feats > self.out_feats:
+            raise NotImplementedError("forward_aggregated: this layer applies fc_neigh before the aggregation")
+        out = self.fc_self(h_dst) + self.fc_neigh(h_mean)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
 
 class GraphConv(nn.Module):
     """GCN layer with DGL `GraphConv(norm='both', allow_zero_in_degree=True)` semantics:

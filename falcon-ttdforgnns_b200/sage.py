@@ -24,12 +24,17 @@ class SAGE(nn.Module):
                  n_layers: int = 3, dropout: float = 0.5, tt_rank: Sequence[int] = (16, 16),
                  p_shapes: Optional[Sequence[int]] = None, q_shapes: Optional[Sequence[int]] = None,
                  sparse: bool = True, learning_rate: float = 0.01, embed_name: str = "fbtt",
-                 device=None):
-        """embed_name: "fbtt" (TTEmbeddingBag, --emb-name fbtt of the reference drivers) or "eff"
+                 device=None, fuse_input: bool = False):
+        """fuse_input (fbtt only): the first layer's neighbour mean comes out of the TT lookup itself -- one
+        EmbeddingBag call whose bags are the destination nodes (one index each) followed by every destination's
+        sampled neighbours (gnn_model.py:199-217 reconstructs all num_src rows and lets the layer gather them:
+        [num_src, in_feats] written and read again every step).
+        embed_name: "fbtt" (TTEmbeddingBag, --emb-name fbtt of the reference drivers) or "eff"
         (Eff_TTEmbedding, Efficient_TT/efficient_tt.py:214-307: forward by prefix reuse, backward = the
         fused SGD update of the cores, no gradient reaches autograd)."""
         super().__init__()
         self.embed_name = embed_name
+        self.fuse_input = bool(fuse_input) and embed_name == "fbtt" and in_feats <= n_hidden
         self.layers = nn.ModuleList()
         self.layers.append(SAGEConv(in_feats, n_hidden, "mean"))
         for _ in range(1, n_layers - 1):
@@ -58,16 +63,37 @@ class SAGE(nn.Module):
         return [p for layer in self.layers for p in layer.parameters()]
 
     def forward(self, blocks: Sequence[Block], input_nodes: torch.Tensor) -> torch.Tensor:
-        if self.embed_name == "eff":
+        first = 0
+        if self.fuse_input:
+            h = self._fused_first_layer(blocks[0], input_nodes)
+            if len(self.layers) > 1:
+                h = self.dropout(F.relu(h))
+            first = 1
+        elif self.embed_name == "eff":
             h = self.embed_layer(input_nodes)
         else:
             offsets = torch.arange(input_nodes.numel() + 1, device=input_nodes.device)
             h = self.embed_layer(input_nodes, offsets)
-        for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+        for l in range(first, len(self.layers)):
+            layer, block = self.layers[l], blocks[l]
             h = layer(block, (h, h[:block.num_dst]))
             if l != len(self.layers) - 1:
                 h = self.dropout(F.relu(h))
         return h
+
+    def _fused_first_layer(self, block: Block, input_nodes: torch.Tensor) -> torch.Tensor:
+        """Bags 0 .. num_dst - 1: the destination nodes themselves; bags num_dst .. 2 num_dst - 1: their
+        sampled neighbours, summed by the lookup (pooling "sum" of TTEmbeddingBag) and divided by the
+        in-degree here.  One lookup, one backward, one fused update of the cores -- the same gradient as
+        gathering reconstructed rows, since the mean is linear in them."""
+        nd = block.num_dst
+        dev = input_nodes.device
+        idx = torch.cat([input_nodes[:nd], input_nodes[block.indices.long()]])
+        offsets = torch.cat([torch.arange(nd, device=dev, dtype=torch.int64), block.indptr.to(torch.int64) + nd])
+        out = self.embed_layer(idx, offsets)
+        deg = block.in_degrees().clamp(min=1).to(torch.float32)
+        h_mean = out[nd:] / deg.unsqueeze(1)
+        return self.layers[0].forward_aggregated(out[:nd], h_mean)
 
 
 def synthetic_graph(num_nodes: int, num_edges: int, device, seed: int = 0, alpha: float = 2.1
