@@ -246,3 +246,56 @@ def dp_backward_step(module, d_cores: Sequence[torch.Tensor], group=None,
                     reduced, module.learning_rate, "sgd" if sgd else "adagrad", module.eps,
                     None if sgd else list(module.optimizer_state))
     return reduced
+
+
+def merged_key_counts(keys: torch.Tensor, counts: torch.Tensor, group=None):
+    """Union of every rank's (key, count) pairs with the counts of equal keys added: the access statistics of the
+    whole job instead of one rank's shard of the seeds.  Collective; every rank returns the same sorted keys and
+    their summed counts.  (The reference populates each replica's cache from its own counts,
+    FBTT/tt_embeddings_ops.py:816-830 under sage_dgl_partition.py:359-361, so the replicas cache different
+    rows)"""
+    keys = keys.reshape(-1).to(torch.int64)
+    counts = counts.reshape(-1).to(torch.int64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        n = torch.tensor([keys.numel()], dtype=torch.int64, device=keys.device)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+        cap = max(int(x.item()) for x in sizes)
+        pad_k = torch.full((cap,), -1, dtype=torch.int64, device=keys.device)
+        pad_c = torch.zeros((cap,), dtype=torch.int64, device=keys.device)
+        pad_k[:keys.numel()] = keys
+        pad_c[:keys.numel()] = counts
+        all_k = [torch.empty_like(pad_k) for _ in range(world)]
+        all_c = [torch.empty_like(pad_c) for _ in range(world)]
+        dist.all_gather(all_k, pad_k, group=group)
+        dist.all_gather(all_c, pad_c, group=group)
+        keys = torch.cat([k[:int(m.item())] for k, m in zip(all_k, sizes)])
+        counts = torch.cat([c[:int(m.item())] for c, m in zip(all_c, sizes)])
+    uk, inv = torch.unique(keys, return_inverse=True)
+    uc = torch.zeros(uk.numel(), dtype=torch.int64, device=keys.device).index_add_(0, inv, counts)
+    return uk, uc
+
+
+def merge_lfu_statistics(module, group=None) -> int:
+    """Replace the LFU table of a cached TTEmbeddingBag (hashtbl, cache_freq) by the merged statistics of all
+    ranks, so that the cache_populate() that follows picks the same rows on every replica.  Call it on every
+    rank right before module.cache_populate().  Returns the number of distinct keys."""
+    import tt_embeddings
+    if not getattr(module, "use_cache", False):
+        return 0
+    tbl, freq = module.hashtbl, module.cache_freq
+    used = tbl >= 0
+    uk, uc = merged_key_counts(tbl[used], freq[used], group)
+    if uk.numel() > tbl.numel():
+        # more distinct rows than slots: keep the most frequent ones (ties by key, the same on every rank)
+        order = torch.argsort(uc * (int(uk.max().item()) + 1) - uk, descending=True)[:tbl.numel()]
+        order, _ = torch.sort(order)
+        uk, uc = uk[order], uc[order]
+    tbl.fill_(-1)
+    freq.fill_(0)
+    tt_embeddings.update_cache_state(uk, tbl, freq)        # every key once
+    slots = (tbl >= 0).nonzero(as_tuple=True)[0]
+    pos = torch.searchsorted(uk, tbl[slots])
+    freq[slots] = uc[pos].to(freq.dtype)
+    return int(uk.numel())

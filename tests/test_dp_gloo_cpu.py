@@ -60,6 +60,48 @@ def test_two_ranks_exchange_and_shard(tmp_path):
     assert abs(z[0]["mine"].size - z[1]["mine"].size) <= 1
 
 
+def _merge_worker(rank, world, port, out_dir):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import dp
+    g = torch.Generator().manual_seed(7 + rank)
+    keys = torch.randperm(500, generator=g)[:120 + 30 * rank]          # ragged: ranks hold different numbers
+    counts = torch.randint(1, 50, (keys.numel(),), generator=g)
+    uk, uc = dp.merged_key_counts(keys, counts)
+    np.savez(os.path.join(out_dir, "merge%d.npz" % rank), keys=keys.numpy(), counts=counts.numpy(),
+             uk=uk.numpy(), uc=uc.numpy())
+    dist.destroy_process_group()
+
+
+def test_two_ranks_merge_lfu_statistics(tmp_path):
+    """dp.merged_key_counts: the union of the ranks' keys with the counts of equal keys added, identical on
+    every rank (what dp.merge_lfu_statistics writes back into the LFU table before cache_populate)."""
+    world = 2
+    mp.spawn(_merge_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    z = [np.load(os.path.join(str(tmp_path), "merge%d.npz" % r)) for r in range(world)]
+    want = {}
+    for r in range(world):
+        for k, c in zip(z[r]["keys"], z[r]["counts"]):
+            want[int(k)] = want.get(int(k), 0) + int(c)
+    ks = np.array(sorted(want))
+    for r in range(world):
+        assert np.array_equal(z[r]["uk"], ks)
+        assert np.array_equal(z[r]["uc"], np.array([want[int(k)] for k in ks]))
+
+
+def test_merged_key_counts_without_a_process_group():
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import dp
+    uk, uc = dp.merged_key_counts(torch.tensor([5, 3, 5, 9]), torch.tensor([1, 2, 3, 4]))
+    assert uk.tolist() == [3, 5, 9] and uc.tolist() == [2, 4, 4]
+
+
 def test_shard_range_is_balanced_and_complete():
     for p in (ROOT, PKG):
         if p not in sys.path:

@@ -109,6 +109,32 @@ def test_cache_flow_matches_uncached_until_rows_are_trained(ttg_lib):
         assert k in sd
 
 
+def test_merge_lfu_statistics_rebuilds_the_table_with_the_same_counts(ttg_lib):
+    """dp.merge_lfu_statistics on one rank is the identity on (key -> count): the table is rebuilt from the merged
+    pairs (the two-rank merge itself is covered on CPU, tests/test_dp_gloo_cpu.py) and cache_populate() then
+    caches the most frequent rows."""
+    import dp
+    n_emb, D, ranks, p, q = 5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]
+    m = _make(n_emb, D, ranks, p, q, sparse=False, use_cache=True, cache_size=20, hashtbl_size=4001)
+    rng = np.random.default_rng(5)
+    hot = torch.from_numpy(rng.choice(n_emb, size=12, replace=False)).to(DEV)
+    for _ in range(4):
+        idx = torch.cat([hot, torch.from_numpy(rng.integers(0, n_emb, size=40)).to(DEV)])
+        m(idx, torch.arange(idx.numel() + 1, device=DEV))
+
+    def table(mod):
+        used = mod.hashtbl >= 0
+        return dict(zip(mod.hashtbl[used].tolist(), mod.cache_freq[used].tolist()))
+
+    before = table(m)
+    assert len(before) > 12 and all(before[int(h)] >= 4 for h in hot.tolist())
+    assert dp.merge_lfu_statistics(m) == len(before)
+    assert table(m) == before
+    m.cache_populate()
+    cached = set(m.hashtbl[m.cache_state >= 0].tolist())
+    assert set(hot.tolist()) <= cached and len(cached) <= 20
+
+
 def test_eff_embedding_forward_and_fused_sgd(ttg_lib):
     from Efficient_TT.efficient_tt import Eff_TTEmbedding
     from FBTT.tt_embeddings_ops import tt_matrix_to_full
