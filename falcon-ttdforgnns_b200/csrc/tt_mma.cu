@@ -1417,6 +1417,7 @@ const MmaEntry kMmaEntries[] = {
     TTG_MMA_SHAPE(4, 5, 5, 16, 16),   // ogbn-products, D = 100   (BASELINE configs 2, 3)
     TTG_MMA_SHAPE(4, 4, 8, 16, 16),   // cora / ogbn-arxiv, D = 128 (configs 1, 4)
     TTG_MMA_SHAPE(4, 4, 8, 32, 32),   // ogbn-papers100M, D = 128 (config 5): table + forward only
+    TTG_MMA_SHAPE(8, 4, 4, 16, 16),   // run_script.sh:299,316 (--q-shapes "8,4,4"), D = 128
 };
 
 const MmaEntry* find_mma(const TTDev& tt) {

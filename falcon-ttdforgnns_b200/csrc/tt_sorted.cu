@@ -1464,6 +1464,8 @@ const Entry kEntries[] = {
     TTG_SHAPE(4, 5, 5, 8, 8),     // rank sweeps of run_script.sh tt-ranks
     TTG_SHAPE(4, 5, 5, 32, 32),
     TTG_SHAPE(4, 4, 8, 8, 8),
+    TTG_SHAPE(8, 4, 4, 16, 16),   // run_script.sh:299,316 (--q-shapes "8,4,4")
+    TTG_SHAPE(5, 4, 5, 16, 16),   // run_script.sh:353 (--q-shapes "5,4,5")
 };
 
 const Entry* find_entry(const TTDev& tt) {

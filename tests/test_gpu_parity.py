@@ -192,6 +192,8 @@ SHAPES = {
     "arxiv": ([55, 55, 56], [4, 4, 8], [1, 16, 16, 1], 169343),
     "papers": ([481, 481, 481], [4, 4, 8], [1, 32, 32, 1], 111059956),
     "cora": ([14, 14, 14], [4, 4, 8], [1, 16, 16, 1], 2708),
+    "arxiv_q844": ([55, 55, 56], [8, 4, 4], [1, 16, 16, 1], 169343),     # run_script.sh:299,316
+    "products_q545": ([125, 140, 140], [5, 4, 5], [1, 16, 16, 1], 2449029),  # run_script.sh:353
 }
 
 
@@ -201,7 +203,7 @@ def _random_cores(p, q, r, n_emb, seed):
             for t in range(3)]
 
 
-@pytest.mark.parametrize("shape", ["products", "arxiv", "papers", "cora"])
+@pytest.mark.parametrize("shape", ["products", "arxiv", "papers", "cora", "arxiv_q844", "products_q545"])
 def test_medium_batch_against_oracle(ttg_lib, shape):
     import tt_embeddings as te
     p, q, r, n_emb = SHAPES[shape]
