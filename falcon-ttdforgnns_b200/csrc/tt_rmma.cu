@@ -92,7 +92,8 @@ struct RmArgs {
   int32_t hp;
   FastDiv div_p0, div_hp;
   int32_t nnz;            // rows the plan was built for (>= the rows it holds: invalid indices are dropped)
-  int32_t rpw;            // backward: nominal rows per warp
+  int32_t rpc, rpw;       // backward: nominal rows per CTA, and per warp in the evenly split part
+  int32_t pool_chunk;     // backward: nominal rows per chunk of the rest
 };
 
 // core0 -> shared memory, hi plane (as stored) and lo plane, [c0_rows * 4][kCS]
@@ -460,17 +461,33 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
   for (int i = threadIdx.x; i < (a.c0_rows + kBW) * 16; i += kBT)
     reinterpret_cast<float4*>(d0s)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = threadIdx.x; i < kBW * kRingFloats; i += kBT) rings[i] = 0.f;   // padded columns meet zeros, not NaNs
-  int total, rs, re;
+  __shared__ int pool_next;
+  if (threadIdx.x == 0) pool_next = 0;
   pdl_wait();
   __syncthreads();
   RM_MARK(1);
-  // Rows are handed to warps in runs of about rpw that begin and end at group boundaries (a group's S1 is then
-  // summed in one warp's registers and stored once).  Everything the set-up needs is requested in one go: the
-  // row count, the windows of sorted rows at the nominal start (which also hold the boundary), and the keys
-  // around the nominal end.
-  const int nw = (int)gridDim.x * kBW;
-  const int w = (int)blockIdx.x * kBW + warp;
-  const int x1 = min(w * a.rpw, a.nnz), x2 = min((w + 1) * a.rpw, a.nnz);
+  // Rows are handed out in runs that begin and end at group boundaries (a group's S1 is then summed in one
+  // warp's registers and stored once).  A CTA owns the nominal rows [blockIdx.x rpc, (blockIdx.x + 1) rpc): the
+  // first part is split evenly over its warps, the rest (none by default, see the launcher) is a pool of small
+  // chunks the warps take as they run out of work.
+  const int cta0 = min((int)blockIdx.x * a.rpc, a.nnz), cta1 = min(cta0 + a.rpc, a.nnz);
+  const int pool0 = min(cta0 + kBW * a.rpw, cta1);
+  float* ring = rings + warp * kRingFloats;
+  for (int item = -1;; ) {
+  int x1, x2;
+  if (item < 0) {
+    x1 = min(cta0 + warp * a.rpw, pool0);
+    x2 = min(x1 + a.rpw, pool0);
+    item = 0;
+  } else {
+    int j = 0;
+    if (lane == 0) j = atomicAdd(&pool_next, 1);
+    j = __shfl_sync(kFull, j, 0);
+    x1 = pool0 + j * a.pool_chunk;
+    if (x1 >= cta1) break;
+    x2 = min(x1 + a.pool_chunk, cta1);
+  }
+  int total, rs, re;
   auto load_key = [&](int at) -> uint32_t { return ld_dep_u32(a.skeys + max(0, min(at + lane, a.nnz - 1))); };
   auto load_src = [&](int at) -> uint32_t { return ld_dep_u32(a.srow + max(0, min(at + lane, a.nnz - 1))); };
   auto split_key = [&](uint32_t key, uint32_t& grp, int32_t& i0c) {
@@ -506,9 +523,9 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
     };
     total = total_;
     rs = boundary(x1, gc);
-    re = (w + 1 == nw) ? total_ : boundary(x2, fdiv(ke, a.div_p0));
+    re = boundary(x2, fdiv(ke, a.div_p0));      // x2 at or beyond the row count: the row count
   }
-  float* ring = rings + warp * kRingFloats;
+  (void)total;
   uint32_t bgh[4][2][2], bgl[4][2][2];
   if (rs < re) {
     if (rs - cb >= 32) {     // rare: the boundary lies beyond the first window
@@ -709,7 +726,9 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
     }
     RM_PHASE_FLUSH;
     cp_async_wait<0>();
+    __syncwarp();
   }
+  }   // runs
   RM_MARK(4);
   __syncthreads();
   float* part = a.d0parts + (size_t)blockIdx.x * a.c0_rows * 64;
@@ -970,7 +989,13 @@ int rm_bwd_launch(const TTDev& tt, int64_t nnz, const RPlan& pl, const float* d_
   if (grid * kBW * 8 > nnz) grid = ceil_div(nnz, kBW * 8);
   *nparts = (int)grid;
   a.nnz = (int32_t)nnz;
-  a.rpw = (int32_t)ceil_div(nnz, grid * kBW);
+  a.rpc = (int32_t)ceil_div(nnz, grid);
+  // TTG_RM_POOL16 sixteenths of a CTA's rows go to the pool.  Default 0: measured at 262,144 rows the pool costs
+  // more in run set-ups than it saves at the end (80.5 us without, 84.2 us with 2/16 in chunks of 32 rows)
+  static const int pool16 = getenv("TTG_RM_POOL16") ? atoi(getenv("TTG_RM_POOL16")) : 0;
+  static const int chunk = getenv("TTG_RM_CHUNK") ? atoi(getenv("TTG_RM_CHUNK")) : 32;
+  a.rpw = (int32_t)((int64_t)a.rpc * (16 - pool16) / 16 / kBW);
+  a.pool_chunk = chunk;
   prof_begin(K_BWD_ROWS, stream);
   TTG_CUDA(launch_pdl(kern, dim3((unsigned)grid), dim3(kBT), smem, stream, a));
   prof_end(K_BWD_ROWS, stream);
