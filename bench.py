@@ -548,15 +548,22 @@ def run_ours(args, shape):
     graphed = {}     # (staging slot, batch) -> the module step captured as a CUDA graph
     e2e_graph = use_graph   # with NCCL in the step it stays eager (see above)
 
+    prof_e2e = os.environ.get("TTG_E2E_PROFILE") == "1"      # host time per call of the loop, to stderr
+    host_t = {"get": 0.0, "put": 0.0, "step": 0.0, "release": 0.0, "push": 0.0}
+
     def e2e_pipelined(nsteps, use_graphs):
         reader = pipeline.DeferredScalars(dev, delay=1)
         got, h0 = [], pipe.h2d_bytes
         pipe.put(idx_host[0], off_host)
+        clk = time.perf_counter
         for i in range(nsteps):
             k = i % NUM_ROT
+            t0 = clk()
             indices, offsets = pipe.get()
+            t1 = clk()
             if i + 1 < nsteps:
                 pipe.put(idx_host[(i + 1) % NUM_ROT], off_host)
+            t2 = clk()
             if use_graphs:
                 gk = (indices.data_ptr(), k)
                 gs = graphed.get(gk)
@@ -566,8 +573,20 @@ def run_ours(args, shape):
                 loss = gs()
             else:
                 loss = module_step(indices, offsets, k)
+            t3 = clk()
             pipe.release()
+            t4 = clk()
             got += reader.push(loss)
+            if prof_e2e:
+                t5 = clk()
+                for name, dt in (("get", t1 - t0), ("put", t2 - t1), ("step", t3 - t2), ("release", t4 - t3),
+                                 ("push", t5 - t4)):
+                    host_t[name] += dt
+        if prof_e2e and nsteps > NUM_ROT:
+            print("bench.py: e2e host us per step (graphs=%s): %s" %
+                  (use_graphs, {n: round(v / nsteps * 1e6, 1) for n, v in host_t.items()}), file=sys.stderr)
+        for n in host_t:
+            host_t[n] = 0.0
         got += reader.drain()
         assert len(got) == nsteps
         return got, (pipe.h2d_bytes - h0) // nsteps, reader.d2h_bytes // nsteps
