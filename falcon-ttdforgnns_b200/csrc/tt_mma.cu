@@ -1156,6 +1156,7 @@ constexpr int kFinPer = 12;      // partial copies one thread sums (all loads in
 
 __global__ void __launch_bounds__(256) mma_finalize_kernel(MmaFinalArgs a) {
   __shared__ float4 sm[kFinSlices][kFinCols];
+  pdl_trigger();     // whatever follows (the exchange kernel, the next call's plan) waits for us by itself
   pdl_wait();
   if ((int)blockIdx.x < a.nb0 + a.nb2) {
     // 16 float4 columns x 16 slices of the partial copies; a slice is summed in order, then the slices

@@ -60,9 +60,13 @@ def test_one_rank_exchange_is_the_plain_update(ttg_lib):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_ranks_match_the_nccl_path_and_each_other(ttg_lib):
+@pytest.mark.parametrize("scatter", ["0", "1"], ids=["all_read_all", "reduce_scatter"])
+def test_two_ranks_match_the_nccl_path_and_each_other(ttg_lib, scatter):
+    """both modes of the exchange kernel (csrc/peer.cu: every rank reads all copies / reduce-scatter + broadcast,
+    the default from four ranks on) on two ranks"""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), WORKER]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, TTG_PEER_SCATTER=scatter))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "PEER_EXCHANGE_OK" in r.stdout
