@@ -272,3 +272,100 @@ def test_fused_sgd_and_adagrad_updates(te):
     for t in range(3):
         assert rel_err(state[t].cpu().numpy(), wstate[t]) < TOL
         assert rel_err(dev[t].cpu().numpy(), want[t]) < TOL
+
+
+# --------------------------------------------------------------------------------------------
+# adversarial index distributions for the right-grouped kernels (run ownership, tails, invalid keys)
+# --------------------------------------------------------------------------------------------
+def _both_ways(te, shape, idx, B=None, row=None, seed=1):
+    p, q, r, n_emb = shape
+    D = int(np.prod(q))
+    cores = _cores(p, q, r, n_emb, 31)
+    cn = [c.numpy() for c in cores]
+    nnz = idx.size
+    row = np.arange(nnz, dtype=np.int64) if row is None else row
+    B = nnz if B is None else B
+    valid = (idx >= 0) & (idx < int(np.prod(p)))
+    out = _fwd(te, shape, cores, idx, row, B)
+    want = orc.tt_forward(p, q, r, cn, idx[valid], row[valid], B)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    dO = (np.random.default_rng(seed).random(size=(1, B, D)).astype(np.float32) - 0.5) * 0.2
+    got = _bwd(te, shape, [c.to(DEV) for c in cores], idx, row, dO)
+    wd = orc.tt_backward_dense(p, q, r, cn, idx[valid], row[valid], dO)
+    for t in range(3):
+        assert rel_err(got[t].cpu().numpy(), wd[t]) < TOL, "core %d" % t
+
+
+@pytest.mark.parametrize("name", ["products", "arxiv"])
+def test_one_right_group_holds_the_batch(te, name):
+    """Every row in one (i1, i2) group -- one warp owns the group's S1, the runs of all other warps are empty --
+    then the same group under a uniform background, and a batch that is one id repeated."""
+    shape = SHAPES[name]
+    p, q, r, n_emb = shape
+    rng = np.random.default_rng(17)
+    hp = p[1] * p[2]
+    h = 37 * p[2] + 5
+    i0_max = (n_emb - 1 - h) // hp
+    one_group = (h + hp * rng.integers(0, i0_max + 1, size=6000)).astype(np.int64)
+    _both_ways(te, shape, one_group)
+    mixed = np.concatenate([one_group[:3000], np.full(1000, h + hp * 3),
+                            rng.integers(0, n_emb, size=max(hp, 6000))]).astype(np.int64)
+    rng.shuffle(mixed)
+    _both_ways(te, shape, mixed)
+    _both_ways(te, shape, np.full(hp + 7, h + hp * 2, dtype=np.int64))
+
+
+def test_ragged_batches_around_the_group_count(te):
+    shape = SHAPES["cora"]           # 196 (i1, i2) groups: the right-grouped path starts at nnz = 196
+    rng = np.random.default_rng(23)
+    for nnz in (196, 197, 211, 255, 513, 1000):
+        _both_ways(te, shape, rng.integers(0, shape[3], size=nnz).astype(np.int64), seed=nnz)
+
+
+def test_invalid_indices_and_bags_backward(te):
+    """Out-of-range / negative ids sort behind every valid key and contribute nothing to either pass; bags of
+    0..7 indices share one d_output row."""
+    shape = SHAPES["arxiv"]
+    p, q, r, n_emb = shape
+    rng = np.random.default_rng(29)
+    lengths = rng.integers(0, 8, size=3000)
+    nnz = int(lengths.sum())
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    bad = rng.permutation(nnz)[:200]
+    idx[bad[:100]] = -1 - rng.integers(0, 5, size=100)
+    idx[bad[100:]] = int(np.prod(p)) + rng.integers(0, 1000, size=100)
+    row = np.repeat(np.arange(lengths.size), lengths).astype(np.int64)
+    _both_ways(te, shape, idx, B=lengths.size, row=row)
+
+
+def test_large_calls_take_the_right_grouped_kernels_by_themselves(ttg_lib):
+    """From 393,216 rows per call on, a call without engine flags runs the right-grouped mma.sync kernels
+    (tt_sorted.cu use_r): bit-identical to the same call with TTG_FLAG_RIGHT, 1e-5 from the left-grouped kernels
+    (TTG_FLAG_MMA_SYNC); below that size it is bit-identical to the left-grouped ones."""
+    import _ttg
+    import tt_embeddings as te
+    shape = SHAPES["products"]
+    p, q, r, n_emb = shape
+    cores = [c.to(DEV) for c in _cores(p, q, r, n_emb, 9)]
+    g = torch.Generator().manual_seed(4)
+    for nnz, same_as in ((393216, _ttg.FLAG_RIGHT), (131072, _ttg.FLAG_MMA_SYNC)):
+        idx = torch.randperm(n_emb, generator=g)[:nnz].to(DEV)
+        row = torch.arange(nnz, device=DEV)
+        tb = torch.zeros_like(idx)
+        dO = ((torch.rand(1, nnz, 100, generator=g) - 0.5) * 0.2).to(DEV)
+        res = {}
+        for fl in (0, _ttg.FLAG_RIGHT, _ttg.FLAG_MMA_SYNC):
+            te.EXTRA_FLAGS = fl
+            try:
+                out = te.tt_forward(1000, 1, nnz, 100, p, q, r, None, nnz, idx, row, tb, cores)
+                gr = te.tt_dense_backward(1000, 100, p, q, r, None, nnz, idx, row, tb, dO, cores)
+            finally:
+                te.EXTRA_FLAGS = 0
+            res[fl] = [out] + [x.clone() for x in gr]
+        other = _ttg.FLAG_MMA_SYNC if same_as == _ttg.FLAG_RIGHT else _ttg.FLAG_RIGHT
+        assert torch.equal(res[0][0], res[same_as][0])      # forward: no atomics on either path
+        assert not torch.equal(res[0][0], res[other][0])
+        for a, b in zip(res[0], res[same_as]):              # gradients: one core per path goes through atomics
+            assert float((a - b).abs().max() / b.abs().max()) < TOL
+        for a, b in zip(res[0], res[other]):
+            assert float((a - b).abs().max() / b.abs().max()) < TOL
