@@ -119,8 +119,11 @@ class TTLookupFunction(torch.autograd.Function):
     def forward(ctx, B, D, tt_p_shapes, tt_q_shapes, tt_ranks, L, nnz_tt, nnz_cached, indices,
                 rowidx, tableidx, optimizer, learning_rate, eps, sparse, cache_locations,
                 cache_optimizer_state, cache_weight, optimizer_state, batch_count, *tt_cores):
+        # the cached entries follow the nnz_tt TT entries (preprocess_indices_sync), or -- unpartitioned lists of
+        # tt_embeddings.cache_mark, nnz_tt == nnz_cached == len(indices) -- both kinds span the whole list
+        c0 = 0 if (nnz_cached > 0 and nnz_tt + nnz_cached > indices.numel()) else int(nnz_tt)
         ctx.cfg = (D, list(tt_p_shapes), list(tt_q_shapes), list(tt_ranks), optimizer,
-                   learning_rate, eps, sparse, int(nnz_tt), int(nnz_cached), batch_count)
+                   learning_rate, eps, sparse, int(nnz_tt), int(nnz_cached), batch_count, c0)
         ctx.tt_cores = tt_cores
         ctx.optimizer_state = optimizer_state
         ctx.save_for_backward(L, indices, rowidx, tableidx, cache_locations,
@@ -129,13 +132,13 @@ class TTLookupFunction(torch.autograd.Function):
                                        tt_q_shapes, tt_ranks, L, nnz_tt, indices, rowidx, tableidx,
                                        list(tt_cores))
         if nnz_cached > 0:
-            tt_embeddings.cache_forward(B, nnz_cached, cache_locations[nnz_tt:], rowidx[nnz_tt:],
+            tt_embeddings.cache_forward(B, nnz_cached, cache_locations[c0:], rowidx[c0:],
                                         cache_weight, out)
         return out
 
     @staticmethod
     def backward(ctx, d_output):
-        (D, p, q, ranks, optimizer, lr, eps, sparse, nnz_tt, nnz_cached, batch_count) = ctx.cfg
+        (D, p, q, ranks, optimizer, lr, eps, sparse, nnz_tt, nnz_cached, batch_count, c0) = ctx.cfg
         (L, indices, rowidx, tableidx, cache_locations, cache_optimizer_state,
          cache_weight) = ctx.saved_tensors
         cores = list(ctx.tt_cores)
@@ -148,7 +151,7 @@ class TTLookupFunction(torch.autograd.Function):
                                               rowidx, tableidx, d_output, cores)
                 if nnz_cached > 0:
                     tt_embeddings.cache_backward_sgd(nnz_cached, d_output,
-                                                     cache_locations[nnz_tt:], rowidx[nnz_tt:], lr,
+                                                     cache_locations[c0:], rowidx[c0:], lr,
                                                      cache_weight)
             else:
                 tt_embeddings.tt_adagrad_backward(batch_count, D, lr, eps, p, q, ranks, L, nnz_tt,
@@ -156,7 +159,7 @@ class TTLookupFunction(torch.autograd.Function):
                                                   ctx.optimizer_state, cores)
                 if nnz_cached > 0:
                     tt_embeddings.cache_backward_rowwise_adagrad_approx(
-                        nnz_cached, d_output, cache_locations[nnz_tt:], rowidx[nnz_tt:], lr, eps,
+                        nnz_cached, d_output, cache_locations[c0:], rowidx[c0:], lr, eps,
                         cache_optimizer_state, cache_weight)
             return tuple(grads + [None] * len(cores))
         # dense gradients for an external optimizer (reference :313-366)
@@ -164,8 +167,8 @@ class TTLookupFunction(torch.autograd.Function):
                                                   rowidx, tableidx, d_output, cores)
         if nnz_cached > 0:
             grads[17] = tt_embeddings.cache_backward_dense(nnz_cached, d_output,
-                                                           cache_locations[nnz_tt:],
-                                                           rowidx[nnz_tt:], lr, cache_weight)
+                                                           cache_locations[c0:],
+                                                           rowidx[c0:], lr, cache_weight)
         return tuple(grads + list(d_cores))
 
 
@@ -329,6 +332,9 @@ class TableBatchedTTEmbeddingBag(nn.Module):
             self.cache_optimizer_state = None
             self.cache_weight = None
         self.warmup = True
+        # the cached / uncached split without a host count (tt_embeddings.cache_mark); False = the reference's
+        # data flow (partitioned lists, one stream synchronisation per forward)
+        self.split_on_device = True
 
     # -- weights ------------------------------------------------------------------------------
     def full_weight(self) -> torch.Tensor:
@@ -480,14 +486,24 @@ class TableBatchedTTEmbeddingBag(nn.Module):
         indices = indices.long().contiguous()
         offsets = offsets.long().contiguous()
         self.update_cache(indices)
-        prepared = None if (self.use_cache and not self.warmup) else self._prepared_for(indices, offsets)
+        cached = self.use_cache and not self.warmup
+        prepared = None if cached else self._prepared_for(indices, offsets)
         if prepared is not None:
             rowidx, tableidx = prepared
             n_tt, cache_locations = indices.numel(), None
+            n_cached = 0
+        elif cached and self.num_tables == 1 and self.split_on_device:
+            # the split stays on the device (tt_embeddings.cache_mark): cached entries become id -1 for the TT
+            # kernels, uncached ones location -1 for the cache kernels, both over the whole list -- no host count,
+            # no stream synchronisation, and the step can be captured in a CUDA graph with the cache on
+            (_, rowidx, tableidx, _, _) = tt_embeddings.preprocess_indices_sync(
+                indices, offsets, self.num_tables, True, self.hashtbl, self.cache_state)
+            indices, cache_locations = tt_embeddings.cache_mark(indices, self.hashtbl, self.cache_state)
+            n_tt = n_cached = indices.numel()
         else:
             (indices, rowidx, tableidx, n_tt, cache_locations) = tt_embeddings.preprocess_indices_sync(
                 indices, offsets, self.num_tables, self.warmup, self.hashtbl, self.cache_state)
-        n_cached = indices.numel() - n_tt
+            n_cached = indices.numel() - n_tt
         return TTLookupFunction.apply(
             (offsets.numel() - 1) // self.num_tables, self.embedding_dim, self.tt_p_shapes,
             self.tt_q_shapes, self.tt_ranks, self.L, n_tt, n_cached, indices, rowidx, tableidx,

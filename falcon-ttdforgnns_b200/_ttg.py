@@ -61,6 +61,7 @@ SIGNATURES = {
     "ttg_preprocess_workspace_bytes": (_sz, [_i64]),
     "ttg_preprocess_indices": (C.c_int, [_i64, _i64, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _vp, _vp,
                                          _vp, _vp, _vp, C.POINTER(C.c_int32), _vp, _sz, _vp]),
+    "ttg_cache_mark": (C.c_int, [_i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ttg_cache_forward": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "ttg_cache_backward_sgd": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _f32, _vp, _vp]),
     "ttg_cache_backward_dense": (C.c_int, [_i64, _i32, _vp, _vp, _vp, _vp, _vp]),

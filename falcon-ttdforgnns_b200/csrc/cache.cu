@@ -166,6 +166,22 @@ lookup_count_kernel(int64_t nnz, const int64_t* __restrict__ colidx, int32_t siz
   }
 }
 
+// The split without moving anything (and without a count for the host): the index itself where the TT cores
+// serve the entry and -1 (an id every TT kernel skips) where the cache does, plus the cache location or -1.
+__global__ void __launch_bounds__(256)
+cache_mark_kernel(int64_t nnz, const int64_t* __restrict__ colidx, int32_t size, const int64_t* __restrict__ keys,
+                  const int32_t* __restrict__ cache_state, int64_t* __restrict__ tt_colidx,
+                  int32_t* __restrict__ cache_loc) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nnz) return;
+  const int64_t idx = __ldg(colidx + n);
+  const int32_t s = table_find(idx, size, keys);
+  int32_t loc = -1;
+  if (s != -1) loc = __ldg(cache_state + s);
+  tt_colidx[n] = (loc == -1) ? idx : -1;
+  cache_loc[n] = loc;
+}
+
 // exclusive scan of the tile counts (single CTA), total -> *num_tt
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int32_t ntiles, int32_t* __restrict__ tile_counts, int32_t* __restrict__ num_tt) {
@@ -267,6 +283,13 @@ __device__ __forceinline__ bool segment_of(int64_t n, int64_t nnz,
   return true;
 }
 
+// does any entry of the segment have a cache row?  (unpartitioned lists carry -1 for entries the TT cores serve)
+__device__ __forceinline__ bool any_cached(const int32_t* __restrict__ loc, int32_t sl) {
+  for (int s = 0; s < sl; ++s)
+    if (__ldg(loc + s) >= 0) return true;
+  return false;
+}
+
 // FBTT/tt_embeddings_cuda.cu:1509-1549
 __global__ void __launch_bounds__(256)
 cache_fwd_kernel(int64_t nnz, int32_t D, const int64_t* __restrict__ rowidx,
@@ -278,10 +301,12 @@ cache_fwd_kernel(int64_t nnz, int32_t D, const int64_t* __restrict__ rowidx,
   int64_t row;
   int32_t sl;
   if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
+  if (!any_cached(loc + n, sl)) return;     // nothing of this bag is cached: its output row stays untouched
   for (int d = lane * 4; d < D; d += 128) {
     float4 acc = *reinterpret_cast<const float4*>(output + row * D + d);
     for (int s = 0; s < sl; ++s) {
       const int64_t c = __ldg(loc + n + s);
+      if (c < 0) continue;      // unpartitioned lists (ttg_cache_mark): an entry served by the TT cores
       const float4 w = ldg4(weight + c * D + d);
       acc.x += w.x;
       acc.y += w.y;
@@ -306,6 +331,7 @@ cache_bwd_kernel(int64_t nnz, int32_t D, const float* __restrict__ grad_output,
   if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
   for (int s = 0; s < sl; ++s) {
     const int64_t c = __ldg(loc + n + s);
+    if (c < 0) continue;
     for (int d = lane * 4; d < D; d += 128) {
       float4 g = ldg4(grad_output + row * D + d);
       if (mode == 0) {
@@ -331,6 +357,7 @@ cache_bwd_rowwise_adagrad_kernel(int64_t nnz, int32_t D, const float* __restrict
   int64_t row;
   int32_t sl;
   if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
+  if (!any_cached(loc + n, sl)) return;
   float sq = 0.f;
   for (int d = lane * 4; d < D; d += 128) {
     const float4 g = ldg4(grad_output + row * D + d);
@@ -341,6 +368,7 @@ cache_bwd_rowwise_adagrad_kernel(int64_t nnz, int32_t D, const float* __restrict
   const float g_avg = sq / D;
   for (int s = 0; s < sl; ++s) {
     const int64_t c = __ldg(loc + n + s);
+    if (c < 0) continue;
     float mult = 0.f;
     if (lane == 0) {
       const float old = atomicAdd(state + c, g_avg);
@@ -521,6 +549,19 @@ extern "C" int ttg_preprocess_indices(int64_t nnz, int64_t num_offsets, const in
   // the op's contract is a host integer (:1492-1499)
   TTG_CUDA(cudaMemcpyAsync(host_nnz_tt, num_tt, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   TTG_CUDA(cudaStreamSynchronize(stream));
+  return TTG_OK;
+}
+
+extern "C" int ttg_cache_mark(int64_t nnz, const int64_t* colidx, int64_t hashtbl_size, const int64_t* hashtbl,
+                              const int32_t* cache_state, int64_t* tt_colidx, int32_t* cache_loc,
+                              void* stream) {
+  if (nnz == 0) return TTG_OK;
+  TTG_CHECK_ARG(colidx && hashtbl && cache_state && tt_colidx && cache_loc, "cache_mark: null pointer");
+  TTG_CHECK_ARG(hashtbl_size > 0 && hashtbl_size < INT32_MAX, "cache_mark: hashtbl_size=%lld",
+                (long long)hashtbl_size);
+  cache_mark_kernel<<<(unsigned)ceil_div(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
+      nnz, colidx, (int32_t)hashtbl_size, hashtbl, cache_state, tt_colidx, cache_loc);
+  TTG_LAUNCH_CHECK();
   return TTG_OK;
 }
 

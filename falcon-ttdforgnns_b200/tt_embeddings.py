@@ -363,6 +363,25 @@ def preprocess_indices_sync(colidx: torch.Tensor, offsets: torch.Tensor, num_tab
     return part_col, part_row, tableidx, int(n_tt.value), part_loc
 
 
+def cache_mark(colidx: torch.Tensor, hashtbl: torch.Tensor, cache_state: torch.Tensor
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(tt_colidx, cache_locations) of ttg_cache_mark: the cached / uncached split in place -- cached entries
+    become id -1 for the TT ops, uncached ones location -1 for the cache ops -- with no host count, hence no
+    stream synchronisation (not an op of the reference: its split is preprocess_indices_sync above)."""
+    _ttg.require_cuda(colidx, "colidx", torch.int64)
+    _ttg.require_cuda(hashtbl, "hashtbl", torch.int64)
+    _ttg.require_cuda(cache_state, "cache_state", torch.int32)
+    dev = colidx.device
+    with _ttg.on_device(dev):
+        tt_col = torch.empty_like(colidx)
+        loc = torch.empty(colidx.numel(), dtype=torch.int32, device=dev)
+        rc = _ttg.lib().ttg_cache_mark(colidx.numel(), _ttg.ptr(colidx), hashtbl.numel(), _ttg.ptr(hashtbl),
+                                       _ttg.ptr(cache_state), _ttg.ptr(tt_col), _ttg.ptr(loc),
+                                       _ttg.stream_of(dev))
+        _ttg.check(rc, "cache_mark")
+    return tt_col, loc
+
+
 def _cache_args(nnz, grad_or_out, cache_locations, rowidx, cache_weight):
     _ttg.require_cuda(cache_locations, "cache_locations", torch.int32)
     _ttg.require_cuda(rowidx, "rowidx", torch.int64)

@@ -238,8 +238,18 @@ int ttg_preprocess_indices(int64_t nnz, int64_t num_offsets, const int64_t* coli
                            int32_t* part_cache_loc, int32_t* host_nnz_tt, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* The cached / uncached split of preprocess_indices_sync_cuda (FBTT/tt_embeddings_cuda.cu:1388-1507: lookup
+ * :1367-1386, partition :1440-1490) without the partition and without the host count it returns: tt_colidx[n] =
+ * colidx[n] where the TT cores serve the entry, -1 (an id every TT kernel skips) where the cache does;
+ * cache_loc[n] = the cache row or -1.  The TT ops then run on (tt_colidx, rowidx) and the cache ops on
+ * (cache_loc, rowidx), both over all nnz entries: no stream synchronisation, so the module step can be
+ * captured in a CUDA graph with the cache on.  The pybind-compatible op keeps its partition and its int. */
+int ttg_cache_mark(int64_t nnz, const int64_t* colidx, int64_t hashtbl_size, const int64_t* hashtbl,
+                   const int32_t* cache_state, int64_t* tt_colidx, int32_t* cache_loc, void* stream);
+
 /* replaces: cache_forward_cuda FBTT/tt_embeddings_cuda.cu:1509-1583
- * output[rowidx[n]][:] += cache_weight[cache_locations[n]][:]  (accumulates) */
+ * output[rowidx[n]][:] += cache_weight[cache_locations[n]][:]  (accumulates; entries with a negative location
+ * are skipped, here and in the cache backward ops) */
 int ttg_cache_forward(int64_t nnz, int32_t D, const int32_t* cache_locations,
                       const int64_t* rowidx, const float* cache_weight, float* output,
                       void* stream);

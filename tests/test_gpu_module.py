@@ -314,3 +314,78 @@ def test_gcn_stack_wiring(ttg_lib):
         assert out.shape == (n, 5) and m.convs[2].bias is not None and m.convs[0].bias is None
         out.sum().backward()
         assert x.grad is not None and float(x.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_device_side_cache_split_equals_the_partitioned_flow(ttg_lib, sparse):
+    """The module's split without a host count (tt_embeddings.cache_mark: cached entries become id -1 for the TT
+    kernels, uncached ones location -1 for the cache kernels) against the reference's data flow (partitioned
+    lists, preprocess_indices_sync): same output, same gradients / same fused updates, bags partly cached."""
+    n_emb, D, ranks, p, q = 5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]
+    rng = np.random.default_rng(9)
+    hot = torch.from_numpy(rng.choice(n_emb, size=15, replace=False)).to(DEV)
+    lengths = rng.integers(0, 5, size=60)
+    idx = torch.from_numpy(np.concatenate([hot.cpu().numpy(), rng.integers(0, n_emb, size=int(lengths.sum()) - 15)])).to(DEV)
+    idx = idx[torch.randperm(idx.numel(), generator=torch.Generator().manual_seed(1)).to(DEV)]
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(lengths)])).to(DEV)
+    res = []
+    for on_device in (True, False):
+        m = _make(n_emb, D, ranks, p, q, sparse=sparse, use_cache=True, cache_size=20, hashtbl_size=4001,
+                  learning_rate=0.1)
+        m.split_on_device = on_device
+        for _ in range(3):
+            w = torch.cat([hot, torch.from_numpy(rng.integers(0, n_emb, size=30)).to(DEV)])
+            m(w, torch.arange(w.numel() + 1, device=DEV))
+        m.cache_populate()
+        out = m(idx, off)
+        g = torch.Generator().manual_seed(2)
+        out.backward((torch.rand(out.shape, generator=g) * 0.1).to(DEV))
+        torch.cuda.synchronize()
+        rec = [out.detach().clone()]
+        if sparse:
+            rec += [c.detach().clone() for c in m.tt_cores] + [m.cache_weight.detach().clone()]
+        else:
+            rec += [c.grad.clone() for c in m.tt_cores] + [m.cache_weight.grad.clone()]
+        res.append(rec)
+        rng = np.random.default_rng(9)       # the same warm-up stream for the second module
+        rng.choice(n_emb, size=15, replace=False)
+        rng.integers(0, 5, size=60)
+        rng.integers(0, n_emb, size=int(lengths.sum()) - 15)
+    assert float(res[0][-1].abs().sum()) > 0
+    for a, b in zip(res[0], res[1]):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def test_cached_module_step_is_capturable(ttg_lib):
+    """With the split on the device nothing in forward + backward synchronises the stream: the cached module's
+    step runs as a CUDA graph and replays to the eager result."""
+    n_emb, D, ranks, p, q = 5 * 6 * 7, 100, [16, 16], [5, 6, 7], [4, 5, 5]
+    rng = np.random.default_rng(11)
+    hot = torch.from_numpy(rng.choice(n_emb, size=15, replace=False)).to(DEV)
+    m = _make(n_emb, D, ranks, p, q, sparse=False, use_cache=True, cache_size=20, hashtbl_size=4001)
+    for _ in range(3):
+        w = torch.cat([hot, torch.from_numpy(rng.integers(0, n_emb, size=30)).to(DEV)])
+        m(w, torch.arange(w.numel() + 1, device=DEV))
+    m.cache_populate()
+    idx = torch.cat([hot[:8], torch.from_numpy(rng.integers(0, n_emb, size=40)).to(DEV)])
+    off = torch.arange(idx.numel() + 1, device=DEV)
+    eager = m(idx, off).detach().clone()
+    torch.cuda.synchronize()
+    static_out = torch.empty_like(eager)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            static_out.copy_(m(idx, off).detach())
+    torch.cuda.current_stream().wait_stream(s)
+    static_out.zero_()
+    gr.replay()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(static_out, eager, rtol=1e-6, atol=1e-7)
+    m.split_on_device = False
+    with pytest.raises(RuntimeError):
+        with torch.cuda.stream(s):
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, stream=s):
+                m(idx, off)
