@@ -270,51 +270,63 @@ partition_scatter_kernel(int64_t nnz, const uint8_t* __restrict__ is_tt,
   }
 }
 
-// ---- cached rows: one warp per index, the warp at a segment start owns the segment ------
-__device__ __forceinline__ bool segment_of(int64_t n, int64_t nnz,
-                                           const int64_t* __restrict__ rowidx, int64_t* row,
-                                           int32_t* len) {
-  const int64_t r = __ldg(rowidx + n);
-  if (n != 0 && __ldg(rowidx + n - 1) == r) return false;
-  int32_t sl = 1;
-  while (n + sl < nnz && __ldg(rowidx + n + sl) == r) ++sl;
-  *row = r;
-  *len = sl;
-  return true;
+// ---- cached rows: a warp looks at 32 consecutive entries; the lane at the start of a segment (the entries of
+// one bag) that holds at least one cached entry hands the segment to the whole warp.  Lists that are mostly
+// uncached (the unpartitioned lists of ttg_cache_mark carry location -1 for entries the TT cores serve) cost a
+// 4-byte load per entry; the work per cached segment, and its summation order, are those of a warp per entry.
+struct Segment {
+  int64_t n, row;
+  int32_t len;
+};
+template <typename Body>
+__device__ __forceinline__ void for_each_cached_segment(int64_t nnz, const int64_t* __restrict__ rowidx,
+                                                         const int32_t* __restrict__ loc, Body body) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32 + lane;
+  int64_t row = 0;
+  int32_t sl = 0;
+  bool mine = false;
+  if (n < nnz) {
+    row = __ldg(rowidx + n);
+    if (n == 0 || __ldg(rowidx + n - 1) != row) {
+      sl = 1;
+      while (n + sl < nnz && __ldg(rowidx + n + sl) == row) ++sl;
+      for (int s = 0; s < sl && !mine; ++s) mine = __ldg(loc + n + s) >= 0;
+    }
+  }
+  uint32_t m = __ballot_sync(0xffffffffu, mine);
+  while (m) {
+    const int src = __ffs(m) - 1;
+    m &= m - 1;
+    Segment sg;
+    sg.n = __shfl_sync(0xffffffffu, n, src);
+    sg.row = __shfl_sync(0xffffffffu, row, src);
+    sg.len = __shfl_sync(0xffffffffu, sl, src);
+    body(sg, lane);
+  }
 }
-
-// does any entry of the segment have a cache row?  (unpartitioned lists carry -1 for entries the TT cores serve)
-__device__ __forceinline__ bool any_cached(const int32_t* __restrict__ loc, int32_t sl) {
-  for (int s = 0; s < sl; ++s)
-    if (__ldg(loc + s) >= 0) return true;
-  return false;
-}
+constexpr int kCacheEntriesPerCta = 256;      // 8 warps x 32 entries
 
 // FBTT/tt_embeddings_cuda.cu:1509-1549
 __global__ void __launch_bounds__(256)
 cache_fwd_kernel(int64_t nnz, int32_t D, const int64_t* __restrict__ rowidx,
                  const int32_t* __restrict__ loc, const float* __restrict__ weight,
                  float* __restrict__ output) {
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= nnz) return;
-  int64_t row;
-  int32_t sl;
-  if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
-  if (!any_cached(loc + n, sl)) return;     // nothing of this bag is cached: its output row stays untouched
-  for (int d = lane * 4; d < D; d += 128) {
-    float4 acc = *reinterpret_cast<const float4*>(output + row * D + d);
-    for (int s = 0; s < sl; ++s) {
-      const int64_t c = __ldg(loc + n + s);
-      if (c < 0) continue;      // unpartitioned lists (ttg_cache_mark): an entry served by the TT cores
-      const float4 w = ldg4(weight + c * D + d);
-      acc.x += w.x;
-      acc.y += w.y;
-      acc.z += w.z;
-      acc.w += w.w;
+  for_each_cached_segment(nnz, rowidx, loc, [&](const Segment& sg, int lane) {
+    for (int d = lane * 4; d < D; d += 128) {
+      float4 acc = *reinterpret_cast<const float4*>(output + sg.row * D + d);
+      for (int s = 0; s < sg.len; ++s) {
+        const int64_t c = __ldg(loc + sg.n + s);
+        if (c < 0) continue;      // an entry served by the TT cores
+        const float4 w = ldg4(weight + c * D + d);
+        acc.x += w.x;
+        acc.y += w.y;
+        acc.z += w.z;
+        acc.w += w.w;
+      }
+      *reinterpret_cast<float4*>(output + sg.row * D + d) = acc;
     }
-    *reinterpret_cast<float4*>(output + row * D + d) = acc;
-  }
+  });
 }
 
 // mode 0: weight[loc] += -lr * g (FBTT/tt_embeddings_cuda.cu:1585-1632)
@@ -323,26 +335,22 @@ __global__ void __launch_bounds__(256)
 cache_bwd_kernel(int64_t nnz, int32_t D, const float* __restrict__ grad_output,
                  const int32_t* __restrict__ loc, const int64_t* __restrict__ rowidx, float lr,
                  int mode, float* __restrict__ dst) {
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= nnz) return;
-  int64_t row;
-  int32_t sl;
-  if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
-  for (int s = 0; s < sl; ++s) {
-    const int64_t c = __ldg(loc + n + s);
-    if (c < 0) continue;
-    for (int d = lane * 4; d < D; d += 128) {
-      float4 g = ldg4(grad_output + row * D + d);
-      if (mode == 0) {
-        g.x = -g.x * lr;
-        g.y = -g.y * lr;
-        g.z = -g.z * lr;
-        g.w = -g.w * lr;
+  for_each_cached_segment(nnz, rowidx, loc, [&](const Segment& sg, int lane) {
+    for (int s = 0; s < sg.len; ++s) {
+      const int64_t c = __ldg(loc + sg.n + s);
+      if (c < 0) continue;
+      for (int d = lane * 4; d < D; d += 128) {
+        float4 g = ldg4(grad_output + sg.row * D + d);
+        if (mode == 0) {
+          g.x = -g.x * lr;
+          g.y = -g.y * lr;
+          g.z = -g.z * lr;
+          g.w = -g.w * lr;
+        }
+        red_add_v4(dst + c * D + d, g);
       }
-      red_add_v4(dst + c * D + d, g);
     }
-  }
+  });
 }
 
 // FBTT/tt_embeddings_cuda.cu:1746-1806
@@ -351,40 +359,35 @@ cache_bwd_rowwise_adagrad_kernel(int64_t nnz, int32_t D, const float* __restrict
                                  const int32_t* __restrict__ loc,
                                  const int64_t* __restrict__ rowidx, float lr, float eps,
                                  float* __restrict__ state, float* __restrict__ weight) {
-  const int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (n >= nnz) return;
-  int64_t row;
-  int32_t sl;
-  if (!segment_of(n, nnz, rowidx, &row, &sl)) return;
-  if (!any_cached(loc + n, sl)) return;
-  float sq = 0.f;
-  for (int d = lane * 4; d < D; d += 128) {
-    const float4 g = ldg4(grad_output + row * D + d);
-    sq += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float g_avg = sq / D;
-  for (int s = 0; s < sl; ++s) {
-    const int64_t c = __ldg(loc + n + s);
-    if (c < 0) continue;
-    float mult = 0.f;
-    if (lane == 0) {
-      const float old = atomicAdd(state + c, g_avg);
-      mult = lr * (1.0f / (sqrtf(old + g_avg) + eps));
-    }
-    mult = __shfl_sync(0xffffffffu, mult, 0);
+  for_each_cached_segment(nnz, rowidx, loc, [&](const Segment& sg, int lane) {
+    float sq = 0.f;
     for (int d = lane * 4; d < D; d += 128) {
-      const float4 g = ldg4(grad_output + row * D + d);
-      float4 w = *reinterpret_cast<const float4*>(weight + c * D + d);
-      w.x -= g.x * mult;
-      w.y -= g.y * mult;
-      w.z -= g.z * mult;
-      w.w -= g.w * mult;
-      *reinterpret_cast<float4*>(weight + c * D + d) = w;
+      const float4 g = ldg4(grad_output + sg.row * D + d);
+      sq += g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w;
     }
-  }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float g_avg = sq / D;
+    for (int s = 0; s < sg.len; ++s) {
+      const int64_t c = __ldg(loc + sg.n + s);
+      if (c < 0) continue;
+      float mult = 0.f;
+      if (lane == 0) {
+        const float old = atomicAdd(state + c, g_avg);
+        mult = lr * (1.0f / (sqrtf(old + g_avg) + eps));
+      }
+      mult = __shfl_sync(0xffffffffu, mult, 0);
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 g = ldg4(grad_output + sg.row * D + d);
+        float4 w = *reinterpret_cast<const float4*>(weight + c * D + d);
+        w.x -= g.x * mult;
+        w.y -= g.y * mult;
+        w.z -= g.z * mult;
+        w.w -= g.w * mult;
+        *reinterpret_cast<float4*>(weight + c * D + d) = w;
+      }
+    }
+  });
 }
 
 struct PopulateWs {
@@ -571,7 +574,7 @@ extern "C" int ttg_cache_forward(int64_t nnz, int32_t D, const int32_t* cache_lo
   TTG_CHECK_ARG(D > 0 && D % 4 == 0, "cache_forward: D=%d must be a positive multiple of 4", D);
   if (nnz == 0) return TTG_OK;
   TTG_CHECK_ARG(cache_locations && rowidx && cache_weight && output, "cache_forward: null pointer");
-  cache_fwd_kernel<<<(unsigned)ceil_div(nnz * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  cache_fwd_kernel<<<(unsigned)ceil_div(nnz, kCacheEntriesPerCta), 256, 0, (cudaStream_t)stream>>>(
       nnz, D, rowidx, cache_locations, cache_weight, output);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -584,7 +587,7 @@ extern "C" int ttg_cache_backward_sgd(int64_t nnz, int32_t D, const float* grad_
   if (nnz == 0) return TTG_OK;
   TTG_CHECK_ARG(grad_output && cache_locations && rowidx && cache_weight,
                 "cache_backward_sgd: null pointer");
-  cache_bwd_kernel<<<(unsigned)ceil_div(nnz * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  cache_bwd_kernel<<<(unsigned)ceil_div(nnz, kCacheEntriesPerCta), 256, 0, (cudaStream_t)stream>>>(
       nnz, D, grad_output, cache_locations, rowidx, lr, 0, cache_weight);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -598,7 +601,7 @@ extern "C" int ttg_cache_backward_dense(int64_t nnz, int32_t D, const float* gra
   if (nnz == 0) return TTG_OK;
   TTG_CHECK_ARG(grad_output && cache_locations && rowidx && grad_cache_weight,
                 "cache_backward_dense: null pointer");
-  cache_bwd_kernel<<<(unsigned)ceil_div(nnz * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+  cache_bwd_kernel<<<(unsigned)ceil_div(nnz, kCacheEntriesPerCta), 256, 0, (cudaStream_t)stream>>>(
       nnz, D, grad_output, cache_locations, rowidx, 0.f, 1, grad_cache_weight);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
@@ -612,7 +615,7 @@ extern "C" int ttg_cache_backward_rowwise_adagrad_approx(
   if (nnz == 0) return TTG_OK;
   TTG_CHECK_ARG(grad_output && cache_locations && rowidx && cache_optimizer_state && cache_weight,
                 "cache_backward_rowwise_adagrad_approx: null pointer");
-  cache_bwd_rowwise_adagrad_kernel<<<(unsigned)ceil_div(nnz * 32, 256), 256, 0,
+  cache_bwd_rowwise_adagrad_kernel<<<(unsigned)ceil_div(nnz, kCacheEntriesPerCta), 256, 0,
                                      (cudaStream_t)stream>>>(
       nnz, D, grad_output, cache_locations, rowidx, lr, eps, cache_optimizer_state, cache_weight);
   TTG_LAUNCH_CHECK();

@@ -470,15 +470,18 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
   // warp's registers and stored once).  A CTA owns the nominal rows [blockIdx.x rpc, (blockIdx.x + 1) rpc): the
   // first part is split evenly over its warps, the rest (none by default, see the launcher) is a pool of small
   // chunks the warps take as they run out of work.
-  const int cta0 = min((int)blockIdx.x * a.rpc, a.nnz), cta1 = min(cta0 + a.rpc, a.nnz);
-  const int pool0 = min(cta0 + kBW * a.rpw, cta1);
+  // The split is laid out for the nnz rows the plan was built from; if fewer are valid (ids out of range, or the
+  // -1 a cached module puts where its cache serves the entry), the first run notices and the split is redone for
+  // the rows there are, so that no warp stays idle.
+  int rows = a.nnz, rpc = a.rpc, rpw = a.rpw;
+  int cta0 = min((int)blockIdx.x * rpc, rows), cta1 = min(cta0 + rpc, rows);
+  int pool0 = min(cta0 + kBW * rpw, cta1);
   float* ring = rings + warp * kRingFloats;
   for (int item = -1;; ) {
   int x1, x2;
   if (item < 0) {
-    x1 = min(cta0 + warp * a.rpw, pool0);
-    x2 = min(x1 + a.rpw, pool0);
-    item = 0;
+    x1 = min(cta0 + warp * rpw, pool0);
+    x2 = min(x1 + rpw, pool0);
   } else {
     int j = 0;
     if (lane == 0) j = atomicAdd(&pool_next, 1);
@@ -525,7 +528,19 @@ __global__ void __launch_bounds__(kBT, 1) rm_bwd_kernel(RmArgs a) {
     rs = boundary(x1, gc);
     re = boundary(x2, fdiv(ke, a.div_p0));      // x2 at or beyond the row count: the row count
   }
-  (void)total;
+  if (item < 0) {
+    item = 0;
+    if (total != rows) {       // fewer valid rows than planned for: lay the split out again (once)
+      rows = total;
+      rpc = (rows + (int)gridDim.x - 1) / (int)gridDim.x;
+      rpw = (int)((long long)rpc * a.rpw / max(a.rpc, 1));
+      cta0 = min((int)blockIdx.x * rpc, rows);
+      cta1 = min(cta0 + rpc, rows);
+      pool0 = min(cta0 + kBW * rpw, cta1);
+      item = -1;
+      continue;
+    }
+  }
   uint32_t bgh[4][2][2], bgl[4][2][2];
   if (rs < re) {
     if (rs - cb >= 32) {     // rare: the boundary lies beyond the first window

@@ -202,15 +202,23 @@ plan_kernel(int64_t nnz, int64_t B, int64_t num_rows, int32_t num_tables, uint32
 #pragma unroll
   for (int k = 0; k < kPlanItems; ++k) {
     const int64_t n = n0 + k * 256;
-    if (n >= nnz) continue;
-    const bool ok = idx[k] >= 0 && idx[k] < num_rows && t[k] >= 0 && t[k] < num_tables &&
+    const bool in = n < nnz;
+    const bool ok = in && idx[k] >= 0 && idx[k] < num_rows && t[k] >= 0 && t[k] < num_tables &&
                     row[k] >= 0 && row[k] < B;
     const int64_t local = hp ? (idx[k] % hp) * tp0 + idx[k] / hp : idx[k];
     const uint32_t key = ok ? (uint32_t)(t[k] * num_rows + local) : total_rows;  // invalid -> end
     const int32_t gr = ok ? (int32_t)(t[k] * B + row[k]) : 0;
+    // invalid entries share one bucket: one atomic per warp instead of one per entry (a cached module hands
+    // the TT ops a list with -1 for every cached entry; 120 k additions to one counter cost 120 us)
+    const uint32_t bad = __ballot_sync(0xffffffffu, in && !ok);
+    int32_t bad_base = 0;
+    const int lane = threadIdx.x & 31;
+    if (bad != 0 && lane == __ffs(bad) - 1) bad_base = atomicAdd(cnt + num_groups, __popc(bad));
+    bad_base = __shfl_sync(0xffffffffu, bad_base, bad ? __ffs(bad) - 1 : 0);
+    if (!in) continue;
     keys[n] = key;
     vals[n] = gr;
-    ranks[n] = atomicAdd(cnt + (ok ? key / p2 : num_groups), 1);
+    ranks[n] = ok ? atomicAdd(cnt + key / p2, 1) : bad_base + __popc(bad & ((1u << lane) - 1));
     if (ok && rowcount) atomicAdd(rowcount + gr, 1);
   }
 }
