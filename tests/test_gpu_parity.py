@@ -704,8 +704,10 @@ def test_plan_is_rebuilt_after_a_raw_pointer_core_update(ttg_lib):
         assert rel_err(d2[t].cpu().numpy(), want[t]) < TOL, "core %d: stale group table" % t
 
 
-def test_plan_built_ahead_on_another_stream(ttg_lib):
-    """ttg_tt_plan: the index plan of the next batch built on a side stream into the other plan slot while the
+@pytest.mark.parametrize("nnz", [50000, 400000], ids=["left_grouped", "right_grouped"])
+def test_plan_built_ahead_on_another_stream(ttg_lib, nnz):
+    """(at 400,000 rows per call the right-grouped kernels run and the plan is sorted by their transposed keys)
+    ttg_tt_plan: the index plan of the next batch built on a side stream into the other plan slot while the
     current batch runs; the forward / backward that follow recognise it (same tensors) and give bit-identical
     results to the calls that plan for themselves.  A batch of another size is refused (the workspace layout
     depends on nnz) and then simply plans for itself."""
@@ -715,7 +717,6 @@ def test_plan_built_ahead_on_another_stream(ttg_lib):
     D = 100
     cores = [c.to(DEV) for c in _random_cores(p, q, r, n_emb, 41)]
     g = torch.Generator().manual_seed(3)
-    nnz = 50000
     batches = [torch.randint(0, n_emb, (nnz,), generator=g).to(DEV) for _ in range(3)]
     dOs = [(torch.rand(1, nnz, D, generator=g) * 0.1).to(DEV) for _ in range(3)]
     row = torch.arange(nnz, device=DEV)
@@ -747,7 +748,10 @@ def test_plan_built_ahead_on_another_stream(ttg_lib):
     assert not te.tt_plan(1, 30000, p, q, r, 30000, small, row[:30000].contiguous(), tb[:30000].contiguous(), 1)
     o = te.tt_forward(1000, 1, 30000, D, p, q, r, None, 30000, small, row[:30000].contiguous(),
                       tb[:30000].contiguous(), cores)
-    assert torch.equal(o[0], want[0][0][0, :30000])
+    if nnz < 393216:
+        assert torch.equal(o[0], want[0][0][0, :30000])
+    else:     # 30,000 rows run on the left-grouped kernels, the 400,000 of `want` on the right-grouped ones
+        assert float((o[0] - want[0][0][0, :30000]).abs().max() / want[0][0].abs().max()) < TOL
 
 
 def test_module_prepare_matches_plain_forward(ttg_lib):
