@@ -1587,15 +1587,17 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
 // in groups
 // Which right-grouped kernels run this call: 0 none (left-grouped path), 1 the mma.sync ones (tt_rmma.cu), 2 the
 // tcgen05 ones (tt_tc5.cu, on request only).  Without a request the mma.sync ones take over from
-// kRightAutoRows rows per call on: their row kernels cost less per row and more per call (tr1 table, cores kernel;
-// profiles/r2c_right_mma.md).
-constexpr int64_t kRightAutoRows = 393216;
+// kRightAutoRowsPerGroup rows per (i1, i2) group and call on: their row kernels cost less per row, their table and
+// cores kernels more per group (profiles/r2c_right_mma.md: level at 13.4 rows per group at products shape,
+// 274,400 rows; 4 to 10 % faster at arxiv shape from 13 rows per group on).
+constexpr int64_t kRightAutoRowsPerGroup = 14;
 int use_r(const TTDev& tt, const SortedWs& w, int32_t flags, int64_t nnz) {
   if (w.tabR == nullptr || (flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC | TTG_FLAG_FORCE_GENERIC))) return 0;
   if (flags & TTG_FLAG_TCGEN05) return 2;
   if (!rm_supported(tt)) return 0;
   if (flags & TTG_FLAG_RIGHT) return 1;
-  return (!(flags & TTG_FLAG_DETERMINISTIC) && nnz >= kRightAutoRows) ? 1 : 0;
+  const int64_t groups = (int64_t)tt.num_tables * tt.p[1] * tt.p[2];
+  return (!(flags & TTG_FLAG_DETERMINISTIC) && nnz >= kRightAutoRowsPerGroup * groups) ? 1 : 0;
 }
 
 RPlan r_plan(const SortedWs& w) {

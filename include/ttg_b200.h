@@ -70,8 +70,9 @@ enum {
                                  for callers that run ttg_tt_plan, a sampler or copies beside a step */
   TTG_FLAG_RIGHT = 1024,      /* the right-grouped mma.sync kernels (csrc/tt_rmma.cu; q0 = 4, ranks 16,16, batch
                                  dense in (i1, i2) groups): groups (i1, i2), tr1 = core1 core2 from a table.
-                                 Without this flag they are used from 393,216 rows per call on (cheaper per
-                                 row, dearer per call); TTG_FLAG_MMA_SYNC keeps the
+                                 Without this flag they are used from 14 rows per (i1, i2) group and call on
+                                 (274,400 rows at products shape: cheaper per row, dearer per group;
+                                 DESIGN.md section 4c); TTG_FLAG_MMA_SYNC keeps the
                                  left-grouped kernels at any size */
   TTG_FLAG_TCGEN05 = 64       /* the tcgen05 / tensor-memory kernels (csrc/tt_tc5.cu; q0 = 4, ranks
                                  16,16, batch dense in (i1, i2) groups): same results, measured

@@ -339,7 +339,7 @@ def test_invalid_indices_and_bags_backward(te):
 
 
 def test_large_calls_take_the_right_grouped_kernels_by_themselves(ttg_lib):
-    """From 393,216 rows per call on, a call without engine flags runs the right-grouped mma.sync kernels
+    """From 14 rows per (i1, i2) group and call on (274,400 rows at products shape), a call without engine flags runs the right-grouped mma.sync kernels
     (tt_sorted.cu use_r): bit-identical to the same call with TTG_FLAG_RIGHT, 1e-5 from the left-grouped kernels
     (TTG_FLAG_MMA_SYNC); below that size it is bit-identical to the left-grouped ones."""
     import _ttg
