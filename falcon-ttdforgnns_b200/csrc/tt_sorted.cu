@@ -1589,15 +1589,17 @@ int table_then_plan(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indi
 // tcgen05 ones (tt_tc5.cu, on request only).  Without a request the mma.sync ones take over from
 // kRightAutoRowsPerGroup rows per (i1, i2) group and call on: their row kernels cost less per row, their table and
 // cores kernels more per group (profiles/r2c_right_mma.md: level at 13.4 rows per group at products shape,
-// 274,400 rows; 4 to 10 % faster at arxiv shape from 13 rows per group on).
-constexpr int64_t kRightAutoRowsPerGroup = 14;
+// 274,400 rows; with a few thousand groups or fewer -- arxiv 3,080, cora 196 -- 4 to 10 % faster from 13 rows per
+// group on, the table and cores kernels being nearly free there).
+constexpr int64_t kRightAutoRowsPerGroup = 14, kRightAutoRowsPerGroupSmall = 12, kRightSmallGroups = 8192;
 int use_r(const TTDev& tt, const SortedWs& w, int32_t flags, int64_t nnz) {
   if (w.tabR == nullptr || (flags & (TTG_FLAG_FFMA | TTG_FLAG_MMA_SYNC | TTG_FLAG_FORCE_GENERIC))) return 0;
   if (flags & TTG_FLAG_TCGEN05) return 2;
   if (!rm_supported(tt)) return 0;
   if (flags & TTG_FLAG_RIGHT) return 1;
   const int64_t groups = (int64_t)tt.num_tables * tt.p[1] * tt.p[2];
-  return (!(flags & TTG_FLAG_DETERMINISTIC) && nnz >= kRightAutoRowsPerGroup * groups) ? 1 : 0;
+  const int64_t per_group = groups >= kRightSmallGroups ? kRightAutoRowsPerGroup : kRightAutoRowsPerGroupSmall;
+  return (!(flags & TTG_FLAG_DETERMINISTIC) && nnz >= per_group * groups) ? 1 : 0;
 }
 
 RPlan r_plan(const SortedWs& w) {
