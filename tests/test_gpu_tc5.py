@@ -369,3 +369,27 @@ def test_large_calls_take_the_right_grouped_kernels_by_themselves(ttg_lib):
             assert float((a - b).abs().max() / b.abs().max()) < TOL
         for a, b in zip(res[0], res[other]):
             assert float((a - b).abs().max() / b.abs().max()) < TOL
+
+
+def test_right_grouped_kernels_on_the_deterministic_plan(te):
+    """TTG_FLAG_DETERMINISTIC (radix-sorted plan, fixed order inside a group) together with the right-grouped
+    engines: same results at 1e-5, and the forward twice bit-identical."""
+    import _ttg
+    shape = SHAPES["arxiv"]
+    p, q, r, n_emb = shape
+    cores = _cores(p, q, r, n_emb, 13)
+    rng = np.random.default_rng(6)
+    nnz = 40000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    row = rng.permutation(nnz).astype(np.int64)
+    fl = TC5 | _ttg.FLAG_DETERMINISTIC
+    out = _fwd(te, shape, cores, idx, row, nnz, flags=fl)
+    out2 = _fwd(te, shape, cores, idx, row, nnz, flags=fl)
+    assert torch.equal(out, out2)
+    want = orc.tt_forward(p, q, r, [c.numpy() for c in cores], idx, row, nnz)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    dO = ((rng.random(size=(1, nnz, int(np.prod(q)))) - 0.5) * 0.2).astype(np.float32)
+    got = _bwd(te, shape, [c.to(DEV) for c in cores], idx, row, dO, flags=fl)
+    wd = orc.tt_backward_dense(p, q, r, [c.numpy() for c in cores], idx, row, dO)
+    for t in range(3):
+        assert rel_err(got[t].cpu().numpy(), wd[t]) < TOL, "core %d" % t
