@@ -69,7 +69,8 @@ edge_softmax_bwd_kernel(int64_t num_dst, int32_t H, const int64_t* __restrict__ 
 __global__ void __launch_bounds__(256)
 head_spmm_fwd_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __restrict__ indptr,
                      const int32_t* __restrict__ indices, const float* __restrict__ a,
-                     const float* __restrict__ ft, float* __restrict__ out) {
+                     const float* __restrict__ ft, float* __restrict__ out,
+                     const int32_t* __restrict__ eid) {   // eid: weights of edge e at a[eid[e]] (transposed block)
   const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (v >= num_dst) return;
@@ -83,14 +84,15 @@ head_spmm_fwd_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __res
       float w[4], r[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        w[u] = __ldg(a + (e + u) * H + h);
+        w[u] = __ldg(a + (eid ? (int64_t)__ldg(eid + e + u) : e + u) * H + h);
         r[u] = __ldg(ft + (int64_t)__ldg(indices + e + u) * HF + d);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc = fmaf(w[u], r[u], acc);
     }
     for (; e < e1; ++e)
-      acc = fmaf(__ldg(a + e * H + h), __ldg(ft + (int64_t)__ldg(indices + e) * HF + d), acc);
+      acc = fmaf(__ldg(a + (eid ? (int64_t)__ldg(eid + e) : e) * H + h),
+                 __ldg(ft + (int64_t)__ldg(indices + e) * HF + d), acc);
     out[v * HF + d] = acc;
   }
 }
@@ -115,7 +117,7 @@ head_spmm_bwd_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __res
       const int h = d / F;
       const float g = __ldg(dout + v * HF + d);
       const float x = __ldg(ft + u * HF + d);
-      atomicAdd(dft + u * HF + d, __ldg(a + e * H + h) * g);
+      if (dft) atomicAdd(dft + u * HF + d, __ldg(a + e * H + h) * g);
 #pragma unroll
       for (int hh = 0; hh < kMaxHeads; ++hh)
         if (hh == h) part[hh] = fmaf(g, x, part[hh]);
@@ -136,11 +138,12 @@ head_spmm_bwd_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __res
 // once per edge (the scalar kernels above re-read index and weight for every column).
 constexpr int kMaxVec = 8;
 
-template <int NV>
+template <int NV, bool EID>
 __global__ void __launch_bounds__(256)
 head_spmm_fwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __restrict__ indptr,
                          const int32_t* __restrict__ indices, const float* __restrict__ a,
-                         const float* __restrict__ ft, float* __restrict__ out) {
+                         const float* __restrict__ ft, float* __restrict__ out,
+                         const int32_t* __restrict__ eid) {
   const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (v >= num_dst) return;
@@ -158,8 +161,8 @@ head_spmm_fwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* _
   for (; e + 2 <= e1; e += 2) {       // two source rows in flight per lane
     const float* r0 = ft + (int64_t)__ldg(indices + e) * HF;
     const float* r1 = ft + (int64_t)__ldg(indices + e + 1) * HF;
-    const float* w0 = a + e * H;
-    const float* w1 = w0 + H;
+    const float* w0 = a + (EID ? (int64_t)__ldg(eid + e) : e) * H;
+    const float* w1 = a + (EID ? (int64_t)__ldg(eid + e + 1) : e + 1) * H;
     float4 x0[NV], x1[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -187,7 +190,7 @@ head_spmm_fwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* _
   }
   if (e < e1) {
     const float* r0 = ft + (int64_t)__ldg(indices + e) * HF;
-    const float* w0 = a + e * H;
+    const float* w0 = a + (EID ? (int64_t)__ldg(eid + e) : e) * H;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = lane + 32 * j;
@@ -242,7 +245,7 @@ head_spmm_bwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* _
       if (c < n4) {
         const float4 x = ldg4(r + 4 * c);
         const float ah = __ldg(w + hj[j]);
-        red_add_v4(dr + 4 * c, make_float4(ah * g[j].x, ah * g[j].y, ah * g[j].z, ah * g[j].w));
+        if (dft) red_add_v4(dr + 4 * c, make_float4(ah * g[j].x, ah * g[j].y, ah * g[j].z, ah * g[j].w));
         const float dot = g[j].x * x.x + g[j].y * x.y + g[j].z * x.z + g[j].w * x.w;
 #pragma unroll
         for (int h = 0; h < kMaxHeads; ++h)
@@ -254,6 +257,70 @@ head_spmm_bwd_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* _
       if (h < H) {
         const float sum = warp_sum(part[h]);
         if (lane == 0) da[e * H + h] = sum;
+      }
+    }
+  }
+}
+
+// da[e][h] = <dout[v][h][:], ft[src(e)][h][:]> alone (the gather backward's first pass): two source rows in
+// flight per lane, as in the forward
+template <int NV>
+__global__ void __launch_bounds__(256)
+head_spmm_da_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __restrict__ indptr,
+                        const int32_t* __restrict__ indices, const float* __restrict__ ft,
+                        const float* __restrict__ dout, float* __restrict__ da) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= num_dst) return;
+  const int64_t e0 = __ldg(indptr + v), e1 = __ldg(indptr + v + 1);
+  if (e1 <= e0) return;
+  const int HF = H * F, n4 = HF / 4;
+  int hj[NV];
+  float4 g[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = lane + 32 * j;
+    hj[j] = (c < n4) ? (4 * c) / F : 0;
+    g[j] = (c < n4) ? ldg4(dout + v * HF + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t e = e0; e < e1; e += 2) {
+    const bool two = e + 1 < e1;
+    const float* r0 = ft + (int64_t)__ldg(indices + e) * HF;
+    const float* r1 = ft + (int64_t)__ldg(indices + (two ? e + 1 : e)) * HF;
+    float4 x0[NV], x1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        x0[j] = ldg4(r0 + 4 * c);
+        x1[j] = ldg4(r1 + 4 * c);
+      }
+    }
+    float p0[kMaxHeads], p1[kMaxHeads];
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) p0[h] = p1[h] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = lane + 32 * j;
+      if (c < n4) {
+        const float d0 = g[j].x * x0[j].x + g[j].y * x0[j].y + g[j].z * x0[j].z + g[j].w * x0[j].w;
+        const float d1 = g[j].x * x1[j].x + g[j].y * x1[j].y + g[j].z * x1[j].z + g[j].w * x1[j].w;
+#pragma unroll
+        for (int h = 0; h < kMaxHeads; ++h)
+          if (h == hj[j]) {
+            p0[h] += d0;
+            p1[h] += d1;
+          }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < kMaxHeads; ++h) {
+      if (h < H) {
+        const float s0 = warp_sum(p0[h]), s1 = warp_sum(p1[h]);
+        if (lane == 0) {
+          da[e * H + h] = s0;
+          if (two) da[(e + 1) * H + h] = s1;
+        }
       }
     }
   }
@@ -302,11 +369,12 @@ extern "C" int ttg_head_spmm_csr_fwd(int64_t num_dst, int32_t H, int32_t F, cons
   const unsigned grid = (unsigned)ceil_div(num_dst * 32, 256);
   const int nv = (int)ceil_div((int64_t)H * F / 4, 32);
   if (F % 4 == 0 && nv <= kMaxVec && ((uintptr_t)ft & 15) == 0 && ((uintptr_t)out & 15) == 0)
-    launch_vec(nv, head_spmm_fwd_vec_kernel<1>, head_spmm_fwd_vec_kernel<2>, head_spmm_fwd_vec_kernel<4>,
-               head_spmm_fwd_vec_kernel<8>, grid, (cudaStream_t)stream, num_dst, H, F, indptr, indices, a,
-               ft, out);
+    launch_vec(nv, head_spmm_fwd_vec_kernel<1, false>, head_spmm_fwd_vec_kernel<2, false>,
+               head_spmm_fwd_vec_kernel<4, false>, head_spmm_fwd_vec_kernel<8, false>, grid, (cudaStream_t)stream,
+               num_dst, H, F, indptr, indices, a, ft, out, (const int32_t*)nullptr);
   else
-    head_spmm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft, out);
+    head_spmm_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft, out,
+                                                                 nullptr);
   TTG_LAUNCH_CHECK();
   return TTG_OK;
 }
@@ -328,6 +396,42 @@ extern "C" int ttg_head_spmm_csr_bwd(int64_t num_dst, int32_t H, int32_t F, cons
   else
     head_spmm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft,
                                                                  dout, dft, da);
+  TTG_LAUNCH_CHECK();
+  return TTG_OK;
+}
+
+/* The same backward without atomics: da by the destination-major pass (no dft there), then
+ * dft[u,h,:] = sum_{e: src(e) = u} a[e,h] dout[dst(e),h,:] as a gather over the block transposed to source-major
+ * order (indptr_t [num_src + 1], dst_t [E] = destination of the e-th edge in that order, eid_t [E] = its position
+ * in the destination-major lists).  Every dft row is written (rows without out-edges get zeros): no zero fill. */
+extern "C" int ttg_head_spmm_csr_bwd_gather(int64_t num_dst, int64_t num_src, int32_t H, int32_t F,
+                                            const int64_t* indptr, const int32_t* indices, const float* a,
+                                            const float* ft, const float* dout, const int64_t* indptr_t,
+                                            const int32_t* dst_t, const int32_t* eid_t, float* dft, float* da,
+                                            void* stream) {
+  TTG_CHECK_ARG(H > 0 && H <= kMaxHeads && F > 0, "head_spmm: heads=%d, F=%d out of range", H, F);
+  if (num_dst == 0 || num_src == 0) return TTG_OK;
+  TTG_CHECK_ARG(indptr && dout && dft && da && indptr_t && dst_t && eid_t, "head_spmm_bwd_gather: null pointer");
+  const int nv = (int)ceil_div((int64_t)H * F / 4, 32);
+  const bool vec = F % 4 == 0 && nv <= kMaxVec && ((uintptr_t)ft & 15) == 0 && ((uintptr_t)dout & 15) == 0 &&
+                   ((uintptr_t)dft & 15) == 0;
+  const unsigned grid = (unsigned)ceil_div(num_dst * 32, 256), grid_t = (unsigned)ceil_div(num_src * 32, 256);
+  float* no_dft = nullptr;
+  if (vec) {
+    launch_vec(nv, head_spmm_da_vec_kernel<1>, head_spmm_da_vec_kernel<2>, head_spmm_da_vec_kernel<4>,
+               head_spmm_da_vec_kernel<8>, grid, (cudaStream_t)stream, num_dst, H, F, indptr, indices, ft, dout,
+               da);
+    TTG_LAUNCH_CHECK();
+    launch_vec(nv, head_spmm_fwd_vec_kernel<1, true>, head_spmm_fwd_vec_kernel<2, true>,
+               head_spmm_fwd_vec_kernel<4, true>, head_spmm_fwd_vec_kernel<8, true>, grid_t, (cudaStream_t)stream,
+               num_src, H, F, indptr_t, dst_t, a, dout, dft, eid_t);
+  } else {
+    head_spmm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_dst, H, F, indptr, indices, a, ft, dout,
+                                                                 no_dft, da);
+    TTG_LAUNCH_CHECK();
+    head_spmm_fwd_kernel<<<grid_t, 256, 0, (cudaStream_t)stream>>>(num_src, H, F, indptr_t, dst_t, a, dout, dft,
+                                                                   eid_t);
+  }
   TTG_LAUNCH_CHECK();
   return TTG_OK;
 }

@@ -47,6 +47,23 @@ class Block:
     def to(self, device):
         return Block(self.indptr.to(device), self.indices.to(device), self.num_src, self.num_dst)
 
+    def transposed(self):
+        """The block in source-major order, computed once and kept: (indptr_t int64 [num_src + 1], dst_t int32 [E],
+        eid_t int32 [E]) -- edge k of that order goes to destination dst_t[k] and is edge eid_t[k] of the
+        destination-major lists.  Backward passes that scatter to source rows become gathers over it."""
+        t = getattr(self, "_transposed", None)
+        if t is None:
+            src = self.indices.long()
+            order = torch.argsort(src, stable=True)
+            deg = self.indptr[1:] - self.indptr[:-1]
+            dst = torch.repeat_interleave(torch.arange(self.num_dst, device=src.device), deg)
+            counts = torch.bincount(src, minlength=self.num_src)
+            indptr_t = torch.zeros(self.num_src + 1, dtype=torch.int64, device=src.device)
+            indptr_t[1:] = torch.cumsum(counts, 0)
+            t = (indptr_t, dst[order].to(torch.int32).contiguous(), order.to(torch.int32).contiguous())
+            object.__setattr__(self, "_transposed", t)
+        return t
+
 
 class _SpMM(torch.autograd.Function):
     @staticmethod
@@ -243,9 +260,13 @@ class _EdgeSoftmax(torch.autograd.Function):
         return None, ds, None
 
 
+GATHER_BACKWARD = True      # attention_aggregate's backward: gather over the transposed block / atomics
+
+
 class _HeadSpMM(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, indptr, indices, a, ft, num_dst):
+    def forward(ctx, block, a, ft):
+        indptr, indices, num_dst = block.indptr, block.indices, block.num_dst
         a = _ttg.require_cuda(a.contiguous(), "a", torch.float32)
         ft = _ttg.require_cuda(ft.contiguous(), "ft", torch.float32)      # [num_src][H][F]
         dev, H, F = ft.device, ft.size(1), ft.size(2)
@@ -257,6 +278,7 @@ class _HeadSpMM(torch.autograd.Function):
             _ttg.check(rc, "head_spmm_csr_fwd")
         ctx.save_for_backward(indptr, indices, a, ft)
         ctx.num_dst = num_dst
+        ctx.block = block
         return out
 
     @staticmethod
@@ -265,14 +287,25 @@ class _HeadSpMM(torch.autograd.Function):
         dev, H, F = ft.device, ft.size(1), ft.size(2)
         with _ttg.on_device(dev):
             dout = dout.to(torch.float32).contiguous()
-            dft = torch.zeros_like(ft)
             da = torch.empty_like(a)
-            rc = _ttg.lib().ttg_head_spmm_csr_bwd(ctx.num_dst, H, F, _ttg.ptr(indptr),
-                                                  _ttg.ptr(indices), _ttg.ptr(a), _ttg.ptr(ft),
-                                                  _ttg.ptr(dout), _ttg.ptr(dft), _ttg.ptr(da),
-                                                  _ttg.stream_of(dev))
-            _ttg.check(rc, "head_spmm_csr_bwd")
-        return None, None, da, dft, None
+            if GATHER_BACKWARD:
+                # dft by a gather over the transposed block (kept with the block: a static graph transposes once)
+                # instead of 16-byte atomics into the source rows: 2x faster at ogbn-arxiv shape
+                indptr_t, dst_t, eid_t = ctx.block.transposed()
+                dft = torch.empty_like(ft)
+                rc = _ttg.lib().ttg_head_spmm_csr_bwd_gather(
+                    ctx.num_dst, ft.size(0), H, F, _ttg.ptr(indptr), _ttg.ptr(indices), _ttg.ptr(a), _ttg.ptr(ft),
+                    _ttg.ptr(dout), _ttg.ptr(indptr_t), _ttg.ptr(dst_t), _ttg.ptr(eid_t), _ttg.ptr(dft),
+                    _ttg.ptr(da), _ttg.stream_of(dev))
+                _ttg.check(rc, "head_spmm_csr_bwd_gather")
+            else:
+                dft = torch.zeros_like(ft)
+                rc = _ttg.lib().ttg_head_spmm_csr_bwd(ctx.num_dst, H, F, _ttg.ptr(indptr),
+                                                      _ttg.ptr(indices), _ttg.ptr(a), _ttg.ptr(ft),
+                                                      _ttg.ptr(dout), _ttg.ptr(dft), _ttg.ptr(da),
+                                                      _ttg.stream_of(dev))
+                _ttg.check(rc, "head_spmm_csr_bwd")
+        return None, da, dft
 
 
 def edge_softmax(block: Block, score: torch.Tensor) -> torch.Tensor:
@@ -282,7 +315,7 @@ def edge_softmax(block: Block, score: torch.Tensor) -> torch.Tensor:
 
 def attention_aggregate(block: Block, a: torch.Tensor, ft: torch.Tensor) -> torch.Tensor:
     """out[v, h, :] = sum_{e in N_in(v)} a[e, h] * ft[src(e), h, :]"""
-    return _HeadSpMM.apply(block.indptr, block.indices, a, ft, block.num_dst)
+    return _HeadSpMM.apply(block, a, ft)
 
 
 class GATConv(nn.Module):

@@ -333,6 +333,13 @@ int ttg_head_spmm_csr_fwd(int64_t num_dst, int32_t H, int32_t F, const int64_t* 
 int ttg_head_spmm_csr_bwd(int64_t num_dst, int32_t H, int32_t F, const int64_t* indptr,
                           const int32_t* indices, const float* a, const float* ft,
                           const float* dout, float* dft, float* da, void* stream);
+/* the same backward without atomics, for callers that hold the block in source-major order as well (a static
+ * graph transposes once): da as above, dft as a gather over (indptr_t [num_src + 1], dst_t [E], eid_t [E] = the
+ * edge's position in the destination-major lists); every dft row is written, no zero fill needed */
+int ttg_head_spmm_csr_bwd_gather(int64_t num_dst, int64_t num_src, int32_t H, int32_t F, const int64_t* indptr,
+                                 const int32_t* indices, const float* a, const float* ft, const float* dout,
+                                 const int64_t* indptr_t, const int32_t* dst_t, const int32_t* eid_t,
+                                 float* dft, float* da, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (f-1) neighbour sampling + block construction on the device, one GNN layer per call.

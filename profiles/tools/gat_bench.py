@@ -47,4 +47,8 @@ bytes_f = ne * (H * F * 4 + H * 4 + 4) + N * H * F * 4
 print("head_spmm fwd      %.3f ms  (%.0f GB/s algorithmic)" % (ms, bytes_f / ms / 1e6))
 go = torch.randn_like(out)
 ms = timed(lambda: torch.autograd.grad(out, (ad, ft), go, retain_graph=True))
-print("head_spmm bwd      %.3f ms  (incl. zero-fill of d_ft; %.0f GB/s algorithmic)" % (ms, (2 * bytes_f) / ms / 1e6))
+print("head_spmm bwd      %.3f ms  (gather over the transposed block; %.0f GB/s algorithmic)" % (ms, (2 * bytes_f) / ms / 1e6))
+gnn_ops.GATHER_BACKWARD = False
+ms = timed(lambda: torch.autograd.grad(out, (ad, ft), go, retain_graph=True))
+print("head_spmm bwd      %.3f ms  (atomics, incl. zero-fill of d_ft; %.0f GB/s algorithmic)" % (ms, (2 * bytes_f) / ms / 1e6))
+gnn_ops.GATHER_BACKWARD = True

@@ -32,9 +32,12 @@ def _ref_softmax(score, dst_of_edge, num_dst):
     return ex / z[dst_of_edge]
 
 
+@pytest.mark.parametrize("gather", [True, False], ids=["gather_backward", "atomic_backward"])
 @pytest.mark.parametrize("H,F", [(1, 64), (3, 256), (4, 47), (8, 5)])
-def test_edge_softmax_and_aggregation_forward_backward(ttg_lib, H, F):
+def test_edge_softmax_and_aggregation_forward_backward(ttg_lib, H, F, gather, monkeypatch):
+    """(both backward passes of the aggregation: the gather over the transposed block and the atomics)"""
     import gnn_ops
+    monkeypatch.setattr(gnn_ops, "GATHER_BACKWARD", gather)
     rng = np.random.default_rng(H * 100 + F)
     num_src, num_dst = 900, 400
     blk, dst_e, src_e = _block(rng, num_src, num_dst, 12)
