@@ -22,6 +22,11 @@ from torch import nn
 import _ttg
 
 
+# backward passes that scatter to source rows: gather over the transposed block (Block.transposed) where that is
+# kept, instead of atomics
+GATHER_BACKWARD = True
+
+
 @dataclass
 class Block:
     indptr: torch.Tensor       # int64 [num_dst + 1]
@@ -65,9 +70,46 @@ class Block:
         return t
 
 
+def _gather_backward(block) -> bool:
+    """Scatter-free backward (an SpMM over the transposed block) where the block is, or looks, static: a
+    full-graph block (square) transposes once and keeps it; a sampled block is used once and the transposition
+    (a sort of its edges) would cost more than the atomics it saves."""
+    return GATHER_BACKWARD and (getattr(block, "_transposed", None) is not None or block.num_src == block.num_dst)
+
+
+def _spmm_backward(block, dout, F, mean, edge_weight):
+    """dx [num_src][F] of out = aggregate(block, x): as a gather over the transposed block or by atomics."""
+    dev = dout.device
+    if _gather_backward(block):
+        indptr_t, dst_t, eid_t = block.transposed()
+        w_t = None
+        if mean:
+            w_t = getattr(block, "_inv_deg_t", None)
+            if w_t is None:
+                inv = 1.0 / block.in_degrees().clamp(min=1).to(torch.float32)
+                w_t = inv[dst_t.long()].contiguous()
+                object.__setattr__(block, "_inv_deg_t", w_t)
+        if edge_weight is not None:
+            we = edge_weight[eid_t.long()]
+            w_t = we if w_t is None else (w_t * we)
+            w_t = w_t.contiguous()
+        dx = torch.empty((block.num_src, F), dtype=torch.float32, device=dev)
+        rc = _ttg.lib().ttg_spmm_csr_fwd(block.num_src, F, _ttg.ptr(indptr_t), _ttg.ptr(dst_t), _ttg.ptr(w_t), 0,
+                                         _ttg.ptr(dout), _ttg.ptr(dx), _ttg.stream_of(dev))
+        _ttg.check(rc, "spmm_csr_fwd (transposed)")
+        return dx
+    dx = torch.zeros((block.num_src, F), dtype=torch.float32, device=dev)
+    rc = _ttg.lib().ttg_spmm_csr_bwd(block.num_dst, F, _ttg.ptr(block.indptr), _ttg.ptr(block.indices),
+                                     _ttg.ptr(edge_weight), 1 if mean else 0, _ttg.ptr(dout), _ttg.ptr(dx),
+                                     _ttg.stream_of(dev))
+    _ttg.check(rc, "spmm_csr_bwd")
+    return dx
+
+
 class _SpMM(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, indptr, indices, x, num_dst, mean, edge_weight):
+    def forward(ctx, block, x, mean, edge_weight):
+        indptr, indices, num_dst = block.indptr, block.indices, block.num_dst
         _ttg.require_cuda(indptr, "indptr", torch.int64)
         _ttg.require_cuda(indices, "indices", torch.int32)
         x = _ttg.require_cuda(x.contiguous(), "x", torch.float32)
@@ -79,23 +121,18 @@ class _SpMM(torch.autograd.Function):
                                              _ttg.ptr(edge_weight), 1 if mean else 0, _ttg.ptr(x),
                                              _ttg.ptr(out), _ttg.stream_of(dev))
             _ttg.check(rc, "spmm_csr_fwd")
-        ctx.save_for_backward(indptr, indices, edge_weight)
-        ctx.cfg = (x.size(0), num_dst, F, mean)
+        ctx.save_for_backward(edge_weight)
+        ctx.block = block
+        ctx.cfg = (F, mean)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        indptr, indices, edge_weight = ctx.saved_tensors
-        num_src, num_dst, F, mean = ctx.cfg
-        dev = dout.device
-        with _ttg.on_device(dev):
-            dout = dout.to(torch.float32).contiguous()
-            dx = torch.zeros((num_src, F), dtype=torch.float32, device=dev)
-            rc = _ttg.lib().ttg_spmm_csr_bwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices),
-                                             _ttg.ptr(edge_weight), 1 if mean else 0,
-                                             _ttg.ptr(dout), _ttg.ptr(dx), _ttg.stream_of(dev))
-            _ttg.check(rc, "spmm_csr_bwd")
-        return None, None, dx, None, None, None
+        (edge_weight,) = ctx.saved_tensors
+        F, mean = ctx.cfg
+        with _ttg.on_device(dout.device):
+            dx = _spmm_backward(ctx.block, dout.to(torch.float32).contiguous(), F, mean, edge_weight)
+        return None, dx, None, None
 
 
 class _SpMMWithSelf(torch.autograd.Function):
@@ -107,7 +144,8 @@ class _SpMMWithSelf(torch.autograd.Function):
     num_dst rows of the aggregation's gradient."""
 
     @staticmethod
-    def forward(ctx, indptr, indices, x, num_dst, mean):
+    def forward(ctx, block, x, mean):
+        indptr, indices, num_dst = block.indptr, block.indices, block.num_dst
         _ttg.require_cuda(indptr, "indptr", torch.int64)
         _ttg.require_cuda(indices, "indices", torch.int32)
         x = _ttg.require_cuda(x.contiguous(), "x", torch.float32)
@@ -119,35 +157,28 @@ class _SpMMWithSelf(torch.autograd.Function):
                                              1 if mean else 0, _ttg.ptr(x), _ttg.ptr(out),
                                              _ttg.stream_of(dev))
             _ttg.check(rc, "spmm_csr_fwd")
-        ctx.save_for_backward(indptr, indices)
-        ctx.cfg = (x.size(0), num_dst, F, mean)
+        ctx.block = block
+        ctx.cfg = (num_dst, F, mean)
         return out, x[:num_dst].clone()
 
     @staticmethod
     def backward(ctx, dout, dself):
-        indptr, indices = ctx.saved_tensors
-        num_src, num_dst, F, mean = ctx.cfg
-        dev = dout.device
-        with _ttg.on_device(dev):
-            dout = dout.to(torch.float32).contiguous()
-            dx = torch.zeros((num_src, F), dtype=torch.float32, device=dev)
-            rc = _ttg.lib().ttg_spmm_csr_bwd(num_dst, F, _ttg.ptr(indptr), _ttg.ptr(indices), None,
-                                             1 if mean else 0, _ttg.ptr(dout), _ttg.ptr(dx),
-                                             _ttg.stream_of(dev))
-            _ttg.check(rc, "spmm_csr_bwd")
+        num_dst, F, mean = ctx.cfg
+        with _ttg.on_device(dout.device):
+            dx = _spmm_backward(ctx.block, dout.to(torch.float32).contiguous(), F, mean, None)
             dx[:num_dst].add_(dself)
-        return None, None, dx, None, None
+        return None, dx, None
 
 
 def aggregate_with_self(block: Block, x: torch.Tensor, mean: bool) -> Tuple[torch.Tensor, torch.Tensor]:
     """(neighbour aggregate, the destination nodes' own rows): see _SpMMWithSelf."""
-    return _SpMMWithSelf.apply(block.indptr, block.indices, x, block.num_dst, mean)
+    return _SpMMWithSelf.apply(block, x, mean)
 
 
 def aggregate(block: Block, x: torch.Tensor, mean: bool,
               edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[v] = (1/deg(v) if mean) * sum_{u in N_in(v)} w_uv * x[u]; rows without in-edges are 0."""
-    return _SpMM.apply(block.indptr, block.indices, x, block.num_dst, mean, edge_weight)
+    return _SpMM.apply(block, x, mean, edge_weight)
 
 
 class SAGEConv(nn.Module):
@@ -260,9 +291,6 @@ class _EdgeSoftmax(torch.autograd.Function):
         return None, ds, None
 
 
-GATHER_BACKWARD = True      # attention_aggregate's backward: gather over the transposed block / atomics
-
-
 class _HeadSpMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, block, a, ft):
@@ -288,7 +316,7 @@ class _HeadSpMM(torch.autograd.Function):
         with _ttg.on_device(dev):
             dout = dout.to(torch.float32).contiguous()
             da = torch.empty_like(a)
-            if GATHER_BACKWARD:
+            if _gather_backward(ctx.block):
                 # dft by a gather over the transposed block (kept with the block: a static graph transposes once)
                 # instead of 16-byte atomics into the source rows: 2x faster at ogbn-arxiv shape
                 indptr_t, dst_t, eid_t = ctx.block.transposed()

@@ -38,6 +38,7 @@ def test_edge_softmax_and_aggregation_forward_backward(ttg_lib, H, F, gather, mo
     """(both backward passes of the aggregation: the gather over the transposed block and the atomics)"""
     import gnn_ops
     monkeypatch.setattr(gnn_ops, "GATHER_BACKWARD", gather)
+    monkeypatch.setattr(gnn_ops, "_gather_backward", lambda block: gather)     # also on this non-square block
     rng = np.random.default_rng(H * 100 + F)
     num_src, num_dst = 900, 400
     blk, dst_e, src_e = _block(rng, num_src, num_dst, 12)
@@ -127,3 +128,37 @@ def test_gat_model_full_graph_step(ttg_lib):
         opt.step()
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("mean", [True, False])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_aggregate_backward_as_a_gather_over_the_transposed_block(ttg_lib, mean, weighted, monkeypatch):
+    """aggregate()'s backward on a full-graph (square) block runs as an SpMM over the transposed block; same
+    gradient as the atomics path and as fp64 torch, with and without edge weights, rows without out-edges zero."""
+    import gnn_ops
+    rng = np.random.default_rng(11)
+    n = 700
+    blk, dst_e, src_e = _block(rng, n, n, 9)
+    E = src_e.numel()
+    g = torch.Generator().manual_seed(3)
+    x64 = torch.randn(n, 48, generator=g, dtype=torch.float64).requires_grad_(True)
+    w64 = torch.rand(E, generator=g, dtype=torch.float64) + 0.5 if weighted else None
+    msg = x64[src_e] * (w64[:, None] if weighted else 1.0)
+    out64 = torch.zeros(n, 48, dtype=torch.float64).index_add_(0, dst_e, msg)
+    if mean:
+        deg = torch.bincount(dst_e, minlength=n).clamp(min=1).double()
+        out64 = out64 / deg[:, None]
+    up = torch.randn(n, 48, generator=g, dtype=torch.float64)
+    (out64 * up).sum().backward()
+    grads = []
+    for gather in (True, False):
+        monkeypatch.setattr(gnn_ops, "GATHER_BACKWARD", gather)
+        x = x64.detach().float().to(DEV).requires_grad_(True)
+        ew = w64.float().to(DEV) if weighted else None
+        out = gnn_ops.aggregate(blk, x, mean=mean, edge_weight=ew)
+        assert float((out.detach().cpu().double() - out64.detach()).abs().max() / out64.abs().max()) < 1e-5
+        (out * up.float().to(DEV)).sum().backward()
+        grads.append(x.grad.cpu().double())
+        assert float((grads[-1] - x64.grad).abs().max() / x64.grad.abs().max()) < 1e-5
+    assert getattr(blk, "_transposed", None) is not None
+    assert float((grads[0] - grads[1]).abs().max() / grads[1].abs().max()) < 1e-6
