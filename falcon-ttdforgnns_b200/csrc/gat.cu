@@ -296,31 +296,29 @@ head_spmm_da_vec_kernel(int64_t num_dst, int32_t H, int32_t F, const int64_t* __
         x1[j] = ldg4(r1 + 4 * c);
       }
     }
-    float p0[kMaxHeads], p1[kMaxHeads];
-#pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) p0[h] = p1[h] = 0.f;
+    float d0[NV], d1[NV];       // per 16-byte column: its share of the two dot products (one head each)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = lane + 32 * j;
+      d0[j] = d1[j] = 0.f;
       if (c < n4) {
-        const float d0 = g[j].x * x0[j].x + g[j].y * x0[j].y + g[j].z * x0[j].z + g[j].w * x0[j].w;
-        const float d1 = g[j].x * x1[j].x + g[j].y * x1[j].y + g[j].z * x1[j].z + g[j].w * x1[j].w;
-#pragma unroll
-        for (int h = 0; h < kMaxHeads; ++h)
-          if (h == hj[j]) {
-            p0[h] += d0;
-            p1[h] += d1;
-          }
+        d0[j] = g[j].x * x0[j].x + g[j].y * x0[j].y + g[j].z * x0[j].z + g[j].w * x0[j].w;
+        d1[j] = g[j].x * x1[j].x + g[j].y * x1[j].y + g[j].z * x1[j].z + g[j].w * x1[j].w;
       }
     }
+    for (int h = 0; h < H; ++h) {
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int h = 0; h < kMaxHeads; ++h) {
-      if (h < H) {
-        const float s0 = warp_sum(p0[h]), s1 = warp_sum(p1[h]);
-        if (lane == 0) {
-          da[e * H + h] = s0;
-          if (two) da[(e + 1) * H + h] = s1;
+      for (int j = 0; j < NV; ++j)
+        if (hj[j] == h) {
+          s0 += d0[j];
+          s1 += d1[j];
         }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        da[e * H + h] = s0;
+        if (two) da[(e + 1) * H + h] = s1;
       }
     }
   }
