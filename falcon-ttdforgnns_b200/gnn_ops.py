@@ -52,6 +52,22 @@ class Block:
     def to(self, device):
         return Block(self.indptr.to(device), self.indices.to(device), self.num_src, self.num_dst)
 
+    def dst_of_edge(self):
+        """int64 [E]: the destination of every edge of the destination-major lists (kept with the block)."""
+        d = getattr(self, "_dst_of_edge", None)
+        if d is None:
+            d = torch.repeat_interleave(torch.arange(self.num_dst, device=self.indptr.device), self.in_degrees())
+            object.__setattr__(self, "_dst_of_edge", d)
+        return d
+
+    def edge_ids(self):
+        """int32 [E]: 0 .. E - 1 (the identity edge map, for segment sums with the aggregation kernel)."""
+        e = getattr(self, "_edge_ids", None)
+        if e is None:
+            e = torch.arange(self.indices.numel(), dtype=torch.int32, device=self.indptr.device)
+            object.__setattr__(self, "_edge_ids", e)
+        return e
+
     def transposed(self):
         """The block in source-major order, computed once and kept: (indptr_t int64 [num_src + 1], dst_t int32 [E],
         eid_t int32 [E]) -- edge k of that order goes to destination dst_t[k] and is edge eid_t[k] of the
@@ -60,8 +76,7 @@ class Block:
         if t is None:
             src = self.indices.long()
             order = torch.argsort(src, stable=True)
-            deg = self.indptr[1:] - self.indptr[:-1]
-            dst = torch.repeat_interleave(torch.arange(self.num_dst, device=src.device), deg)
+            dst = self.dst_of_edge()
             counts = torch.bincount(src, minlength=self.num_src)
             indptr_t = torch.zeros(self.num_src + 1, dtype=torch.int64, device=src.device)
             indptr_t[1:] = torch.cumsum(counts, 0)
@@ -336,6 +351,42 @@ class _HeadSpMM(torch.autograd.Function):
         return None, da, dft
 
 
+class _EdgeAddUV(torch.autograd.Function):
+    """score[e] = el[src(e)] + er[dst(e)] (DGL's u_add_v) on a block whose transposed form is kept: the backward
+    sums d_score over each source's out-edges and each destination's in-edges with the aggregation kernel
+    (rows of d_score gathered through the edge map / the identity) instead of torch's index_put with accumulate."""
+
+    @staticmethod
+    def forward(ctx, block, el, er):
+        ctx.block = block
+        return el[block.indices.long()] + er[block.dst_of_edge()]
+
+    @staticmethod
+    def backward(ctx, d):
+        block = ctx.block
+        d = _ttg.require_cuda(d.contiguous(), "d_score", torch.float32)
+        H = d.size(1)
+        dev = d.device
+        indptr_t, _, eid_t = block.transposed()
+        with _ttg.on_device(dev):
+            d_el = torch.empty((block.num_src, H), dtype=torch.float32, device=dev)
+            d_er = torch.empty((block.num_dst, H), dtype=torch.float32, device=dev)
+            lib = _ttg.lib()
+            _ttg.check(lib.ttg_spmm_csr_fwd(block.num_src, H, _ttg.ptr(indptr_t), _ttg.ptr(eid_t), None, 0,
+                                            _ttg.ptr(d), _ttg.ptr(d_el), _ttg.stream_of(dev)), "u_add_v backward (src)")
+            _ttg.check(lib.ttg_spmm_csr_fwd(block.num_dst, H, _ttg.ptr(block.indptr), _ttg.ptr(block.edge_ids()),
+                                            None, 0, _ttg.ptr(d), _ttg.ptr(d_er), _ttg.stream_of(dev)),
+                       "u_add_v backward (dst)")
+        return None, d_el, d_er
+
+
+def edge_add_uv(block: Block, el: torch.Tensor, er: torch.Tensor) -> torch.Tensor:
+    """[E][H] scores el[src(e)] + er[dst(e)]."""
+    if _gather_backward(block) and el.dtype == torch.float32 and er.dtype == torch.float32:
+        return _EdgeAddUV.apply(block, el, er)
+    return el[block.indices.long()] + er[block.dst_of_edge()]
+
+
 def edge_softmax(block: Block, score: torch.Tensor) -> torch.Tensor:
     """softmax of score [E][H] over the in-edges of every destination node, per head."""
     return _EdgeSoftmax.apply(block.indptr, score, block.num_dst)
@@ -414,8 +465,7 @@ class GATConv(nn.Module):
         el = (feat_src * self.attn_l).sum(dim=-1)              # [num_src][H]
         er = (feat_dst * self.attn_r).sum(dim=-1)              # [num_dst][H]
         deg_in = block.in_degrees()
-        dst_of_edge = torch.repeat_interleave(torch.arange(block.num_dst, device=el.device), deg_in)
-        e = self.leaky_relu(el[block.indices.long()] + er[dst_of_edge])      # u_add_v
+        e = self.leaky_relu(edge_add_uv(block, el, er))      # u_add_v
         a = self.attn_drop(edge_softmax(block, e))
         rst = attention_aggregate(block, a, feat_src)
         if self._norm == "both":

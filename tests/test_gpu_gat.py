@@ -162,3 +162,23 @@ def test_aggregate_backward_as_a_gather_over_the_transposed_block(ttg_lib, mean,
         assert float((grads[-1] - x64.grad).abs().max() / x64.grad.abs().max()) < 1e-5
     assert getattr(blk, "_transposed", None) is not None
     assert float((grads[0] - grads[1]).abs().max() / grads[1].abs().max()) < 1e-6
+
+
+def test_edge_add_uv_backward_on_a_full_graph_block(ttg_lib):
+    """edge_add_uv (u_add_v of the attention scores) with its gather backward against plain torch indexing."""
+    import gnn_ops
+    rng = np.random.default_rng(21)
+    n, H = 600, 3
+    blk, dst_e, src_e = _block(rng, n, n, 11)
+    g = torch.Generator().manual_seed(5)
+    el = torch.randn(n, H, generator=g).to(DEV).requires_grad_(True)
+    er = torch.randn(n, H, generator=g).to(DEV).requires_grad_(True)
+    up = torch.randn(src_e.numel(), H, generator=g).to(DEV)
+    assert gnn_ops._gather_backward(blk)
+    (gnn_ops.edge_add_uv(blk, el, er) * up).sum().backward()
+    got = (el.grad.clone(), er.grad.clone())
+    el.grad = er.grad = None
+    ((el[src_e.to(DEV)] + er[dst_e.to(DEV)]) * up).sum().backward()
+    for a, b in zip(got, (el.grad, er.grad)):
+        assert float((a - b).abs().max() / b.abs().max()) < 1e-5
+    assert float(got[1][0].abs().max()) == 0.0       # destination 0 has no in-edges
