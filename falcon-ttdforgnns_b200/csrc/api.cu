@@ -95,12 +95,135 @@ int make_ttdev(const ttg_shape* shape, const float* const* host_core_ptrs, TTDev
   return TTG_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Four cores on the three-core kernels.  The first two cores of a T = 4 chain are contracted into one,
+//   M[(i0, i1)][(j0, j1)][k2] = sum_k1 G0[i0][j0][k1] G1[i1][k1][j1][k2]      p' = p0 p1, q' = q0 q1, ranks (1, r2),
+// which turns the table into a T = 3 one with the same rows in the same order (the mixed-radix digits (i0, i1)
+// and (j0, j1) are adjacent), e.g. p = 50,60,60,60 q = 4,2,4,4 ranks 16,16,16 (run_script.sh:501-541) into
+// p = 3000,60,60 q = 8,4,4 ranks 16,16.  When the T = 3 shape has sorted / tensor-core kernels the lookup runs on
+// them; the backward's d_M goes back through the contraction,
+//   dG0[i0][j0][k1] = sum_{i1, j1, k2} dM[(i0, i1)][(j0, j1)][k2] G1[i1][k1][j1][k2]
+//   dG1[i1][k1][j1][k2] = sum_{i0, j0} G0[i0][j0][k1] dM[(i0, i1)][(j0, j1)][k2]
+// and a fused update is the dense backward followed by the optimizer kernel on all four cores.  M and dM live at
+// the head of the caller's workspace (ttg_tt_workspace_bytes accounts for them).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+struct MergeDims {
+  int tables, p0, p1, q0, q1, r1, r2;
+};
+
+__global__ void __launch_bounds__(256) merge_cores_kernel(MergeDims d, const float* __restrict__ g0,
+                                                          const float* __restrict__ g1, float* __restrict__ m) {
+  const int row = blockIdx.x;                       // (table, i0, i1)
+  const int tb = row / (d.p0 * d.p1), i0 = (row / d.p1) % d.p0, i1 = row % d.p1;
+  const float* a = g0 + ((size_t)tb * d.p0 + i0) * (d.q0 * d.r1);
+  const float* b = g1 + ((size_t)tb * d.p1 + i1) * (d.r1 * d.q1 * d.r2);
+  const int n = d.q0 * d.q1 * d.r2;
+  for (int o = threadIdx.x; o < n; o += blockDim.x) {
+    const int k2 = o % d.r2, j1 = (o / d.r2) % d.q1, j0 = o / (d.r2 * d.q1);
+    float acc = 0.f;
+    for (int k1 = 0; k1 < d.r1; ++k1) acc = fmaf(a[j0 * d.r1 + k1], b[(k1 * d.q1 + j1) * d.r2 + k2], acc);
+    m[(size_t)row * n + o] = acc;
+  }
+}
+
+// both backward kernels split their reduction axis over blockIdx.y and add their share to the zeroed output
+constexpr int kMergeSplit = 8;
+
+__global__ void __launch_bounds__(256) merge_bwd0_kernel(MergeDims d, const float* __restrict__ dm,
+                                                         const float* __restrict__ g1, float* __restrict__ dg0) {
+  const int ti0 = blockIdx.x, tb = ti0 / d.p0;      // (table, i0)
+  const int n = d.q0 * d.q1 * d.r2, e_n = d.q1 * d.r2;
+  const int per = (d.p1 + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(lo + per, d.p1);
+  for (int o = threadIdx.x; o < d.q0 * d.r1; o += blockDim.x) {
+    const int k1 = o % d.r1, j0 = o / d.r1;
+    float acc = 0.f;
+    for (int i1 = lo; i1 < hi; ++i1) {
+      const float* x = dm + ((size_t)ti0 * d.p1 + i1) * n + j0 * e_n;
+      const float* b = g1 + ((size_t)tb * d.p1 + i1) * (d.r1 * e_n) + k1 * e_n;
+      for (int e = 0; e < e_n; ++e) acc = fmaf(__ldg(x + e), __ldg(b + e), acc);
+    }
+    atomicAdd(dg0 + (size_t)ti0 * (d.q0 * d.r1) + o, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) merge_bwd1_kernel(MergeDims d, const float* __restrict__ dm,
+                                                         const float* __restrict__ g0, float* __restrict__ dg1) {
+  const int ti1 = blockIdx.x, tb = ti1 / d.p1, i1 = ti1 % d.p1;      // (table, i1)
+  const int n = d.q0 * d.q1 * d.r2, e_n = d.q1 * d.r2;
+  const int per = (d.p0 + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int lo = blockIdx.y * per, hi = min(lo + per, d.p0);
+  for (int o = threadIdx.x; o < d.r1 * e_n; o += blockDim.x) {
+    const int e = o % e_n, k1 = o / e_n;
+    float acc = 0.f;
+    for (int i0 = lo; i0 < hi; ++i0) {
+      const float* a = g0 + ((size_t)tb * d.p0 + i0) * (d.q0 * d.r1) + k1;
+      const float* x = dm + (((size_t)tb * d.p0 + i0) * d.p1 + i1) * n + e;
+      for (int j0 = 0; j0 < d.q0; ++j0) acc = fmaf(__ldg(a + j0 * d.r1), __ldg(x + j0 * e_n), acc);
+    }
+    atomicAdd(dg1 + (size_t)ti1 * (d.r1 * e_n) + o, acc);
+  }
+}
+
+// the T = 3 form of a T = 4 table (cores: merged, core2, core3); false when it has no sorted kernels
+struct Merged {
+  TTDev tt3;
+  MergeDims dims;
+  size_t m_floats;        // floats of M (and of dM)
+  size_t head_bytes;      // bytes M and dM take at the head of the workspace
+};
+bool merged_form(const TTDev& tt, Merged* mg) {
+  if (tt.T != 4) return false;
+  ttg_shape s3;
+  memset(&s3, 0, sizeof(s3));
+  s3.T = 3;
+  s3.num_tables = tt.num_tables;
+  s3.p[0] = tt.p[0] * tt.p[1];
+  s3.p[1] = tt.p[2];
+  s3.p[2] = tt.p[3];
+  s3.q[0] = tt.q[0] * tt.q[1];
+  s3.q[1] = tt.q[2];
+  s3.q[2] = tt.q[3];
+  s3.r[0] = 1;
+  s3.r[1] = tt.r[2];
+  s3.r[2] = tt.r[3];
+  s3.r[3] = 1;
+  if ((int64_t)tt.p[0] * tt.p[1] > INT32_MAX) return false;
+  const float* cores3[TTG_MAX_CORES] = {nullptr, tt.core[2], tt.core[3], nullptr};
+  if (make_ttdev(&s3, cores3, &mg->tt3) != TTG_OK) return false;
+  if (!sorted_supported(mg->tt3)) return false;
+  mg->dims = MergeDims{tt.num_tables, tt.p[0], tt.p[1], tt.q[0], tt.q[1], tt.r[1], tt.r[2]};
+  mg->m_floats = (size_t)tt.num_tables * tt.p[0] * tt.p[1] * (tt.q[0] * tt.q[1] * tt.r[2]);
+  mg->head_bytes = 2 * align_up(mg->m_floats * sizeof(float), 256);
+  return true;
+}
+
+}  // namespace
+
 int tt_forward_dispatch(const TTDev& tt, int64_t B, int64_t nnz, const int64_t* indices,
                         const int64_t* rowidx, const int64_t* tableidx, float* output, void* ws,
                         size_t ws_bytes, int32_t flags, cudaStream_t stream) {
   if (!(flags & TTG_FLAG_FORCE_GENERIC) && sorted_supported(tt))
     return sorted_forward(tt, B, nnz, indices, rowidx, tableidx, output, ws, ws_bytes, flags,
                           stream);
+  Merged mg;
+  if (!(flags & TTG_FLAG_FORCE_GENERIC) && nnz > 0 && merged_form(tt, &mg)) {
+    if (ws == nullptr || ws_bytes < mg.head_bytes) {
+      set_error("tt_forward: workspace %zu < %zu bytes", ws_bytes, mg.head_bytes);
+      return TTG_ENOMEM;
+    }
+    float* m = (float*)ws;
+    mg.tt3.core[0] = m;
+    if (!(flags & TTG_FLAG_PLAN_VALID)) {      // otherwise M of these cores is still in the workspace
+      merge_cores_kernel<<<(unsigned)(tt.num_tables * tt.p[0] * tt.p[1]), 256, 0, stream>>>(mg.dims, tt.core[0],
+                                                                                          tt.core[1], m);
+      TTG_LAUNCH_CHECK();
+    }
+    return sorted_forward(mg.tt3, B, nnz, indices, rowidx, tableidx, output, (char*)ws + mg.head_bytes,
+                          ws_bytes - mg.head_bytes, flags, stream);
+  }
   return generic_forward(tt, B, nnz, indices, rowidx, tableidx, output, stream);
 }
 
@@ -113,6 +236,35 @@ static int tt_backward_dispatch(const TTDev& tt, int64_t B, int64_t nnz, const i
   if (!(flags & TTG_FLAG_FORCE_GENERIC) && sorted_supported(tt))
     return sorted_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, optim, lr, eps,
                            state, ws, ws_bytes, flags, stream);
+  Merged mg;
+  if (!(flags & TTG_FLAG_FORCE_GENERIC) && nnz > 0 && merged_form(tt, &mg)) {
+    if (ws == nullptr || ws_bytes < mg.head_bytes) {
+      set_error("tt_backward: workspace %zu < %zu bytes", ws_bytes, mg.head_bytes);
+      return TTG_ENOMEM;
+    }
+    float* m = (float*)ws;
+    float* dm = (float*)((char*)ws + mg.head_bytes / 2);
+    mg.tt3.core[0] = m;
+    if (!(flags & TTG_FLAG_PLAN_VALID)) {
+      merge_cores_kernel<<<(unsigned)(tt.num_tables * tt.p[0] * tt.p[1]), 256, 0, stream>>>(mg.dims, tt.core[0],
+                                                                                          tt.core[1], m);
+      TTG_LAUNCH_CHECK();
+    }
+    float* dcore3[TTG_MAX_CORES] = {dm, dcore[2], dcore[3], nullptr};
+    int rc = sorted_backward(mg.tt3, B, nnz, indices, rowidx, tableidx, d_output, dcore3, TTG_OPTIM_DENSE, 0.f,
+                             0.f, nullptr, (char*)ws + mg.head_bytes, ws_bytes - mg.head_bytes, flags, stream);
+    if (rc != TTG_OK) return rc;
+    TTG_CUDA(cudaMemsetAsync(dcore[0], 0, sizeof(float) * (size_t)tt.num_tables * tt.p[0] * tt.cols[0], stream));
+    TTG_CUDA(cudaMemsetAsync(dcore[1], 0, sizeof(float) * (size_t)tt.num_tables * tt.p[1] * tt.cols[1], stream));
+    merge_bwd0_kernel<<<dim3((unsigned)(tt.num_tables * tt.p[0]), kMergeSplit), 256, 0, stream>>>(
+        mg.dims, dm, tt.core[1], dcore[0]);
+    TTG_LAUNCH_CHECK();
+    merge_bwd1_kernel<<<dim3((unsigned)(tt.num_tables * tt.p[1]), kMergeSplit), 256, 0, stream>>>(
+        mg.dims, dm, tt.core[0], dcore[1]);
+    TTG_LAUNCH_CHECK();
+    if (optim == TTG_OPTIM_DENSE) return TTG_OK;
+    return apply_optimizer(tt, optim, lr, eps, dcore, state, stream);
+  }
   int rc = generic_backward(tt, B, nnz, indices, rowidx, tableidx, d_output, dcore, stream);
   if (rc != TTG_OK || nnz == 0) return rc;  // FBTT/tt_embeddings_cuda.cu:450-452: no update
   return apply_optimizer(tt, optim, lr, eps, dcore, state, stream);
@@ -218,6 +370,9 @@ extern "C" size_t ttg_tt_workspace_bytes(const ttg_shape* shape, int64_t B, int6
   TTDev tt;
   const float* dummy[TTG_MAX_CORES] = {nullptr, nullptr, nullptr, nullptr};
   if (make_ttdev(shape, dummy, &tt) != TTG_OK) return 0;
+  Merged mg;
+  if (!sorted_supported(tt) && merged_form(tt, &mg))      // T = 4 on the T = 3 kernels: M, dM, then their workspace
+    return mg.head_bytes + sorted_workspace_bytes(mg.tt3, B, nnz);
   return sorted_workspace_bytes(tt, B, nnz);
 }
 
@@ -247,6 +402,12 @@ extern "C" int ttg_tt_plan(const ttg_shape* shape, int64_t B, int64_t nnz, const
   if (rc != TTG_OK) return rc;
   TTG_CHECK_ARG(B > 0 && nnz >= 0, "tt_plan: bad B / nnz");
   TTG_CHECK_ARG(nnz == 0 || (indices && rowidx && tableidx), "tt_plan: null index arrays");
+  Merged mg;
+  if (!(flags & TTG_FLAG_FORCE_GENERIC) && !sorted_supported(tt) && merged_form(tt, &mg)) {
+    TTG_CHECK_ARG(workspace && workspace_bytes >= mg.head_bytes, "tt_plan: workspace too small");
+    return sorted_plan(mg.tt3, B, nnz, indices, rowidx, tableidx, (char*)workspace + mg.head_bytes,
+                       workspace_bytes - mg.head_bytes, flags, (cudaStream_t)stream);
+  }
   if ((flags & TTG_FLAG_FORCE_GENERIC) || !sorted_supported(tt)) {
     set_error("tt_plan: the shape-generic kernels have no index plan");
     return TTG_ENOTSUP;

@@ -112,7 +112,11 @@ const char* ttg_profile_name(int32_t id);
  * `output` does not need to be initialised.  (tableidx, rowidx) may come in any order.
  * workspace: ttg_tt_workspace_bytes(shape, B, nnz) bytes, 256-byte aligned; the same
  * (shape, B, nnz) gives the same layout, which is what TTG_FLAG_PLAN_VALID relies on.
- * ---------------------------------------------------------------------------------- */
+ * ----------------------------------------------------------------------------------  *
+ * T = 4 tables whose T = 3 form (the first two cores contracted: p = (p0 p1, p2, p3), q = (q0 q1, q2, q3), ranks
+ * (r2, r3)) has sorted / tensor-core kernels run on those; the contraction and its backward are part of the call,
+ * and ttg_tt_workspace_bytes accounts for the merged core and its gradient.
+ */
 size_t ttg_tt_workspace_bytes(const ttg_shape* shape, int64_t B, int64_t nnz);
 
 int ttg_tt_forward(const ttg_shape* shape, int64_t B, int64_t nnz,

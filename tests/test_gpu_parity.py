@@ -773,3 +773,63 @@ def test_module_prepare_matches_plain_forward(ttg_lib):
     m(idx, off).sum().backward()
     for a, c in zip(g1, m.tt_cores):
         assert float((a - c.grad).abs().max() / c.grad.abs().max()) < 1e-6
+
+
+# --------------------------------------------------------------------------------------------
+# four cores on the three-core kernels (the first two cores merged): run_script.sh:501-541
+# --------------------------------------------------------------------------------------------
+def test_four_core_recipe_runs_on_the_three_core_kernels(ttg_lib):
+    """p = 50,60,60,60 q = 4,2,4,4 ranks 16,16,16 (the reference's final GCN / GAT recipe): forward, dense
+    gradients and both fused updates against the oracle, and against this library's shape-generic kernels."""
+    import _ttg
+    import tt_embeddings as te
+    p, q, r, n_emb = [50, 60, 60, 60], [4, 2, 4, 4], [1, 16, 16, 16, 1], 169343
+    D = 128
+    g = torch.Generator().manual_seed(51)
+    cores_cpu = [torch.randn(1, p[t], r[t] * q[t] * r[t + 1], generator=g) * (0.6 / np.sqrt(r[t])) for t in range(4)]
+    cn = [c.numpy() for c in cores_cpu]
+    rng = np.random.default_rng(7)
+    nnz = 30000
+    idx = rng.integers(0, n_emb, size=nnz).astype(np.int64)
+    idx[:5000] = np.arange(5000)                      # a contiguous stretch, as in a full-graph lookup
+    idx[5] = idx[6] = idx[7]
+    idx[9] = -3                                       # invalid ids contribute nothing
+    row = rng.permutation(nnz).astype(np.int64)
+    valid = idx >= 0
+    tb = torch.zeros(nnz, dtype=torch.int64, device=DEV)
+    dO = ((rng.random(size=(1, nnz, D)) - 0.5) * 0.2).astype(np.float32)
+    want = orc.tt_forward(p, q, r, cn, idx[valid], row[valid], nnz)
+    wd = orc.tt_backward_dense(p, q, r, cn, idx[valid], row[valid], dO)
+    cores = [c.to(DEV) for c in cores_cpu]
+    out = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    gd = te.tt_dense_backward(1000, D, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), cores)
+    for t in range(4):
+        assert rel_err(gd[t].cpu().numpy(), wd[t]) < TOL, "core %d" % t
+    te.EXTRA_FLAGS = _ttg.FLAG_FORCE_GENERIC
+    try:
+        out_g = te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, cores)
+    finally:
+        te.EXTRA_FLAGS = 0
+    assert float((out - out_g).abs().max() / out_g.abs().max()) < TOL
+    cols = [r[t] * q[t] * r[t + 1] for t in range(4)]
+    # fused SGD
+    dev = [c.to(DEV) for c in cores_cpu]
+    te.tt_forward(1000, 1, nnz, D, p, q, r, None, nnz, _t(idx), _t(row), tb, dev)     # leaves its plan behind
+    te.tt_sgd_backward(1000, D, 0.1, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), dev)
+    ws = [c.copy() for c in cn]
+    orc.apply_optimizer(p, cols, "sgd", 0.1, 0.0, ws, None, wd)
+    for t in range(4):
+        assert rel_err(dev[t].cpu().numpy(), ws[t]) < TOL
+    # fused Adagrad, two steps
+    dev = [c.to(DEV) for c in cores_cpu]
+    state = [torch.zeros_like(c) for c in dev]
+    wa = [c.copy() for c in cn]
+    wstate = [np.zeros_like(c) for c in wa]
+    for _ in range(2):
+        te.tt_adagrad_backward(1000, D, 0.05, 1e-10, p, q, r, None, nnz, _t(idx), _t(row), tb, _t(dO), state, dev)
+        gr = orc.tt_backward_dense(p, q, r, wa, idx[valid], row[valid], dO)
+        orc.apply_optimizer(p, cols, "adagrad", 0.05, 1e-10, wa, wstate, gr)
+    for t in range(4):
+        assert rel_err(state[t].cpu().numpy(), wstate[t]) < TOL
+        assert rel_err(dev[t].cpu().numpy(), wa[t]) < TOL
