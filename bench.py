@@ -652,6 +652,18 @@ def run_ours(args, shape):
                 extra[name] = {"error": str(ex)[:300]}
                 if world > 1:
                     raise
+        # BASELINE config 4 (full-graph GCN / GAT at ogbn-arxiv shape) is a single-GPU recipe
+        # (gcn_gat_partition.py): rank 0 runs it alone while the others wait at the end
+        if rank == 0:
+            try:
+                import bench_fullgraph
+                recs = bench_fullgraph.fullgraph_records(dev, epochs=5)
+                extra["fullgraph"] = {r["metric"].split()[1].lower() + "_epoch_ms": r["value"] for r in recs}
+                extra["fullgraph"]["records"] = recs
+            except Exception as ex:
+                extra["fullgraph"] = {"error": str(ex)[:300]}
+        if world > 1:
+            dist.barrier()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -777,6 +789,7 @@ def run_ours(args, shape):
         "sage": extra.get("sage"),
         "config3": extra.get("config3"),
         "papers": extra.get("papers"),
+        "fullgraph": extra.get("fullgraph"),
     }
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

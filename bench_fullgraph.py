@@ -18,20 +18,16 @@ for _p in (ROOT, os.path.join(ROOT, "falcon-ttdforgnns_b200")):
         sys.path.insert(0, _p)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--epochs", type=int, default=10)
-    ap.add_argument("--hidden", type=int, default=256)
-    ap.add_argument("--layers", type=int, default=3)
-    ap.add_argument("--heads", type=int, default=3)
-    ap.add_argument("--models", default="gcn,gat")
-    args = ap.parse_args()
+def fullgraph_records(dev, models=("gcn", "gat"), epochs=10, hidden=256, layers=3, heads=3):
+    """One record per model (a list of dicts): what main() prints, for bench.py's `fullgraph` sub-record."""
+    import types
+    args = types.SimpleNamespace(epochs=epochs, hidden=hidden, layers=layers, heads=heads, models=",".join(models))
     if not torch.cuda.is_available():
         raise RuntimeError("bench_fullgraph.py needs a CUDA device (the product has no CPU path)")
     import gnn_ops
     import sage
     from FBTT.tt_embeddings_ops import OptimType, TTEmbeddingBag
-    dev = torch.device("cuda", 0)
+    records = []
     N, E, C, D = 169343, 2332486, 40, 128
     g = sage.synthetic_graph(N, E, dev, seed=0)
     graph = gnn_ops.Block(g.indptr, g.indices, N, N)
@@ -78,7 +74,7 @@ def main():
 
         ms = timed(epoch, args.epochs)
         ms_tt = timed(tt_only, args.epochs)
-        print(json.dumps({
+        records.append({
             "metric": "full-graph %s epoch milliseconds @ogbn-arxiv shape" % name.upper(), "value": ms,
             "unit": "ms", "higher_is_better": False, "n_gpus": 1, "epochs_timed": args.epochs,
             "tt_forward_backward_ms_incl_dot_loss": ms_tt, "loss_last": float(last["loss"]),
@@ -86,8 +82,21 @@ def main():
             "config": {"workload": "%s, %d layers, hidden %d%s, graph %d nodes / %d directed edges, "
                                    "TT p=55,55,56 q=4,4,8 ranks 16,16, all %d rows per epoch"
                                    % (name.upper(), args.layers, args.hidden,
-                                      ", %d heads" % args.heads if name == "gat" else "", N, E, N)}}),
-              flush=True)
+                                      ", %d heads" % args.heads if name == "gat" else "", N, E, N)}})
+    return records
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--epochs", type=int, default=10)
+    ap.add_argument("--hidden", type=int, default=256)
+    ap.add_argument("--layers", type=int, default=3)
+    ap.add_argument("--heads", type=int, default=3)
+    ap.add_argument("--models", default="gcn,gat")
+    args = ap.parse_args()
+    for rec in fullgraph_records(torch.device("cuda", 0), tuple(args.models.split(",")), args.epochs, args.hidden,
+                                 args.layers, args.heads):
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":
