@@ -3,16 +3,22 @@
 'custom' permutation), without DGL.
 
     new_graph, perm = reorder_graph(graph, "rcmk")               # perm[i] = old id of new node i
-    new_graph, perm = reorder_graph(graph, "grow", k=125)        # METIS-k stand-in (NOT METIS)
+    new_graph, perm = reorder_graph(graph, "metis", k=125)       # multilevel k-way partition, part by part
+    new_graph, perm = recursive_metis_reorder(graph, [50, 60, 60])   # graphloader.py:358-372
+    new_graph, perm = reorder_graph(graph, "grow", k=125)        # label propagation on the device
     new_graph, perm = reorder_graph(graph, "custom", nodes_perm=p)
     labels_new = labels_old[perm]; train_idx_new = inverse(perm)[train_idx_old]
 
 * "rcmk" is exactly what DGL computes: scipy.sparse.csgraph.reverse_cuthill_mckee on the CSR
   adjacency (host, offline preprocessing -- scipy is DGL's own dependency for this).
+* "metis" is a multilevel k-way partitioner on the host (ttg_partition_kway, csrc/kway_host.cu:
+  heavy-edge coarsening, grown initial parts, greedy k-way refinement), where the reference calls
+  libmetis through DGL -- host code there too.  Same scheme and balance bound as METIS, not the
+  same partition (METIS is not in this image; parity with its order is unpinned).  The new order
+  is part by part, old order within a part (stable), as DGL's METIS reorder sorts by part id.
 * "grow" partitions on the device (ttg_partition_grow): k connected parts of at most
   ceil(N / k * slack) nodes grown from k seed nodes drawn uniformly (seeded); nodes no part
-  could take fill the parts with room.  The new order is part by part,
-  old order within a part (stable), like DGL's METIS reorder.
+  could take fill the parts with room.  Much faster than "metis" and a much larger cut.
 * the relabelling itself runs on the device (ttg_permute_csr), bit-exact against
   oracle/reorder_oracle.py.
 """
@@ -105,6 +111,27 @@ def grow_partition(g: CSRGraph, k: int, slack: float = 1.03, seed: int = 0,
     return la
 
 
+def kway_partition(g: CSRGraph, k: int, ubfactor: float = 1.03, seed: int = 0, refine_passes: int = 10,
+                   return_cut: bool = False):
+    """int32 part id of every node from the multilevel k-way partitioner (host code, like the METIS
+    call it stands for: dgl.metis_partition_assignment behind graphloader.py:370,440); parts hold at
+    most ubfactor * ceil(N / k) nodes.  The graph is copied to the host and the labels come back
+    on the graph's device.  With return_cut also the number of edges between different parts."""
+    n, dev = g.num_nodes, g.indptr.device
+    k = int(k)
+    if not 0 < k <= max(n, 1):
+        raise RuntimeError("kway_partition: k=%d out of range" % k)
+    indptr = np.ascontiguousarray(g.indptr.cpu().numpy(), dtype=np.int64)
+    indices = np.ascontiguousarray(g.indices.cpu().numpy()[:int(indptr[-1])], dtype=np.int32)
+    part = np.empty(n, dtype=np.int32)
+    cut = C.c_int64(0)
+    rc = _ttg.lib().ttg_partition_kway(n, indptr.ctypes.data, indices.ctypes.data, k, float(ubfactor), int(seed),
+                                       int(refine_passes), part.ctypes.data, C.byref(cut))
+    _ttg.check(rc, "partition_kway")
+    labels = torch.from_numpy(part).to(dev)
+    return (labels, int(cut.value)) if return_cut else labels
+
+
 def partition_permutation(labels: torch.Tensor) -> torch.Tensor:
     """Part by part, old order inside a part (stable sort by part id)."""
     return torch.sort(labels.long(), stable=True).indices
@@ -124,8 +151,20 @@ def reorder_graph(g: CSRGraph, algo: str, k: Optional[int] = None,
             raise RuntimeError("reorder_graph('grow') needs k")
         perm = partition_permutation(grow_partition(g, k, seed=seed))
     elif algo == "metis":
-        raise RuntimeError("reorder_graph: METIS is not part of this image; use 'grow' (a different, "
-                           "simpler partitioner) or pass a METIS order as nodes_perm with 'custom'")
+        if k is None:
+            raise RuntimeError("reorder_graph('metis') needs k")
+        perm = partition_permutation(kway_partition(g, k, seed=seed))
     else:
         raise RuntimeError("reorder_graph: unknown algorithm %r" % algo)
     return permute_graph(g, perm), perm
+
+
+def recursive_metis_reorder(g: CSRGraph, partition_list, seed: int = 0) -> Tuple[CSRGraph, torch.Tensor]:
+    """graphloader.py:358-372: one 'metis' reorder per entry of partition_list ([50, 60, 60] at
+    :432), each applied to the graph the previous one produced.  Returns the final graph and the
+    composed permutation (perm[i] = id in the ORIGINAL graph of final node i)."""
+    perm = torch.arange(g.num_nodes, dtype=torch.int64, device=g.indptr.device)
+    for level, k in enumerate(partition_list):
+        g, p = reorder_graph(g, "metis", k=int(k), seed=seed + level)
+        perm = perm[p]
+    return g, perm

@@ -393,6 +393,18 @@ int ttg_partition_grow(int64_t num_nodes, const int64_t* indptr, const int32_t* 
                        int32_t cap, const int64_t* seeds, int32_t sweeps, int32_t* labels_a,
                        int32_t* labels_b, int32_t* sizes, int32_t* changed, void* stream);
 
+/* ttg_partition_kway: multilevel k-way partition (heavy-edge coarsening, grown initial parts, greedy
+ * k-way refinement while uncoarsening) -- the role of METIS behind dgl.reorder_graph(g, 'metis',
+ * permute_config={'k': k}) and dgl.metis_partition (graphloader.py:370, 377, 440).  HOST code like
+ * METIS itself: every pointer is host memory, no stream.  The graph is symmetrised first (DGL does the
+ * same), self loops and duplicate edges are allowed.  Every part holds at most
+ * max(ceil(n / k), ubfactor * ceil(n / k)) nodes (ubfactor >= 1, METIS' ufactor; 1.03 is METIS'
+ * default).  Deterministic in `seed`.  refine_passes <= 0 selects 10.  *edge_cut_out (may be NULL):
+ * number of input edges whose two ends lie in different parts.  Not METIS' partition (csrc/kway_host.cu). */
+int ttg_partition_kway(int64_t num_nodes, const int64_t* indptr, const int32_t* indices, int32_t k,
+                       float ubfactor, uint64_t seed, int32_t refine_passes, int32_t* part_out,
+                       int64_t* edge_cut_out);
+
 #ifdef __cplusplus
 }
 #endif

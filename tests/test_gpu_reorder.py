@@ -106,9 +106,52 @@ def test_grow_partition_invariants_and_locality(ttg_lib):
     assert inside(ip, ix) > 5 * inside(indptr, indices)
 
 
+def test_metis_reorder_is_part_by_part_and_local(ttg_lib):
+    """reorder_graph(g, 'metis', k) (graphloader.py:440): the multilevel k-way partition of
+    csrc/kway_host.cu, nodes sorted by part (stable), relabelled on the device."""
+    import reorder
+    rng = np.random.default_rng(5)
+    n, k = 20000, 40
+    indptr, indices, comm = _community_graph(rng, n, k, 8, 0.9)
+    g = _to_graph(indptr, indices)
+    labels, cut = reorder.kway_partition(g, k, seed=1, return_cut=True)
+    lab = labels.cpu().numpy()
+    assert labels.device.type == "cuda" and lab.min() == 0 and lab.max() == k - 1
+    assert np.bincount(lab, minlength=k).max() <= int(1.03 * np.ceil(n / k))
+    dst = np.repeat(np.arange(n), np.diff(indptr))
+    assert cut == int((lab[dst] != lab[indices]).sum())
+    assert cut <= 1.05 * int((comm[dst] != comm[indices]).sum())       # the planted communities, or better
+    g2, perm = reorder.reorder_graph(g, "metis", k=k, seed=1)
+    p = perm.cpu().numpy()
+    assert np.array_equal(np.sort(p), np.arange(n))
+    assert np.all(np.diff(lab[p]) >= 0)                               # part by part ...
+    for c in (0, k // 2, k - 1):                                      # ... old order inside a part
+        assert np.all(np.diff(p[lab[p] == c]) > 0)
+    ip, ix, _ = ro.permute_csr(indptr, indices, p)
+    assert np.array_equal(g2.indptr.cpu().numpy(), ip) and np.array_equal(g2.indices.cpu().numpy(), ix)
+    # far fewer edges leave a part than the device-side label propagation leaves ("grow")
+    grow = reorder.grow_partition(g, k, slack=1.05, seed=1).cpu().numpy()
+    assert cut < 0.8 * int((grow[dst] != grow[indices]).sum())
+
+
+def test_recursive_metis_reorder_composes_the_permutations(ttg_lib):
+    """graphloader.py:358-372: one METIS reorder per level on the graph the previous level left."""
+    import reorder
+    rng = np.random.default_rng(6)
+    n = 6000
+    indptr, indices, _ = _community_graph(rng, n, 12, 6, 0.85)
+    g = _to_graph(indptr, indices)
+    g3, perm = reorder.recursive_metis_reorder(g, [4, 6, 12])
+    p = perm.cpu().numpy()
+    assert np.array_equal(np.sort(p), np.arange(n))
+    ip, ix, _ = ro.permute_csr(indptr, indices, p)
+    assert np.array_equal(g3.indptr.cpu().numpy(), ip) and np.array_equal(g3.indices.cpu().numpy(), ix)
+
+
 def test_unknown_algorithms_fail_loudly(ttg_lib):
     import reorder
     g = _to_graph(np.array([0, 1, 2], dtype=np.int64), np.array([1, 0], dtype=np.int32))
-    for algo in ("metis", "nope"):
-        with pytest.raises(RuntimeError):
-            reorder.reorder_graph(g, algo, k=2)
+    with pytest.raises(RuntimeError):
+        reorder.reorder_graph(g, "nope", k=2)
+    with pytest.raises(RuntimeError):
+        reorder.reorder_graph(g, "metis")          # k is required
