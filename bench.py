@@ -819,7 +819,7 @@ def main():
                          "beside the running step (forked stream / copy stream)")
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the sub-records (GraphSAGE epoch of configs 2 and 3, papers-shape step)")
-    ap.add_argument("--sage-epochs", type=int, default=3, help="timed GraphSAGE epochs per sub-record (the best one counts)")
+    ap.add_argument("--sage-epochs", type=int, default=5, help="timed GraphSAGE epochs per sub-record (the best one counts)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

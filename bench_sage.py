@@ -145,6 +145,9 @@ def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0,
     return {
         "metric": "GraphSAGE epoch seconds @ogbn-products shape", "value": best, "unit": "s",
         "n_gpus": world, "higher_is_better": False, "scaling": "strong", "epochs_timed": secs,
+        "epoch_median_s": sorted(secs)[len(secs) // 2],
+        "epoch_spread": "value = best timed epoch; single epochs take up to 1.6x as long on a shared host "
+                        "(isolated stalls of 50-100 ms in the host's sampling calls, profiles/r2d_sage_variance2.jsonl)",
         "steps_per_epoch_per_rank": steps, "ms_per_step": best / steps * 1e3,
         "first_layer": ("neighbour mean taken by the TT lookup (one EmbeddingBag call, bags = destinations + their "
                         "sampled neighbours); [num_src, 100] is never written" if model.fuse_input else
@@ -205,6 +208,8 @@ def main():
     if rank == 0:
         from bench import ClockSampler
         sampler_factory = lambda: ClockSampler(local)
+        if os.environ.get("TTG_NO_CLOCKS") == "1":     # experiment: does the nvidia-smi poll perturb the epochs?
+            sampler_factory = None
     rec = sage_epoch_record(world, rank, dev, config=args.config, epochs=args.epochs,
                             batch=args.batch or None, flags=args.flags, matmul=args.matmul,
                             nodes=args.nodes, edges=args.edges, train=args.train, hidden=args.hidden,

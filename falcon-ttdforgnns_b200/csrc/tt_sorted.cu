@@ -1474,6 +1474,9 @@ const Entry kEntries[] = {
     TTG_SHAPE(4, 4, 8, 8, 8),
     TTG_SHAPE(8, 4, 4, 16, 16),   // run_script.sh:299,316 (--q-shapes "8,4,4")
     TTG_SHAPE(5, 4, 5, 16, 16),   // run_script.sh:353 (--q-shapes "5,4,5")
+    TTG_SHAPE(5, 5, 4, 16, 16),   // run_script.sh:259-261 (--q-shapes "5,5,4", the tt-ranks sweep at products shape)
+    TTG_SHAPE(5, 5, 4, 8, 8),
+    TTG_SHAPE(5, 5, 4, 32, 32),
 };
 
 const Entry* find_entry(const TTDev& tt) {

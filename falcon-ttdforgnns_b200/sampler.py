@@ -11,6 +11,7 @@ csrc/sampler.cu and pinned by oracle/sampler_oracle.py.
 nodes), `input_nodes` the global ids whose features layer 0 reads.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import List, Sequence, Tuple
 
@@ -86,18 +87,32 @@ class NeighborSampler:
 
 
 def prefetched_minibatches(g: CSRGraph, sampler: NeighborSampler, seeds_of_step, seed_of_step,
-                           num_steps: int):
+                           num_steps: int, depth: int = 2, thread=None):
     """Yields (input_nodes, output_nodes, blocks) for steps 0 .. num_steps - 1, each sampled on a
-    side stream while the consumer's previous step is still running on the current stream -- what
-    DGL's DataLoader does for GPU sampling (use_alternate_streams; sage_dgl_partition.py:141-154
-    takes the default).  The two size read-backs per layer then wait for the sampler's own kernels
-    only, not for the training step queued in front of them, so the host keeps the training stream
-    fed.  `seeds_of_step(s)` -> int64 seed nodes on the device, `seed_of_step(s)` -> draw seed."""
+    side stream while the consumer's earlier steps are still running on the current stream -- what
+    DGL's DataLoader does for GPU sampling (use_alternate_streams + its prefetcher thread;
+    sage_dgl_partition.py:141-154 takes the defaults).  The two size read-backs per layer then wait
+    for the sampler's own kernels only, not for the training step queued in front of them.
+
+    thread=True (or TTG_SAMPLER_THREAD=1; default off): the sampling calls are issued by a worker thread
+    up to `depth` minibatches ahead, so the consumer's thread does nothing but enqueue training steps.
+    Measured on the GraphSAGE epoch at products shape (`profiles/r2d_sage_variance*.jsonl`,
+    `profiles/r2d_sage_thread.txt`): the consumer's wait for a sample drops from 1.0-1.2 ms to 0.18 ms per
+    step, but the epoch is bound by the device (4.15 ms per step against ~3.9 ms of host work) and its best
+    time (0.80 s) and its run-to-run spread (epochs of 0.80 .. 1.3 s on a shared host, with either setting,
+    with or without the clock poll, with either allocator mode) do not change -- hence off by default.
+    The draws are a pure function of (seed, node, position), so the minibatches are the same either way.
+    `seeds_of_step(s)` -> int64 seed nodes on the device, `seed_of_step(s)` -> draw seed."""
     if num_steps <= 0:
         return
-    main = torch.cuda.current_stream(g.indptr.device)
-    side = torch.cuda.Stream(g.indptr.device)
+    dev = g.indptr.device
+    main = torch.cuda.current_stream(dev)
+    # TTG_SAMPLER_PRIORITY=-1: the sampler's short kernels take the next free SMs instead of queueing behind
+    # the training step's grids (measured: no effect on the epoch, `profiles/r2d_sage_priority.txt`)
+    side = torch.cuda.Stream(dev, priority=int(os.environ.get("TTG_SAMPLER_PRIORITY", "0")))
     side.wait_stream(main)            # the graph and the seed tensors are ready
+    if thread is None:
+        thread = os.environ.get("TTG_SAMPLER_THREAD", "0") == "1"
 
     def produce(s):
         with torch.cuda.stream(side):
@@ -106,12 +121,54 @@ def prefetched_minibatches(g: CSRGraph, sampler: NeighborSampler, seeds_of_step,
             ev.record(side)
         return batch, ev
 
-    nxt = produce(0)
-    for s in range(num_steps):
-        (inp, outp, blocks), ev = nxt
+    def hand_over(item):
+        (inp, outp, blocks), ev = item
         main.wait_event(ev)
         for t in [inp, outp] + [x for b in blocks for x in (b.indptr, b.indices)]:
             t.record_stream(main)     # allocated under the side stream, consumed on this one
-        yield inp, outp, blocks       # the consumer enqueues its step ...
-        if s + 1 < num_steps:
-            nxt = produce(s + 1)      # ... and only then does the host wait for the next sample
+        return inp, outp, blocks
+
+    if not thread:
+        nxt = produce(0)
+        for s in range(num_steps):
+            batch = hand_over(nxt)
+            yield batch                   # the consumer enqueues its step ...
+            if s + 1 < num_steps:
+                nxt = produce(s + 1)      # ... and only then does the host wait for the next sample
+        return
+
+    import queue
+    import threading
+    q = queue.Queue(maxsize=max(int(depth), 1))
+    stop = threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def worker():
+        try:
+            torch.cuda.set_device(dev)
+            for s in range(num_steps):
+                if stop.is_set() or not put(produce(s)):
+                    return
+        except BaseException as ex:   # noqa: BLE001 -- handed to the consumer, which re-raises it
+            put(ex)
+
+    t = threading.Thread(target=worker, name="ttg-sampler", daemon=True)
+    t.start()
+    try:
+        for s in range(num_steps):
+            item = q.get()
+            if isinstance(item, BaseException):
+                raise item
+            yield hand_over(item)
+    finally:
+        stop.set()
+        t.join(timeout=10.0)
+        main.wait_stream(side)        # whatever the worker still had in flight is done before its tensors go

@@ -3,6 +3,8 @@ vectors of the reference, and size-independent properties at BASELINE.json's ful
 
 Tolerances: values 1e-5 relative (north star), index / hash / partition results bit-exact.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 import torch
@@ -194,6 +196,11 @@ SHAPES = {
     "cora": ([14, 14, 14], [4, 4, 8], [1, 16, 16, 1], 2708),
     "arxiv_q844": ([55, 55, 56], [8, 4, 4], [1, 16, 16, 1], 169343),     # run_script.sh:299,316
     "products_q545": ([125, 140, 140], [5, 4, 5], [1, 16, 16, 1], 2449029),  # run_script.sh:353
+    # run_script.sh:247-264: the tt-ranks sweep at products shape (--q-shapes "5,5,4"; ranks 64 and up stay on
+    # the any-shape kernels)
+    "products_q554": ([125, 140, 140], [5, 5, 4], [1, 16, 16, 1], 2449029),
+    "products_q554_r8": ([125, 140, 140], [5, 5, 4], [1, 8, 8, 1], 2449029),
+    "products_q554_r32": ([125, 140, 140], [5, 5, 4], [1, 32, 32, 1], 2449029),
 }
 
 
@@ -203,9 +210,14 @@ def _random_cores(p, q, r, n_emb, seed):
             for t in range(3)]
 
 
-@pytest.mark.parametrize("shape", ["products", "arxiv", "papers", "cora", "arxiv_q844", "products_q545"])
+@pytest.mark.parametrize("shape", ["products", "arxiv", "papers", "cora", "arxiv_q844", "products_q545",
+                                   "products_q554", "products_q554_r8", "products_q554_r32"])
 def test_medium_batch_against_oracle(ttg_lib, shape):
+    import _ttg
     import tt_embeddings as te
+    # the shape runs on the plan-based kernels, not on the any-shape fallback (TTG_ENOTSUP = -4 there)
+    assert _ttg.lib().ttg_tt_plan(C.byref(_ttg.make_shape(*SHAPES[shape][:3])), 1, 0, None, None, None, None, 0, 0,
+                                  None) == 0
     p, q, r, n_emb = SHAPES[shape]
     D = int(np.prod(q))
     cores_cpu = _random_cores(p, q, r, n_emb, 11)

@@ -94,9 +94,11 @@ def test_sampled_blocks_drive_sageconv(ttg_lib):
     assert np.abs(got - want).max() < 1e-5
 
 
-def test_prefetched_minibatches_equal_direct_sampling(ttg_lib):
-    """Sampling one step ahead on a side stream yields exactly the batches of the plain loop, and
-    the tensors are safe to consume on the main stream while the next sample is being drawn."""
+@pytest.mark.parametrize("thread", [False, True], ids=["same-thread", "worker-thread"])
+def test_prefetched_minibatches_equal_direct_sampling(ttg_lib, thread):
+    """Sampling ahead on a side stream (from the consumer's thread or from the worker thread) yields
+    exactly the batches of the plain loop, and the tensors are safe to consume on the main stream
+    while the next samples are being drawn."""
     import sage
     import sampler
     g = sage.synthetic_graph(20000, 400000, torch.device(DEV), seed=3)
@@ -106,7 +108,7 @@ def test_prefetched_minibatches_equal_direct_sampling(ttg_lib):
     direct = [smp.sample_blocks(g, seeds_of(s), seed=100 + s) for s in range(6)]
     sums = []
     n = 0
-    for inp, outp, blocks in sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: 100 + s, 6):
+    for inp, outp, blocks in sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: 100 + s, 6, thread=thread):
         torch.cuda._sleep(3_000_000)                  # a slow "training step" on the main stream
         sums.append((inp.sum(), blocks[0].indices.long().sum()))
         d_inp, d_outp, d_blocks = direct[n]
@@ -119,4 +121,28 @@ def test_prefetched_minibatches_equal_direct_sampling(ttg_lib):
     torch.cuda.synchronize()
     for (a, b), (d_inp, _, d_blocks) in zip(sums, direct):
         assert int(a) == int(d_inp.sum()) and int(b) == int(d_blocks[0].indices.long().sum())
-    assert list(sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: s, 0)) == []
+    assert list(sampler.prefetched_minibatches(g, smp, seeds_of, lambda s: s, 0, thread=thread)) == []
+
+
+def test_prefetch_worker_hands_errors_over_and_stops_when_the_consumer_leaves(ttg_lib):
+    import threading
+    import sage
+    import sampler
+    g = sage.synthetic_graph(5000, 60000, torch.device(DEV), seed=4)
+    smp = sampler.NeighborSampler([3, 3])
+    seeds = torch.arange(128, device=DEV)
+
+    def bad_seeds(s):
+        if s == 2:
+            raise ValueError("no seeds for step 2")
+        return seeds
+
+    got = 0
+    with pytest.raises(ValueError, match="step 2"):
+        for _ in sampler.prefetched_minibatches(g, smp, bad_seeds, lambda s: s, 5, thread=True):
+            got += 1
+    assert got == 2
+    it = sampler.prefetched_minibatches(g, smp, lambda s: seeds, lambda s: s, 50, thread=True)
+    next(it)
+    it.close()                                     # the consumer stops early: the worker must not linger
+    assert not [t for t in threading.enumerate() if t.name == "ttg-sampler" and t.is_alive()]
