@@ -224,34 +224,28 @@ class SAGEConv(nn.Module):
                                  and h_dst.stride() == h_src.stride())
         if head and self.in_feats <= self.out_feats and h_src.requires_grad:
             agg, h_dst = aggregate_with_self(block, h_src, mean=True)
-            return self._combine(h_dst, agg)
-        if h_dst is None:
-            h_dst = h_src[:block.num_dst]
-        if self.in_feats > self.out_feats:
-            h_neigh = aggregate(block, self.fc_neigh(h_src), mean=True)
-            out = self.fc_self(h_dst) if self.bias is None else torch.addmm(self.bias, h_dst, self.fc_self.weight.t())
-            return out.add_(h_neigh)
-        return self._combine(h_dst, aggregate(block, h_src, mean=True))
-
-    def _combine(self, h_dst: torch.Tensor, h_mean: torch.Tensor) -> torch.Tensor:
-        """fc_self(h_dst) + fc_neigh(h_mean) + bias with both additions inside the GEMMs (bias as the first
-        product's epilogue, the second product accumulating onto the first): two passes over
-        [num_dst, out_feats] less than Linear + Linear + add + add, per layer and direction."""
-        if h_dst.dim() != 2 or h_mean.dim() != 2:
-            out = self.fc_self(h_dst) + self.fc_neigh(h_mean)
-            return out if self.bias is None else out + self.bias
-        if self.bias is None:
-            out = self.fc_neigh(h_mean)
+            h_neigh = self.fc_neigh(agg)
         else:
-            out = torch.addmm(self.bias, h_mean, self.fc_neigh.weight.t())
-        return out.addmm_(h_dst, self.fc_self.weight.t())
+            if h_dst is None:
+                h_dst = h_src[:block.num_dst]
+            if self.in_feats > self.out_feats:
+                h_neigh = aggregate(block, self.fc_neigh(h_src), mean=True)
+            else:
+                h_neigh = self.fc_neigh(aggregate(block, h_src, mean=True))
+        out = self.fc_self(h_dst) + h_neigh
+        if self.bias is not None:
+            out = out + self.bias
+        return out
 
     def forward_aggregated(self, h_dst: torch.Tensor, h_mean: torch.Tensor) -> torch.Tensor:
         """The same layer when the caller already holds the destination rows and the neighbour mean
         (sage.SAGE with fuse_input: the TT lookup sums the neighbours' rows per destination itself)."""
         if self.in_feats > self.out_feats:
             raise NotImplementedError("forward_aggregated: this layer applies fc_neigh before the aggregation")
-        return self._combine(h_dst, h_mean)
+        out = self.fc_self(h_dst) + self.fc_neigh(h_mean)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
 
 
 class GraphConv(nn.Module):
