@@ -35,6 +35,9 @@ import subprocess
 import sys
 import time
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _cublas_emulation  # noqa: E402,F401 -- before torch: the sub-records' dense GNN layers (see the module)
+
 import numpy as np
 import torch
 
@@ -790,6 +793,9 @@ def run_ours(args, shape):
         "config3": extra.get("config3"),
         "papers": extra.get("papers"),
         "fullgraph": extra.get("fullgraph"),
+        # the sub-records' dense GNN layers (torch library GEMMs, not the TT path): which cuBLAS ran them
+        "library_gemms": ("fp32 on " + _cublas_emulation.WHY) if _cublas_emulation.ACTIVE
+                         else "fp32 on torch's bundled cuBLAS (%s)" % _cublas_emulation.WHY,
     }
     print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

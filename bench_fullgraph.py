@@ -9,6 +9,9 @@ import json
 import os
 import sys
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _cublas_emulation  # noqa: E402,F401 -- before torch (see the module)
+
 import torch
 import torch.nn.functional as F
 

@@ -27,6 +27,11 @@ import json
 import os
 import sys
 
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import _cublas_emulation  # noqa: E402,F401 -- before torch: the dense layers' fp32 GEMMs on cuBLAS 12.9's BF16x9 emulation
+
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -154,7 +159,9 @@ def sage_epoch_record(world, rank, dev, config=2, epochs=2, batch=None, flags=0,
                         "all num_src rows reconstructed, then aggregated (gnn_model.py:199-217)"),
         ("ms_per_step_plain_first_layer" if model.fuse_input else "ms_per_step_fused_first_layer"): ms_other,
         "seeds_per_s": train / best, "data": "synthetic", "dtype": "f32",
-        "dense_layer_matmul": matmul, "loss_last": losses[-1], "clocks": clocks,
+        "dense_layer_matmul": matmul + (" on " + _cublas_emulation.WHY if _cublas_emulation.ACTIVE and matmul == "fp32"
+                                        else ""),
+        "loss_last": losses[-1], "clocks": clocks,
         "replicas_bit_identical": identical, "exchange_failed": failed,
         "per_step_mean": {"layer0_input_nodes": st["input_nodes"] / steps,
                           "layer0_edges": st["edges0"] / steps},
