@@ -7,6 +7,7 @@
     new_graph, perm = recursive_metis_reorder(graph, [50, 60, 60])   # graphloader.py:358-372
     new_graph, perm = reorder_graph(graph, "grow", k=125)        # label propagation on the device
     new_graph, perm = reorder_graph(graph, "custom", nodes_perm=p)
+    new_graph, perm = reorder_graph(graph, "degree")             # graphloader.py:275-285: high in-degree first
     labels_new = labels_old[perm]; train_idx_new = inverse(perm)[train_idx_old]
 
 * "rcmk" is exactly what DGL computes: scipy.sparse.csgraph.reverse_cuthill_mckee on the CSR
@@ -132,6 +133,20 @@ def kway_partition(g: CSRGraph, k: int, ubfactor: float = 1.03, seed: int = 0, r
     return (labels, int(cut.value)) if return_cut else labels
 
 
+def degree_permutation(g: CSRGraph, percentile: float = 80.0) -> torch.Tensor:
+    """graphloader.py:275-285 (custom_reordering, is_degree=True): the nodes whose in-degree reaches the
+    `percentile`-th percentile of all in-degrees first, the others behind them, both in increasing id."""
+    deg = (g.indptr[1:] - g.indptr[:-1]).to(torch.float64)
+    if deg.numel() == 0:
+        return torch.empty(0, dtype=torch.int64, device=g.indptr.device)
+    # np.percentile's default (linear interpolation between the two nearest ranks), on the host in fp64:
+    # torch.quantile refuses more than 16 M elements
+    threshold = float(np.percentile(deg.cpu().numpy(), percentile))
+    high = deg >= threshold
+    ids = torch.arange(deg.numel(), dtype=torch.int64, device=deg.device)
+    return torch.cat([ids[high], ids[~high]])
+
+
 def partition_permutation(labels: torch.Tensor) -> torch.Tensor:
     """Part by part, old order inside a part (stable sort by part id)."""
     return torch.sort(labels.long(), stable=True).indices
@@ -146,6 +161,8 @@ def reorder_graph(g: CSRGraph, algo: str, k: Optional[int] = None,
         perm = nodes_perm.to(g.indptr.device, torch.int64).contiguous()
     elif algo == "rcmk":
         perm = rcmk_permutation(g)
+    elif algo == "degree":
+        perm = degree_permutation(g)
     elif algo == "grow":
         if k is None:
             raise RuntimeError("reorder_graph('grow') needs k")

@@ -155,3 +155,21 @@ def test_unknown_algorithms_fail_loudly(ttg_lib):
         reorder.reorder_graph(g, "nope", k=2)
     with pytest.raises(RuntimeError):
         reorder.reorder_graph(g, "metis")          # k is required
+
+
+def test_degree_reorder_is_the_reference_expression(ttg_lib):
+    """graphloader.py:275-285 restated with numpy: nodes at or above the 80th percentile of the in-degrees first."""
+    import reorder
+    rng = np.random.default_rng(8)
+    n, e = 5000, 60000
+    deg = rng.multinomial(e, rng.dirichlet(np.full(n, 0.3)))
+    indptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    indices = rng.integers(0, n, size=e).astype(np.int32)
+    g = _to_graph(indptr, indices)
+    degrees = np.diff(indptr)
+    high = np.where(degrees >= np.percentile(degrees, 80))[0]
+    want = np.concatenate((high, np.setdiff1d(np.arange(n), high)))
+    g2, perm = reorder.reorder_graph(g, "degree")
+    assert np.array_equal(perm.cpu().numpy(), want)
+    ip, ix, _ = ro.permute_csr(indptr, indices, want)
+    assert np.array_equal(g2.indptr.cpu().numpy(), ip) and np.array_equal(g2.indices.cpu().numpy(), ix)
