@@ -24,7 +24,8 @@
 //   uncoarsen    the partition is projected level by level and improved by greedy k-way refinement
 //                (a vertex moves to the adjacent part with the largest cut gain that has room, ties
 //                towards the lighter part; only vertices next to a move are revisited), preceded
-//                by a balancing sweep when a part is above its bound.
+//                by a balancing sweep when a part is outside its bounds; the bounds are 1.3 x wider on
+//                every level but the finest, which lets split communities flow together.
 //
 // The result is a k-way partition with every part at most ubfactor * ceil(n / k) and at least
 // floor(n / k) / ubfactor vertices (the bounds METIS' ufactor sets) and a cut in METIS' league -- NOT METIS' partition: parity with DGL's
@@ -390,6 +391,7 @@ int64_t weighted_cut(const WGraph& g, const std::vector<int32_t>& part) {
 }
 
 constexpr int kInitialTrials = 8;
+constexpr double kCoarseSlack = 1.3;
 
 }  // namespace
 }  // namespace ttg
@@ -439,6 +441,11 @@ extern "C" int ttg_partition_kway(int64_t num_nodes, const int64_t* indptr, cons
   const int64_t ideal = (num_nodes + k - 1) / k;
   const int64_t maxpw = std::max<int64_t>(ideal, (int64_t)((double)ubfactor * (double)ideal));
   const int64_t minpw = (int64_t)((double)(num_nodes / k) / (double)ubfactor);   // METIS keeps parts above 1/ufactor too
+  // On every level but the finest the parts may be kCoarseSlack times heavier / lighter than the bound: with the
+  // strict bound a community that the grown parts split in halves stays split (each half is balanced against the
+  // other, the part it should join is full); with slack the halves flow together and the parts that lose them
+  // take their own strays back, so the bound is met again by the time the finest level enforces it.
+  const int64_t maxpw_coarse = (int64_t)(maxpw * kCoarseSlack), minpw_coarse = (int64_t)(minpw / kCoarseSlack);
   // a few grown partitions of the coarsest graph, each refined there; the one with the smallest cut goes on
   std::vector<int32_t> part;
   {
@@ -447,7 +454,7 @@ extern "C" int ttg_partition_kway(int64_t num_nodes, const int64_t* indptr, cons
     for (int trial = 0; trial < kInitialTrials; ++trial) {
       std::vector<int32_t> cand;
       initial_partition(cg, k, rng, cand);
-      Refiner r(cg, k, maxpw, minpw, cand);
+      Refiner r(cg, k, maxpw_coarse, minpw_coarse, cand);
       r.balance(rng);
       r.refine(refine_passes, rng);
       r.balance(rng);
@@ -459,7 +466,7 @@ extern "C" int ttg_partition_kway(int64_t num_nodes, const int64_t* indptr, cons
     }
   }
   for (size_t lv = levels.size(); lv-- > 0;) {
-    Refiner r(levels[lv], k, maxpw, minpw, part);
+    Refiner r(levels[lv], k, lv > 0 ? maxpw_coarse : maxpw, lv > 0 ? minpw_coarse : minpw, part);
     r.balance(rng);
     r.refine(refine_passes, rng);
     r.balance(rng);
