@@ -164,3 +164,13 @@ def test_bad_arguments_fail_loudly(ttg_lib):
     dec = indptr.copy()
     dec[5] = dec[4] - 1
     assert call(dec, indices, 2) != 0
+
+
+def test_partition_does_not_depend_on_the_number_of_host_threads(ttg_lib, monkeypatch):
+    rng = np.random.default_rng(3)
+    indptr, indices, _, _ = _planted(rng, 40000, 20, 10, 3)
+    parts = []
+    for threads in ("1", "4"):
+        monkeypatch.setenv("TTG_KWAY_THREADS", threads)
+        parts.append(_kway(ttg_lib, indptr, indices, 20, seed=2))
+    assert np.array_equal(parts[0][0], parts[1][0]) and parts[0][1] == parts[1][1]
